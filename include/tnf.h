@@ -1,0 +1,179 @@
+/*
+ * tnf.h -- C ABI of the B200-native torch_nf bijector-chain hot path.
+ *
+ * The reference (srbittner/torch_nf) is pure Python: it has no FFI layer, its
+ * "plugin" boundary is the duck-typed Bijector protocol
+ *     bijector(z, params) -> (z, log_det)            torch_nf/bijectors.py:30-63
+ * called from NormFlow.forward / NormFlow.inverse_and_log_det
+ *                                    torch_nf/density_estimator.py:375-387,395-405.
+ * Each entry point below is what a binding for one of those protocol methods
+ * calls; the reference method it replaces is cited on the declaration.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by
+ *     the caller; the library never allocates, frees or keeps device memory.
+ *   - `z` tensors are row-major contiguous (M, N, D); `rows` = M*N.
+ *   - `params` is the reference's flat parameter matrix: the pointer addresses
+ *     the FIRST parameter of this bijector inside row 0 and `param_row_stride`
+ *     is the element distance between rows (so a column slice
+ *     params[:, idx:idx+n] of a wider matrix is passed without a copy;
+ *     trailing extra columns are legal, tests/test_bijectors.py:89-93).
+ *     `param_row_stride == 0` broadcasts row 0 to every m (shared weights).
+ *   - `dtype`: TNF_F32 or TNF_F64, the element type of z / params / log_det.
+ *   - `accum`: TNF_LD_WRITE stores the log-det, TNF_LD_ADD / TNF_LD_SUB
+ *     accumulate it into a running per-sample buffer (log_q_z -= log_det,
+ *     density_estimator.py:387; sum_log_det += log_det, :405).
+ *   - work is enqueued on `stream` (a cudaStream_t); no implicit sync.
+ *   - return 0 on success, >0 a cudaError_t from the launch, <0 an argument
+ *     error; tnf_last_error() gives a thread-local message.
+ */
+#ifndef TNF_H_
+#define TNF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNF_ABI_VERSION 1
+
+enum { TNF_F32 = 0, TNF_F64 = 1 };
+enum { TNF_FORWARD = 0, TNF_INVERSE = 1 };
+enum { TNF_LD_WRITE = 0, TNF_LD_ADD = 1, TNF_LD_SUB = -1 };
+enum { TNF_ERR_ARG = -1, TNF_ERR_UNSUPPORTED = -2, TNF_ERR_ALIGN = -3 };
+
+typedef void* tnf_stream_t; /* cudaStream_t */
+
+int tnf_abi_version(void);
+const char* tnf_last_error(void);
+/* number of kernel launches issued through this library by the calling
+ * process since load (bench.py's gpu_launches counter). */
+int64_t tnf_launch_count(void);
+
+/* ---- RealNVP coupling layer, exact-precision CUDA-core path -------------
+ * replaces RealNVP.forward_and_log_det (bijectors.py:145-181) and
+ * RealNVP.inverse_and_log_det (:183-206) incl. _t_s_layer (:208-242).
+ * Any D >= 2 (odd D splits as :157-165), 1 <= L <= 5, 1 <= U <= 1000.
+ * log_det is (M, N). z_out may alias z_in. */
+int tnf_coupling(const void* z_in, void* z_out, void* log_det, const void* params,
+                 int64_t param_row_stride, int64_t M, int64_t N, int D, int U, int L,
+                 int transform_upper, int direction, int accum, int dtype, tnf_stream_t stream);
+
+/* backward of tnf_coupling.  g_z_out (M,N,D) and g_log_det (M,N) (either may
+ * be NULL = zero) are the gradients of the outputs; g_log_det is the gradient
+ * w.r.t. the PLAIN log_det (sum s).  g_z_in (M,N,D) is written.  g_params
+ * (row stride g_param_row_stride, 0 = one shared row) is ACCUMULATED into, so
+ * the caller zero-fills it first.  Activations are recomputed from z_in. */
+int tnf_coupling_bwd(const void* z_in, const void* params, int64_t param_row_stride,
+                     const void* g_z_out, const void* g_log_det, void* g_z_in, void* g_params,
+                     int64_t g_param_row_stride, int64_t M, int64_t N, int D, int U, int L,
+                     int transform_upper, int direction, int dtype, tnf_stream_t stream);
+
+/* ---- RealNVP coupling layer, tcgen05 tensor-core path (bf16 conditioner) --
+ * Same math as tnf_coupling for shared weights (regime A: one parameter row),
+ * fp32 z / log_det, conditioner GEMMs in bf16 on tcgen05 with fp32 TMEM
+ * accumulation, affine transform and log-det in fp32.
+ * Weights are repacked once per parameter update by tnf_tc_pack (fp32 flat
+ * params -> bf16 UMMA operand images + fp32 biases).
+ * pre_scale/pre_shift (D floats each, or NULL): per-column affine
+ * z <- z*pre_scale + pre_shift applied on load, which is how BatchNorm /
+ * Affine neighbours (bijectors.py:292,399,423-424) are folded in.
+ * col_stats (or NULL): [2*D] doubles, accumulates sum and sum of squares of
+ * the OUTPUT columns (the next BatchNorm's batch statistics, :401-410). */
+int tnf_tc_supported(int D, int U, int L);
+size_t tnf_tc_packed_bytes(int D, int U, int L);
+int tnf_tc_pack(const float* params, void* packed, int D, int U, int L, int transform_upper,
+                tnf_stream_t stream);
+int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void* packed,
+                    int64_t rows, int D, int U, int L, int transform_upper, int direction,
+                    int accum, const float* pre_scale, const float* pre_shift,
+                    double* col_stats, tnf_stream_t stream);
+
+/* ---- Affine: replaces Affine.forward_and_log_det / inverse_and_log_det
+ * (bijectors.py:277-315).  params row = [alpha(D), shift(D)].
+ * log_det (M) = sum alpha, written when non-NULL. */
+int tnf_affine(const void* z_in, void* z_out, void* log_det, const void* params,
+               int64_t param_row_stride, int64_t M, int64_t N, int D, int direction, int dtype,
+               tnf_stream_t stream);
+int tnf_affine_bwd(const void* z_in, const void* params, int64_t param_row_stride,
+                   const void* g_z_out, const void* g_log_det, void* g_z_in, void* g_params,
+                   int64_t g_param_row_stride, int64_t M, int64_t N, int D, int direction,
+                   int dtype, tnf_stream_t stream);
+
+/* ---- BatchNorm: replaces BatchNorm.forward_and_log_det / inverse_and_log_det
+ * (bijectors.py:389-426).
+ * tnf_colstats: deterministic two-stage reduction of per-column sum and sum
+ *   of squares over `rows` rows -> sums[2*D+1] doubles: [sum | sumsq | rows]
+ *   (this rank's partial; a data-parallel caller all-reduces the whole buffer,
+ *   so the global row count travels with the sums and no host sync is needed).
+ *   `workspace` must hold tnf_colstats_workspace_bytes(D) bytes.
+ * tnf_bn_finalize: mean, alpha = sqrt(biased var + eps), log_det = -sum log alpha
+ *   (all in `dtype`) from the (reduced) sums; the row count is sums[2*D].
+ * tnf_bn_apply: TNF_FORWARD (z-mean)/alpha ; TNF_INVERSE z*alpha+mean. */
+size_t tnf_colstats_workspace_bytes(int D);
+int tnf_colstats(const void* z, int64_t rows, int D, double* sums, void* workspace, int dtype,
+                 tnf_stream_t stream);
+int tnf_bn_finalize(const double* sums, int D, double eps, void* mean, void* alpha,
+                    void* log_det, int dtype, tnf_stream_t stream);
+int tnf_bn_apply(const void* z_in, void* z_out, const void* mean, const void* alpha,
+                 int64_t rows, int D, int direction, int dtype, tnf_stream_t stream);
+/* backward of batch-statistics normalisation y=(z-mean)/alpha, incl. the
+ * log-det term: g_z = (g_y - mean_r(g_y) - y*mean_r(g_y*y))/alpha - g_ld*(y/alpha)/R,
+ * given the (all-reduced) column sums gsums = [sum g_y (D), sum g_y*y (D), -]
+ * and `count` = pointer to the global row count R (device double). */
+int tnf_bn_bwd_sums(const void* g_y, const void* y, int64_t rows, int D, double* gsums,
+                    void* workspace, int dtype, tnf_stream_t stream);
+int tnf_bn_bwd_apply(const void* g_y, const void* y, const void* alpha, const double* gsums,
+                     const void* g_log_det, const double* count, void* g_z, int64_t rows, int D,
+                     int dtype, tnf_stream_t stream);
+
+/* ---- ToInterval: replaces ToInterval.forward_and_log_det /
+ * inverse_and_log_det (bijectors.py:509-557).  consts = 6*D floats
+ * [tanh_flg | softplus_flg | tanh_m | tanh_c | softplus_m | softplus_c]
+ * (the float32 constants the reference builds at :475-480). log_det (rows). */
+int tnf_tointerval(const void* z_in, void* z_out, void* log_det, const float* consts,
+                   int64_t rows, int D, int direction, int accum, int dtype, tnf_stream_t stream);
+int tnf_tointerval_bwd(const void* z_in, const float* consts, const void* g_z_out,
+                       const void* g_log_det, void* g_z_in, int64_t rows, int D, int direction,
+                       int dtype, tnf_stream_t stream);
+
+/* ---- ToSimplex: replaces ToSimplex.forward_and_log_det (bijectors.py:574-591).
+ * z_in (rows, D_in) -> z_out (rows, D_in+1); D_attr is the bijector's D used in
+ * the log-det.  No inverse exists in the reference. */
+int tnf_tosimplex(const void* z_in, void* z_out, void* log_det, int64_t rows, int D_in,
+                  int D_attr, int accum, int dtype, tnf_stream_t stream);
+int tnf_tosimplex_bwd(const void* z_in, const void* g_z_out, const void* g_log_det, void* g_z_in,
+                      int64_t rows, int D_in, int D_attr, int dtype, tnf_stream_t stream);
+
+/* ---- base density of NormFlow
+ * Log-dets come in two shapes: per sample (M,N) from
+ * RealNVP / ToInterval / ToSimplex, and per parameter row from Affine (M,1)
+ * and BatchNorm (scalar).  The chain keeps a per-sample accumulator `sub`
+ * and a per-row accumulator `scal`; `scal_div` maps a sample row r to its
+ * entry scal[r / scal_div] (N for per-m weights, rows for shared weights).
+ * tnf_accum_bcast: dst[i] += src[i / div] for i < n_dst.
+ * tnf_base_logprob: out(rows) = -sum(z^2)/2 - D*log(sqrt(2*pi)) - sub(rows) - scal
+ *   (density_estimator.py:413-416; `sub`, `scal` may be NULL).
+ * tnf_base_sample: omega ~ N(0,1) by Philox4x32-10 + Box-Muller into z (fp32)
+ *   and the float64 base log-density of the same draw (:366-372).
+ * tnf_base_logq: log_q(rows, f64) = -sum(omega^2)/2 - D*log(sqrt(2*pi)) for
+ *   an injected fp32 omega (parity runs).
+ * tnf_finish_logq: log_q(rows, f64) -= ld_acc(rows, dtype) + scal[r / scal_div]. */
+int tnf_accum_bcast(void* dst, const void* src, int64_t n_dst, int64_t div, int dtype,
+                    tnf_stream_t stream);
+int tnf_base_logprob(const void* z, const void* sub, const void* scal, int64_t scal_div, void* out,
+                     int64_t rows, int D, int dtype, tnf_stream_t stream);
+int tnf_base_logprob_bwd(const void* z, const void* g_out, void* g_z, int64_t rows, int D,
+                         int dtype, tnf_stream_t stream);
+int tnf_base_sample(float* z, double* log_q, int64_t rows, int D, uint64_t seed,
+                    uint64_t offset, tnf_stream_t stream);
+int tnf_base_logq(const float* omega, double* log_q, int64_t rows, int D, tnf_stream_t stream);
+int tnf_finish_logq(double* log_q, const void* ld_acc, const void* scal, int64_t scal_div,
+                    int64_t rows, int dtype, tnf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNF_H_ */

@@ -1,0 +1,68 @@
+"""Build the C-ABI CUDA library ``torch_nf_b200/_C.so`` in-tree with nvcc for sm_100a.
+
+The library exports exactly the ``extern "C"`` entry points declared in
+``include/tnf.h``; it has no torch or Python dependency (plain pointers and
+sizes), so it is loaded with ``ctypes``.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "_C.so")
+STAMP = os.path.join(HERE, "_C.so.stamp")
+SOURCES = ["elementwise.cu", "coupling_generic.cu", "coupling_tc.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "--cudart", "static",
+]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def source_digest():
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    files.append(os.path.join(os.path.dirname(HERE), "include", "tnf.h"))
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_current():
+    if not (os.path.exists(LIB) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as fh:
+        return fh.read().strip() == source_digest()
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source into one shared library. Returns its path."""
+    if not force and is_current():
+        return LIB
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build torch_nf_b200/_C.so")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    with open(STAMP, "w") as fh:
+        fh.write(source_digest())
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

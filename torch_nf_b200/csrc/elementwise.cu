@@ -1,0 +1,830 @@
+// Elementwise / row-reduction bijectors of the torch_nf chain (sm_100a).
+// HBM-bound kernels: coalesced accesses, grid sized in multiples of the SM count.
+//   Affine      reference torch_nf/bijectors.py:277-315
+//   BatchNorm   reference torch_nf/bijectors.py:389-426
+//   ToInterval  reference torch_nf/bijectors.py:509-557
+//   ToSimplex   reference torch_nf/bijectors.py:574-591
+//   base density / sampling  reference torch_nf/density_estimator.py:366-372,413-416
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace tnf {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+static inline int grid_for(int64_t work_items, int per_block, int waves = 8) {
+  int64_t need = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)num_sms() * waves;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// rounding-explicit helpers: the reference evaluates a*b and +c as two torch
+// ops (two roundings); keep that so closed-form tests hold to the last ulp.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+// exp rounded from a double evaluation: matches a correctly-rounded host exp
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ double exp_cr(double x) { return exp(x); }
+
+// ---------------------------------------------------------------- Affine
+template <typename T>
+__global__ void affine_kernel(const T* __restrict__ z_in, T* __restrict__ z_out, T* __restrict__ log_det,
+                              const T* __restrict__ params, int64_t pstride, int64_t M, int64_t N, int D,
+                              int inverse, int chunks_per_m, int64_t rows_per_chunk) {
+  extern __shared__ unsigned char smem_raw[];
+  T* scale = reinterpret_cast<T*>(smem_raw);
+  T* shift = scale + D;
+  for (int64_t blk = blockIdx.x; blk < M * chunks_per_m; blk += gridDim.x) {
+    int64_t m = blk / chunks_per_m;
+    int chunk = (int)(blk % chunks_per_m);
+    const T* p = params + m * pstride;
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      scale[d] = exp_cr(p[d]);
+      shift[d] = p[D + d];
+    }
+    __syncthreads();
+    if (chunk == 0 && log_det != nullptr && threadIdx.x == 0) {
+      T s = T(0);
+      for (int d = 0; d < D; ++d) s += p[d];
+      log_det[m] = s;
+    }
+    int64_t r0 = (int64_t)chunk * rows_per_chunk;
+    int64_t r1 = r0 + rows_per_chunk < N ? r0 + rows_per_chunk : N;
+    const T* zi = z_in + (m * N + r0) * D;
+    T* zo = z_out + (m * N + r0) * D;
+    int64_t n_el = (r1 - r0) * D;
+    for (int64_t e = threadIdx.x; e < n_el; e += blockDim.x) {
+      int d = (int)(e % D);
+      T v = zi[e];
+      zo[e] = inverse ? (v - shift[d]) / scale[d] : add_rn(mul_rn(scale[d], v), shift[d]);
+    }
+  }
+}
+
+// regime B (few samples per parameter row): one thread per element
+template <typename T>
+__global__ void affine_flat_kernel(const T* __restrict__ z_in, T* __restrict__ z_out, T* __restrict__ log_det,
+                                   const T* __restrict__ params, int64_t pstride, int64_t M, int64_t N, int D,
+                                   int inverse) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t n_el = M * N * D;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += stride) {
+    int d = (int)(e % D);
+    int64_t m = e / ((int64_t)N * D);
+    const T* p = params + m * pstride;
+    T sc = exp_cr(p[d]), sh = p[D + d];
+    T v = z_in[e];
+    z_out[e] = inverse ? (v - sh) / sc : add_rn(mul_rn(sc, v), sh);
+    if (log_det != nullptr && d == 0 && (e / D) % N == 0) {
+      T s = T(0);
+      for (int k = 0; k < D; ++k) s += p[k];
+      log_det[m] = s;
+    }
+  }
+}
+
+// grad: forward  y = e^a z + b : g_z = g_y e^a ; g_a = sum_n g_y z e^a + g_ld ; g_b = sum_n g_y
+//       inverse  y = (z-b)/e^a : g_z = g_y/e^a ; g_a = -sum_n g_y y   + g_ld ; g_b = -sum_n g_y/e^a
+// one block per m; threads own columns (deterministic per-column sums over n).
+template <typename T>
+__global__ void affine_bwd_kernel(const T* __restrict__ z_in, const T* __restrict__ params, int64_t pstride,
+                                  const T* __restrict__ g_y, const T* __restrict__ g_ld, T* __restrict__ g_z,
+                                  T* __restrict__ g_params, int64_t gstride, int64_t M, int64_t N, int D,
+                                  int inverse) {
+  extern __shared__ unsigned char smem_raw[];
+  double* red = reinterpret_cast<double*>(smem_raw);  // [2][blockDim.x]
+  const int lanes_per_col = blockDim.x / D > 0 ? blockDim.x / D : 1;
+  for (int64_t m = blockIdx.x; m < M; m += gridDim.x) {
+    const T* p = params + m * pstride;
+    T gl = g_ld ? g_ld[m] : T(0);
+    for (int d0 = 0; d0 < D; d0 += blockDim.x) {
+      // columns d0 .. d0+blockDim.x-1 ; when D < blockDim.x several lanes share a column
+      int t = threadIdx.x;
+      int d = d0 + (D < (int)blockDim.x ? t % D : t);
+      int sub = D < (int)blockDim.x ? t / D : 0;
+      bool active = d < D && sub < lanes_per_col;
+      double ga = 0.0, gb = 0.0;
+      if (active) {
+        T sc = exp_cr(p[d]);
+        T sh = p[D + d];
+        for (int64_t n = sub; n < N; n += lanes_per_col) {
+          int64_t e = (m * N + n) * D + d;
+          T gy = g_y ? g_y[e] : T(0);
+          T z = z_in[e];
+          if (!inverse) {
+            g_z[e] = gy * sc;
+            ga += (double)(gy * z * sc);
+            gb += (double)gy;
+          } else {
+            T y = (z - sh) / sc;
+            T gz = gy / sc;
+            g_z[e] = gz;
+            ga -= (double)(gy * y);
+            gb -= (double)gz;
+          }
+        }
+      }
+      __syncthreads();
+      red[t] = ga;
+      red[blockDim.x + t] = gb;
+      __syncthreads();
+      if (active && sub == 0) {
+        double sa = 0.0, sb = 0.0;
+        for (int k = 0; k < lanes_per_col; ++k) {
+          int src = D < (int)blockDim.x ? k * D + (d - d0) : t;
+          sa += red[src];
+          sb += red[blockDim.x + src];
+        }
+        T* gp = g_params + (gstride ? m * gstride : 0);
+        if (gstride) {
+          gp[d] += (T)(sa + (double)gl);
+          gp[D + d] += (T)sb;
+        } else {  // one shared row: every m accumulates into it
+          atomicAdd(&gp[d], (T)(sa + (double)gl));
+          atomicAdd(&gp[D + d], (T)sb);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------- column statistics
+constexpr int kStatThreads = 256;
+constexpr int kStatMaxBlocks = 1184;  // 8 x 148
+
+template <typename T>
+__global__ void colstats_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t rows, int D,
+                                double* __restrict__ partial /* [grid][2][D] */) {
+  // a: values whose column sums are wanted; if b != nullptr the second sum is sum(a*b)
+  // instead of sum(a*a)  (BatchNorm backward needs sum g, sum g*y).
+  __shared__ double red[2][kStatThreads];
+  const int nt = blockDim.x;
+  double* out = partial + (int64_t)blockIdx.x * 2 * D;
+  int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+  int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  if (D <= nt) {
+    const int lanes = nt / D;  // threads sharing one column
+    const int t = threadIdx.x;
+    const int d = t % D, sub = t / D;
+    double s1 = 0.0, s2 = 0.0;
+    if (sub < lanes) {
+      for (int64_t r = r0 + sub; r < r1; r += lanes) {
+        double v = (double)a[r * D + d];
+        double w = b ? (double)b[r * D + d] : v;
+        s1 += v;
+        s2 += v * w;
+      }
+    }
+    red[0][t] = s1;
+    red[1][t] = s2;
+    __syncthreads();
+    if (t < D) {
+      double t1 = 0.0, t2 = 0.0;
+      for (int k = 0; k < lanes; ++k) {
+        t1 += red[0][k * D + t];
+        t2 += red[1][k * D + t];
+      }
+      out[t] = t1;
+      out[D + t] = t2;
+    }
+  } else {
+    for (int d = threadIdx.x; d < D; d += nt) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int64_t r = r0; r < r1; ++r) {
+        double v = (double)a[r * D + d];
+        double w = b ? (double)b[r * D + d] : v;
+        s1 += v;
+        s2 += v * w;
+      }
+      out[d] = s1;
+      out[D + d] = s2;
+    }
+  }
+}
+
+__global__ void colstats_reduce_kernel(const double* __restrict__ partial, int nblocks, int D,
+                                       double* __restrict__ sums, double rows) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 2 * D) sums[i] = rows;
+  if (i >= 2 * D) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * 2 * D + i];
+  sums[i] = s;
+}
+
+template <typename T>
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int D, double eps,
+                                   T* __restrict__ mean, T* __restrict__ alpha, T* __restrict__ log_det) {
+  __shared__ double red[256];
+  const double n = sums[2 * D];
+  double acc = 0.0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double mu = sums[d] / n;
+    double var = sums[D + d] / n - mu * mu;
+    if (var < 0.0) var = 0.0;
+    T al = (T)sqrt(var + eps);
+    mean[d] = (T)mu;
+    alpha[d] = al;
+    acc += (double)t_log<T>(al);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) log_det[0] = (T)(-red[0]);
+}
+
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ z_in, T* __restrict__ z_out, const T* __restrict__ mean,
+                                const T* __restrict__ alpha, int64_t n_el, int D, int inverse) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += stride) {
+    int d = (int)(e % D);
+    T v = z_in[e];
+    z_out[e] = inverse ? add_rn(mul_rn(v, alpha[d]), mean[d]) : (v - mean[d]) / alpha[d];
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ g_y, const T* __restrict__ y, const T* __restrict__ alpha,
+                                    const double* __restrict__ gsums, const T* __restrict__ g_ld,
+                                    const double* __restrict__ count, T* __restrict__ g_z, int64_t n_el, int D) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const double n = count[0];
+  T gl = g_ld ? g_ld[0] : T(0);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += stride) {
+    int d = (int)(e % D);
+    T mg = (T)(gsums[d] / n), mgy = (T)(gsums[D + d] / n);
+    T yy = y[e];
+    T gy = g_y ? g_y[e] : T(0);
+    // log_det = -sum_d log alpha_d  =>  d log_det / d z = -(y/alpha)/n
+    g_z[e] = (gy - mg - yy * mgy) / alpha[d] - gl * (yy / alpha[d]) / (T)n;
+  }
+}
+
+// ---------------------------------------------------------------- row-group kernels
+// G lanes cooperate on one row (G = 1, 8 or 32); rows are distributed grid-stride.
+template <typename T> __device__ __forceinline__ T softplus_t(T x) {  // F.softplus(beta=1, threshold=20)
+  return x > T(20) ? x : t_log1p<T>(t_exp<T>(x));
+}
+template <typename T> __device__ __forceinline__ T logsigmoid_t(T x) {
+  T mn = x < T(0) ? x : T(0);
+  return mn - t_log1p<T>(t_exp<T>(-t_abs<T>(x)));
+}
+template <typename T> __device__ __forceinline__ T sigmoid_t(T x) { return T(1) / (T(1) + t_exp<T>(-x)); }
+
+template <typename T, int G> __device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T> struct TiEps { static __device__ __forceinline__ T v() { return (T)1e-12; } };
+
+template <typename T, int G>
+__global__ void tointerval_kernel(const T* __restrict__ z_in, T* __restrict__ z_out, T* __restrict__ log_det,
+                                  const float* __restrict__ c, int64_t rows, int D, int inverse, int accum) {
+  const float *tanh_flg = c, *sp_flg = c + D, *tanh_m = c + 2 * D, *tanh_c = c + 3 * D, *sp_m = c + 4 * D,
+              *sp_c = c + 5 * D;
+  const T eps = TiEps<T>::v();
+  int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  int lane = threadIdx.x % G;
+  int64_t ngroups = (int64_t)gridDim.x * blockDim.x / G;
+  int64_t rows_pad = (rows + ngroups - 1) / ngroups * ngroups;  // keep shuffles convergent
+  for (int64_t r = gid; r < rows_pad; r += ngroups) {
+    T ld = T(0);
+    if (r < rows) {
+      for (int d = lane; d < D; d += G) {
+        T z = z_in[r * D + d];
+        if (!inverse) {
+          if (tanh_flg[d] != 0.f) {
+            T th = t_tanh<T>(z);
+            ld += t_log<T>((T)tanh_m[d]) + t_log<T>(T(1) - th * th + eps);
+            z = add_rn(mul_rn((T)tanh_m[d], th), (T)tanh_c[d]);
+          } else if (sp_flg[d] != 0.f) {
+            ld += logsigmoid_t<T>(z);
+            z = add_rn(mul_rn((T)sp_m[d], softplus_t<T>(z)), (T)sp_c[d]);
+          }
+        } else {
+          if (sp_flg[d] != 0.f) {
+            z = t_log<T>(t_exp<T>((z - (T)sp_c[d]) / (T)sp_m[d]) - T(1) + eps);
+            ld += logsigmoid_t<T>(z);
+          } else if (tanh_flg[d] != 0.f) {
+            T x = (z - (T)tanh_c[d]) / (T)tanh_m[d];
+            z = T(0.5) * (t_log<T>(T(1) + x + eps) - t_log<T>(T(1) - x + eps));
+            T th = t_tanh<T>(z);
+            ld += t_log<T>((T)tanh_m[d]) + t_log<T>(T(1) - th * th + eps);
+          }
+        }
+        z_out[r * D + d] = z;
+      }
+    }
+    ld = group_sum<T, G>(ld);
+    if (r < rows && lane == 0) {
+      if (accum == TNF_LD_WRITE) log_det[r] = ld;
+      else if (accum == TNF_LD_ADD) log_det[r] += ld;
+      else log_det[r] -= ld;
+    }
+  }
+}
+
+// backward w.r.t. the INPUT of the direction that was run.
+//  forward : y = f(z),  ld = l(z)         g_z = g_y f'(z) + g_ld l'(z)
+//  inverse : x = f^-1(z), ld = l(x)       g_z = (g_x + g_ld l'(x)) / f'(x)
+template <typename T, int G>
+__global__ void tointerval_bwd_kernel(const T* __restrict__ z_in, const float* __restrict__ c,
+                                      const T* __restrict__ g_out, const T* __restrict__ g_ld, T* __restrict__ g_in,
+                                      int64_t rows, int D, int inverse) {
+  const float *tanh_flg = c, *sp_flg = c + D, *tanh_m = c + 2 * D, *tanh_c = c + 3 * D, *sp_m = c + 4 * D,
+              *sp_c = c + 5 * D;
+  const T eps = TiEps<T>::v();
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t n_el = rows * D;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += stride) {
+    int d = (int)(e % D);
+    int64_t r = e / D;
+    T z = z_in[e];
+    T go = g_out ? g_out[e] : T(0);
+    T gl = g_ld ? g_ld[r] : T(0);
+    T g = go;
+    if (tanh_flg[d] != 0.f) {
+      T x = z;
+      if (inverse) {
+        T u = (z - (T)tanh_c[d]) / (T)tanh_m[d];
+        x = T(0.5) * (t_log<T>(T(1) + u + eps) - t_log<T>(T(1) - u + eps));
+      }
+      T th = t_tanh<T>(x);
+      T sech2 = T(1) - th * th;
+      T fp = (T)tanh_m[d] * sech2;                       // f'(x)
+      T lp = -T(2) * th * sech2 / (sech2 + eps);         // l'(x)
+      g = inverse ? (go + gl * lp) / fp : go * fp + gl * lp;
+    } else if (sp_flg[d] != 0.f) {
+      T x = z;
+      if (inverse) x = t_log<T>(t_exp<T>((z - (T)sp_c[d]) / (T)sp_m[d]) - T(1) + eps);
+      T sg = sigmoid_t<T>(x);
+      T fp = (T)sp_m[d] * sg;
+      T lp = T(1) - sg;
+      g = inverse ? (go + gl * lp) / fp : go * fp + gl * lp;
+    }
+    g_in[e] = g;
+  }
+}
+
+template <typename T, int G>
+__global__ void tosimplex_kernel(const T* __restrict__ z_in, T* __restrict__ z_out, T* __restrict__ log_det,
+                                 int64_t rows, int Din, int Dattr, int accum) {
+  int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  int lane = threadIdx.x % G;
+  int64_t ngroups = (int64_t)gridDim.x * blockDim.x / G;
+  int64_t rows_pad = (rows + ngroups - 1) / ngroups * ngroups;
+  for (int64_t r = gid; r < rows_pad; r += ngroups) {
+    T se = T(0), sz = T(0);
+    if (r < rows)
+      for (int d = lane; d < Din; d += G) {
+        T z = z_in[r * Din + d];
+        se += t_exp<T>(z);
+        sz += z;
+      }
+    se = group_sum<T, G>(se);
+    sz = group_sum<T, G>(sz);
+    if (r < rows) {
+      T den = se + T(1);
+      for (int d = lane; d < Din; d += G) z_out[r * (Din + 1) + d] = t_exp<T>(z_in[r * Din + d]) / den;
+      if (lane == 0) {
+        z_out[r * (Din + 1) + Din] = T(1) / den;
+        T ld = t_log<T>(T(1) - (se / den) + (T)1e-10) - (T)Dattr * t_log<T>(den) + sz;
+        if (accum == TNF_LD_WRITE) log_det[r] = ld;
+        else if (accum == TNF_LD_ADD) log_det[r] += ld;
+        else log_det[r] -= ld;
+      }
+    }
+  }
+}
+
+// y_d = e_d/den, y_last = 1/den, den = 1 + S, S = sum e.   With G_d = g_y[d]:
+//  g_z[k] = e_k/den * (G_k - sum_d G_d y_d - G_last/den) + g_ld * (1 - Dattr e_k/den - e_k/(den^2 (1-S/den+eps)))
+template <typename T, int G>
+__global__ void tosimplex_bwd_kernel(const T* __restrict__ z_in, const T* __restrict__ g_out,
+                                     const T* __restrict__ g_ld, T* __restrict__ g_in, int64_t rows, int Din,
+                                     int Dattr) {
+  int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  int lane = threadIdx.x % G;
+  int64_t ngroups = (int64_t)gridDim.x * blockDim.x / G;
+  int64_t rows_pad = (rows + ngroups - 1) / ngroups * ngroups;
+  for (int64_t r = gid; r < rows_pad; r += ngroups) {
+    T se = T(0), sge = T(0);
+    if (r < rows)
+      for (int d = lane; d < Din; d += G) {
+        T e = t_exp<T>(z_in[r * Din + d]);
+        se += e;
+        if (g_out) sge += g_out[r * (Din + 1) + d] * e;
+      }
+    se = group_sum<T, G>(se);
+    sge = group_sum<T, G>(sge);
+    if (r < rows) {
+      T den = se + T(1);
+      T glast = g_out ? g_out[r * (Din + 1) + Din] : T(0);
+      T gl = g_ld ? g_ld[r] : T(0);
+      T dot = (sge + glast) / den;  // sum_d G_d y_d incl. the last coordinate
+      T q = T(1) - (se / den) + (T)1e-10;
+      for (int d = lane; d < Din; d += G) {
+        T e = t_exp<T>(z_in[r * Din + d]);
+        T gk = g_out ? g_out[r * (Din + 1) + d] : T(0);
+        T gz = e / den * (gk - dot);
+        gz += gl * (T(1) - (T)Dattr * e / den - e / (den * den * q));
+        g_in[r * Din + d] = gz;
+      }
+    }
+  }
+}
+
+template <typename T, int G>
+__global__ void base_logprob_kernel(const T* __restrict__ z, const T* __restrict__ sub, const T* __restrict__ scal,
+                                    int64_t scal_div, T* __restrict__ out, int64_t rows, int D) {
+  int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  int lane = threadIdx.x % G;
+  int64_t ngroups = (int64_t)gridDim.x * blockDim.x / G;
+  int64_t rows_pad = (rows + ngroups - 1) / ngroups * ngroups;
+  const T cst = (T)((double)D * 0.91893853320467274178);  // D*log(sqrt(2*pi))
+  for (int64_t r = gid; r < rows_pad; r += ngroups) {
+    T s = T(0);
+    if (r < rows)
+      for (int d = lane; d < D; d += G) {
+        T v = z[r * D + d];
+        s -= v * v;
+      }
+    s = group_sum<T, G>(s);
+    if (r < rows && lane == 0) {
+      T lp = s / T(2) - cst;
+      T ld = sub ? sub[r] : T(0);
+      if (scal) ld += scal[r / scal_div];
+      out[r] = (sub || scal) ? lp - ld : lp;
+    }
+  }
+}
+
+template <typename T>
+__global__ void base_logprob_bwd_kernel(const T* __restrict__ z, const T* __restrict__ g_out, T* __restrict__ g_z,
+                                        int64_t n_el, int D) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += stride)
+    g_z[e] = -z[e] * g_out[e / D];
+}
+
+// ---------------------------------------------------------------- base sampling (Philox4x32-10)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  // u1 in (0,1], u2 in [0,1)
+  float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
+  float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+// one thread per row-quad-of-4 elements; log-density reduced per row in a second pass
+__global__ void base_sample_kernel(float* __restrict__ z, int64_t n_el, uint64_t seed, uint64_t offset) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t nq = (n_el + 3) / 4;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+    uint64_t cidx = (uint64_t)q + offset;
+    uint4 ctr = make_uint4((uint32_t)cidx, (uint32_t)(cidx >> 32), 0u, 0u);
+    uint4 rnd = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    float2 p0 = box_muller(rnd.x, rnd.y), p1 = box_muller(rnd.z, rnd.w);
+    int64_t e = q * 4;
+    if (e + 3 < n_el) {
+      reinterpret_cast<float4*>(z)[q] = make_float4(p0.x, p0.y, p1.x, p1.y);
+    } else {
+      float v[4] = {p0.x, p0.y, p1.x, p1.y};
+      for (int k = 0; k < 4 && e + k < n_el; ++k) z[e + k] = v[k];
+    }
+  }
+}
+
+template <int G>
+__global__ void base_logq_kernel(const float* __restrict__ omega, double* __restrict__ log_q, int64_t rows, int D) {
+  int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  int lane = threadIdx.x % G;
+  int64_t ngroups = (int64_t)gridDim.x * blockDim.x / G;
+  int64_t rows_pad = (rows + ngroups - 1) / ngroups * ngroups;
+  for (int64_t r = gid; r < rows_pad; r += ngroups) {
+    double s = 0.0;
+    if (r < rows)
+      for (int d = lane; d < D; d += G) {
+        double v = (double)omega[r * D + d];
+        s -= v * v;
+      }
+    s = group_sum<double, G>(s);
+    if (r < rows && lane == 0) log_q[r] = 0.5 * s - (double)D * 0.91893853320467274178;
+  }
+}
+
+template <typename T>
+__global__ void finish_logq_kernel(double* __restrict__ log_q, const T* __restrict__ ld, const T* __restrict__ scal,
+                                   int64_t scal_div, int64_t rows) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
+    T v = ld ? ld[r] : T(0);
+    if (scal) v += scal[r / scal_div];
+    log_q[r] -= (double)v;
+  }
+}
+
+template <typename T>
+__global__ void accum_bcast_kernel(T* __restrict__ dst, const T* __restrict__ src, int64_t n, int64_t div) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i / div];
+}
+
+// launch helper for the row-group kernels
+#define TNF_ROWGROUP(D, ...)                       \
+  do {                                             \
+    if ((D) < 16) { constexpr int G = 1; __VA_ARGS__; }      \
+    else if ((D) < 64) { constexpr int G = 8; __VA_ARGS__; } \
+    else { constexpr int G = 32; __VA_ARGS__; }              \
+  } while (0)
+
+static inline int rowgroup_grid(int64_t rows, int G) { return grid_for(rows * G, 256, 16); }
+
+}  // namespace tnf
+
+using namespace tnf;
+
+extern "C" {
+
+int tnf_abi_version(void) { return TNF_ABI_VERSION; }
+const char* tnf_last_error(void) { return tnf::g_err; }
+int64_t tnf_launch_count(void) { return tnf::g_launches.load(std::memory_order_relaxed); }
+
+int tnf_affine(const void* z_in, void* z_out, void* log_det, const void* params, int64_t pstride, int64_t M,
+               int64_t N, int D, int direction, int dtype, tnf_stream_t stream) {
+  TNF_REQUIRE(z_in && z_out && params, TNF_ERR_ARG, "tnf_affine: null pointer");
+  TNF_REQUIRE(M >= 0 && N >= 0 && D >= 1, TNF_ERR_ARG, "tnf_affine: bad shape M=%lld N=%lld D=%d", (long long)M,
+              (long long)N, D);
+  if (M == 0 || N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N <= 16) {
+    TNF_DISPATCH(dtype, {
+      affine_flat_kernel<T><<<grid_for(M * N * D, 256), 256, 0, st>>>((const T*)z_in, (T*)z_out, (T*)log_det,
+                                                                      (const T*)params, pstride, M, N, D,
+                                                                      direction == TNF_INVERSE);
+    });
+    return check_launch("tnf_affine");
+  }
+  // split each m's N rows into chunks so that M*chunks fills the machine
+  int64_t want = (int64_t)num_sms() * 8;
+  int64_t chunks = (want + M - 1) / M;
+  int64_t max_chunks = (N * D + 4095) / 4096;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int64_t rpc = (N + chunks - 1) / chunks;
+  chunks = (N + rpc - 1) / rpc;
+  int64_t nblk = M * chunks;
+  int grid = (int)(nblk < want ? nblk : want);
+  TNF_DISPATCH(dtype, {
+    size_t smem = 2 * (size_t)D * sizeof(T);
+    affine_kernel<T><<<grid, 256, smem, st>>>((const T*)z_in, (T*)z_out, (T*)log_det, (const T*)params, pstride, M,
+                                               N, D, direction == TNF_INVERSE, (int)chunks, rpc);
+  });
+  return check_launch("tnf_affine");
+}
+
+int tnf_affine_bwd(const void* z_in, const void* params, int64_t pstride, const void* g_z_out, const void* g_log_det,
+                   void* g_z_in, void* g_params, int64_t gstride, int64_t M, int64_t N, int D, int direction,
+                   int dtype, tnf_stream_t stream) {
+  TNF_REQUIRE(z_in && params && g_z_in && g_params, TNF_ERR_ARG, "tnf_affine_bwd: null pointer");
+  if (M == 0 || N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int nt = 256;
+  int grid = (int)(M < (int64_t)num_sms() * 8 ? M : (int64_t)num_sms() * 8);
+  TNF_DISPATCH(dtype, {
+    affine_bwd_kernel<T><<<grid, nt, 2 * nt * sizeof(double), st>>>(
+        (const T*)z_in, (const T*)params, pstride, (const T*)g_z_out, (const T*)g_log_det, (T*)g_z_in, (T*)g_params,
+        gstride, M, N, D, direction == TNF_INVERSE);
+  });
+  return check_launch("tnf_affine_bwd");
+}
+
+size_t tnf_colstats_workspace_bytes(int D) { return (size_t)kStatMaxBlocks * 2 * (size_t)D * sizeof(double); }
+
+static int colstats_launch(const void* a, const void* b, int64_t rows, int D, double* sums, void* workspace,
+                           int dtype, cudaStream_t st, const char* what) {
+  TNF_REQUIRE(a && sums && workspace, TNF_ERR_ARG, "%s: null pointer", what);
+  TNF_REQUIRE(rows >= 1 && D >= 1, TNF_ERR_ARG, "%s: bad shape rows=%lld D=%d", what, (long long)rows, D);
+  int64_t nb = (rows + 63) / 64;
+  int64_t cap = (int64_t)num_sms() * 8;
+  if (cap > kStatMaxBlocks) cap = kStatMaxBlocks;
+  int grid = (int)(nb < cap ? nb : cap);
+  int nt = D <= kStatThreads ? (kStatThreads / D) * D : kStatThreads;
+  if (nt < 32) nt = 32;
+  TNF_DISPATCH(dtype, {
+    colstats_kernel<T><<<grid, nt, 0, st>>>((const T*)a, (const T*)b, rows, D, (double*)workspace);
+  });
+  int rc = check_launch(what);
+  if (rc) return rc;
+  colstats_reduce_kernel<<<(2 * D + 1 + 127) / 128, 128, 0, st>>>((const double*)workspace, grid, D, sums,
+                                                                  (double)rows);
+  return check_launch(what);
+}
+
+int tnf_colstats(const void* z, int64_t rows, int D, double* sums, void* workspace, int dtype, tnf_stream_t stream) {
+  return colstats_launch(z, nullptr, rows, D, sums, workspace, dtype, (cudaStream_t)stream, "tnf_colstats");
+}
+
+int tnf_bn_bwd_sums(const void* g_y, const void* y, int64_t rows, int D, double* gsums, void* workspace, int dtype,
+                    tnf_stream_t stream) {
+  TNF_REQUIRE(y, TNF_ERR_ARG, "tnf_bn_bwd_sums: null pointer");
+  return colstats_launch(g_y, y, rows, D, gsums, workspace, dtype, (cudaStream_t)stream, "tnf_bn_bwd_sums");
+}
+
+int tnf_bn_finalize(const double* sums, int D, double eps, void* mean, void* alpha, void* log_det, int dtype,
+                    tnf_stream_t stream) {
+  TNF_REQUIRE(sums && mean && alpha && log_det, TNF_ERR_ARG, "tnf_bn_finalize: null pointer");
+  TNF_REQUIRE(D >= 1, TNF_ERR_ARG, "tnf_bn_finalize: bad shape");
+  TNF_DISPATCH(dtype, {
+    bn_finalize_kernel<T><<<1, 256, 0, (cudaStream_t)stream>>>(sums, D, eps, (T*)mean, (T*)alpha, (T*)log_det);
+  });
+  return check_launch("tnf_bn_finalize");
+}
+
+int tnf_bn_apply(const void* z_in, void* z_out, const void* mean, const void* alpha, int64_t rows, int D,
+                 int direction, int dtype, tnf_stream_t stream) {
+  TNF_REQUIRE(z_in && z_out && mean && alpha, TNF_ERR_ARG, "tnf_bn_apply: null pointer");
+  if (rows == 0) return 0;
+  int64_t n_el = rows * D;
+  TNF_DISPATCH(dtype, {
+    bn_apply_kernel<T><<<grid_for(n_el, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)z_in, (T*)z_out, (const T*)mean, (const T*)alpha, n_el, D, direction == TNF_INVERSE);
+  });
+  return check_launch("tnf_bn_apply");
+}
+
+int tnf_bn_bwd_apply(const void* g_y, const void* y, const void* alpha, const double* gsums, const void* g_log_det,
+                     const double* count, void* g_z, int64_t rows, int D, int dtype, tnf_stream_t stream) {
+  TNF_REQUIRE(y && alpha && gsums && g_z && count, TNF_ERR_ARG, "tnf_bn_bwd_apply: null pointer");
+  if (rows == 0) return 0;
+  int64_t n_el = rows * D;
+  TNF_DISPATCH(dtype, {
+    bn_bwd_apply_kernel<T><<<grid_for(n_el, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)g_y, (const T*)y, (const T*)alpha, gsums, (const T*)g_log_det, count, (T*)g_z, n_el, D);
+  });
+  return check_launch("tnf_bn_bwd_apply");
+}
+
+int tnf_tointerval(const void* z_in, void* z_out, void* log_det, const float* consts, int64_t rows, int D,
+                   int direction, int accum, int dtype, tnf_stream_t stream) {
+  TNF_REQUIRE(z_in && z_out && log_det && consts, TNF_ERR_ARG, "tnf_tointerval: null pointer");
+  if (rows == 0) return 0;
+  TNF_DISPATCH(dtype, TNF_ROWGROUP(D, {
+    tointerval_kernel<T, G><<<rowgroup_grid(rows, G), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)z_in, (T*)z_out, (T*)log_det, consts, rows, D, direction == TNF_INVERSE, accum);
+  }));
+  return check_launch("tnf_tointerval");
+}
+
+int tnf_tointerval_bwd(const void* z_in, const float* consts, const void* g_z_out, const void* g_log_det,
+                       void* g_z_in, int64_t rows, int D, int direction, int dtype, tnf_stream_t stream) {
+  TNF_REQUIRE(z_in && consts && g_z_in, TNF_ERR_ARG, "tnf_tointerval_bwd: null pointer");
+  if (rows == 0) return 0;
+  TNF_DISPATCH(dtype, {
+    tointerval_bwd_kernel<T, 1><<<grid_for(rows * D, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)z_in, consts, (const T*)g_z_out, (const T*)g_log_det, (T*)g_z_in, rows, D,
+        direction == TNF_INVERSE);
+  });
+  return check_launch("tnf_tointerval_bwd");
+}
+
+int tnf_tosimplex(const void* z_in, void* z_out, void* log_det, int64_t rows, int D_in, int D_attr, int accum,
+                  int dtype, tnf_stream_t stream) {
+  TNF_REQUIRE(z_in && z_out && log_det, TNF_ERR_ARG, "tnf_tosimplex: null pointer");
+  if (rows == 0) return 0;
+  TNF_DISPATCH(dtype, TNF_ROWGROUP(D_in, {
+    tosimplex_kernel<T, G><<<rowgroup_grid(rows, G), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)z_in, (T*)z_out, (T*)log_det, rows, D_in, D_attr, accum);
+  }));
+  return check_launch("tnf_tosimplex");
+}
+
+int tnf_tosimplex_bwd(const void* z_in, const void* g_z_out, const void* g_log_det, void* g_z_in, int64_t rows,
+                      int D_in, int D_attr, int dtype, tnf_stream_t stream) {
+  TNF_REQUIRE(z_in && g_z_in, TNF_ERR_ARG, "tnf_tosimplex_bwd: null pointer");
+  if (rows == 0) return 0;
+  TNF_DISPATCH(dtype, TNF_ROWGROUP(D_in, {
+    tosimplex_bwd_kernel<T, G><<<rowgroup_grid(rows, G), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)z_in, (const T*)g_z_out, (const T*)g_log_det, (T*)g_z_in, rows, D_in, D_attr);
+  }));
+  return check_launch("tnf_tosimplex_bwd");
+}
+
+int tnf_accum_bcast(void* dst, const void* src, int64_t n_dst, int64_t div, int dtype, tnf_stream_t stream) {
+  TNF_REQUIRE(dst && src && div >= 1, TNF_ERR_ARG, "tnf_accum_bcast: bad argument");
+  if (n_dst == 0) return 0;
+  TNF_DISPATCH(dtype, {
+    accum_bcast_kernel<T><<<grid_for(n_dst, 256 * 4), 256, 0, (cudaStream_t)stream>>>((T*)dst, (const T*)src, n_dst,
+                                                                                      div);
+  });
+  return check_launch("tnf_accum_bcast");
+}
+
+int tnf_base_logprob(const void* z, const void* sub, const void* scal, int64_t scal_div, void* out, int64_t rows,
+                     int D, int dtype, tnf_stream_t stream) {
+  TNF_REQUIRE(z && out, TNF_ERR_ARG, "tnf_base_logprob: null pointer");
+  TNF_REQUIRE(!scal || scal_div >= 1, TNF_ERR_ARG, "tnf_base_logprob: scal_div must be >= 1");
+  if (rows == 0) return 0;
+  TNF_DISPATCH(dtype, TNF_ROWGROUP(D, {
+    base_logprob_kernel<T, G><<<rowgroup_grid(rows, G), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)z, (const T*)sub, (const T*)scal, scal_div, (T*)out, rows, D);
+  }));
+  return check_launch("tnf_base_logprob");
+}
+
+int tnf_base_logprob_bwd(const void* z, const void* g_out, void* g_z, int64_t rows, int D, int dtype,
+                         tnf_stream_t stream) {
+  TNF_REQUIRE(z && g_out && g_z, TNF_ERR_ARG, "tnf_base_logprob_bwd: null pointer");
+  if (rows == 0) return 0;
+  TNF_DISPATCH(dtype, {
+    base_logprob_bwd_kernel<T><<<grid_for(rows * D, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)z, (const T*)g_out, (T*)g_z, rows * D, D);
+  });
+  return check_launch("tnf_base_logprob_bwd");
+}
+
+int tnf_base_sample(float* z, double* log_q, int64_t rows, int D, uint64_t seed, uint64_t offset,
+                    tnf_stream_t stream) {
+  TNF_REQUIRE(z && log_q, TNF_ERR_ARG, "tnf_base_sample: null pointer");
+  TNF_REQUIRE(((uintptr_t)z & 15) == 0, TNF_ERR_ALIGN, "tnf_base_sample: z must be 16-byte aligned");
+  if (rows == 0) return 0;
+  int64_t n_el = rows * D;
+  base_sample_kernel<<<grid_for((n_el + 3) / 4, 256 * 2), 256, 0, (cudaStream_t)stream>>>(z, n_el, seed, offset);
+  int rc = check_launch("tnf_base_sample");
+  if (rc) return rc;
+  return tnf_base_logq(z, log_q, rows, D, stream);
+}
+
+int tnf_base_logq(const float* omega, double* log_q, int64_t rows, int D, tnf_stream_t stream) {
+  TNF_REQUIRE(omega && log_q, TNF_ERR_ARG, "tnf_base_logq: null pointer");
+  if (rows == 0) return 0;
+  TNF_ROWGROUP(D, {
+    base_logq_kernel<G><<<rowgroup_grid(rows, G), 256, 0, (cudaStream_t)stream>>>(omega, log_q, rows, D);
+  });
+  return check_launch("tnf_base_logq");
+}
+
+int tnf_finish_logq(double* log_q, const void* ld_acc, const void* scal, int64_t scal_div, int64_t rows, int dtype,
+                    tnf_stream_t stream) {
+  TNF_REQUIRE(log_q, TNF_ERR_ARG, "tnf_finish_logq: null pointer");
+  TNF_REQUIRE(!scal || scal_div >= 1, TNF_ERR_ARG, "tnf_finish_logq: scal_div must be >= 1");
+  if (rows == 0) return 0;
+  TNF_DISPATCH(dtype, {
+    finish_logq_kernel<T><<<grid_for(rows, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+        log_q, (const T*)ld_acc, (const T*)scal, scal_div, rows);
+  });
+  return check_launch("tnf_finish_logq");
+}
+
+}  // extern "C"

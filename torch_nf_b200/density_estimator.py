@@ -1,0 +1,386 @@
+"""Density estimators of the torch_nf API on the B200 hot path.
+
+Host-side mirror of reference ``torch_nf/density_estimator.py``
+(``DensityEstimator`` :11-55, ``NormFlow`` :240-421): same constructor,
+validation, bijector order, parameter slicing and return dtypes
+(``forward`` -> ``z`` float32 + ``log_q_z`` float64, ``log_prob`` -> float32).
+The chain runs as CUDA kernels; without autograd it runs as a fused plan in
+which every bijector accumulates its log-det in place, BatchNorm / Affine are
+folded into the neighbouring coupling kernel where the tensor-core path is
+active, and nothing but ``z`` and the accumulators touches HBM between layers.
+"""
+import numpy as np
+import torch
+
+from . import config, ops
+from .bijectors import Affine, BatchNorm, Bijector, MAF, RealNVP, ToInterval, ToSimplex
+from .error_formatters import format_type_err_msg
+from .ops import TNF_FORWARD, TNF_INVERSE, TNF_LD_ADD
+
+
+class DensityEstimator(object):
+    """Abstract base (reference density_estimator.py:11-55)."""
+
+    def __init__(self, D, conditioner=False):
+        super().__init__()
+        self.D = D
+        self.conditioner = conditioner
+
+    @property
+    def D(self):
+        return self._D
+
+    @D.setter
+    def D(self, val):
+        if type(val) is not int:
+            raise TypeError(format_type_err_msg(self, "D", val, int))
+        if val < 2:
+            raise ValueError("DensityEstimator D %d must be greater than 1." % val)
+        self._D = val
+
+    @property
+    def conditioner(self):
+        return self._conditioner
+
+    @conditioner.setter
+    def conditioner(self, val):
+        if type(val) is not bool:
+            raise TypeError(format_type_err_msg(self, "conditioner", val, bool))
+        self._conditioner = val
+
+    def __call__(self, N=100, params=None):
+        if not self.conditioner:
+            return self.forward(self.params, N)
+        return self.forward(params, N)
+
+    def forward(self, params, N=100, freeze_bn=False):
+        raise NotImplementedError()
+
+    def log_prob(self, z, params=None):
+        raise NotImplementedError()
+
+    def count_num_params(self):
+        raise NotImplementedError()
+
+    def _param_init(self):
+        raise NotImplementedError()
+
+
+class NormFlow(DensityEstimator):
+    """Normalizing flow (reference density_estimator.py:240-421).
+
+    ``arch_type='coupling'`` stacks, per stage,
+    ``RealNVP(upper) -> BatchNorm -> RealNVP(lower) -> BatchNorm -> Affine``
+    (:260-270); ``'AR'`` is ``MAF -> BatchNorm -> Affine``; ``'affine'`` a single
+    ``Affine``; an optional ``support_layer`` bijector instance is appended.
+    ``params`` is the flat ``(M, D_params)`` matrix in chain order.
+
+    Extensions that do not change reference behaviour: ``forward(...,
+    omega=)`` injects the base noise (parity runs); tensors may live on the GPU,
+    in which case results stay there.
+    """
+
+    def __init__(self, D, conditioner=False, arch_type="AR", num_stages=1, num_layers=2, num_units=15,
+                 support_layer=None):
+        super().__init__(D, conditioner)
+        self.arch_type = arch_type
+        self.num_stages = num_stages
+        self.num_layers = num_layers
+        self.num_units = num_units
+        self.support_layer = support_layer
+
+        self.bijectors = []
+        if arch_type == "coupling":
+            for _ in range(num_stages):
+                self.bijectors.append(RealNVP(D, num_layers, num_units, transform_upper=True))
+                self.bijectors.append(BatchNorm(D))
+                self.bijectors.append(RealNVP(D, num_layers, num_units, transform_upper=False))
+                self.bijectors.append(BatchNorm(D))
+                self.bijectors.append(Affine(D))
+        elif arch_type == "AR":
+            self.bijectors.append(MAF(D, self.num_layers, self.num_units, fwd_fac=True))
+            self.bijectors.append(BatchNorm(D))
+            self.bijectors.append(Affine(D))
+        elif arch_type == "affine":
+            self.bijectors.append(Affine(D))
+
+        if support_layer is not None:
+            if issubclass(type(support_layer), Bijector):
+                self.bijectors.append(support_layer)
+            else:
+                raise TypeError("Support layer not Bijector.")
+
+        self.count_num_params()
+        self._tc_cache = {}
+        if not self.conditioner:
+            self._param_init()
+
+    # ---- validated attributes (density_estimator.py:289-350)
+    @property
+    def arch_type(self):
+        return self._arch_type
+
+    @arch_type.setter
+    def arch_type(self, val):
+        if type(val) is not str:
+            raise TypeError(format_type_err_msg(self, "arch_type", val, str))
+        if val not in ("coupling", "AR", "affine"):
+            raise ValueError('NormalizingFlow arch_type must be "coupling", "AR", or "affine".')
+        self._arch_type = val
+
+    @property
+    def num_stages(self):
+        return self._num_stages
+
+    @num_stages.setter
+    def num_stages(self, val):
+        if type(val) is not int:
+            raise TypeError(format_type_err_msg(self, "num_stages", val, int))
+        if val < 1:
+            raise ValueError("NormalizingFlow num_stages %d must be greater than 0." % val)
+        self._num_stages = val
+
+    @property
+    def num_layers(self):
+        return self._num_layers
+
+    @num_layers.setter
+    def num_layers(self, val):
+        if type(val) is not int:
+            raise TypeError(format_type_err_msg(self, "num_layers", val, int))
+        if val < 1:
+            raise ValueError("NormalizingFlow num_layers arg %d must be greater than 0." % val)
+        self._num_layers = val
+
+    @property
+    def num_units(self):
+        return self._num_units
+
+    @num_units.setter
+    def num_units(self, val):
+        if type(val) is not int:
+            raise TypeError(format_type_err_msg(self, "num_units", val, int))
+        if val < 1:
+            raise ValueError("NormalizingFlow num_units %d must be greater than 0." % val)
+        if val < 15:
+            print("Warning: NormFlow.num_layers set to minimum of 15 (received %d)." % val)
+            val = 15
+        self._num_units = val
+
+    def count_num_params(self):
+        self.D_params = 0
+        for b in self.bijectors:
+            self.D_params += b.count_num_params()
+
+    def _param_init(self):
+        """xavier_normal_ on a (1, D_params) leaf tensor kept as a plain
+        attribute (density_estimator.py:352-356)."""
+        self.params = torch.nn.init.xavier_normal_(torch.zeros(1, self.D_params, requires_grad=True))
+        return None
+
+    def to(self, device):
+        """Keep the unconditional weights resident on ``device`` (HBM)."""
+        if not self.conditioner:
+            self.params = self.params.detach().to(device).requires_grad_(True)
+        return self
+
+    # ---- sampling ------------------------------------------------------
+    def __call__(self, N=100, params=None, freeze_bn=False):
+        if not self.conditioner:
+            return self.forward(self.params, N, freeze_bn=freeze_bn)
+        return self.forward(params, N, freeze_bn=freeze_bn)
+
+    def forward(self, params, N=100, freeze_bn=False, omega=None):
+        """Sample ``N`` points per parameter row and their log-density
+        (density_estimator.py:364-388). Returns ``(z (M,N,D) float32,
+        log_q_z (M,N) float64)`` on the device of ``params``."""
+        home = params.device
+        pd = ops.to_device(params, torch.float32)
+        M = pd.size(0)
+        z, log_q = self._base(M, N, pd.device, omega)
+        if torch.is_grad_enabled() and pd.requires_grad:
+            z, log_q = self._forward_autograd(z, log_q, pd, freeze_bn)
+        else:
+            z, log_q = self._forward_plan(z, log_q, pd.detach(), freeze_bn, home)
+        return _to(z, home), _to(log_q, home)
+
+    def _base(self, M, N, device, omega):
+        if omega is None:
+            # one draw from numpy's global stream seeds the device Philox stream, so
+            # np.random.seed(s) makes sampling reproducible as it does for the reference
+            seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + 12345
+            return ops.base_sample(M, N, self.D, seed, 0, device)
+        if isinstance(omega, np.ndarray):
+            omega = torch.from_numpy(np.ascontiguousarray(omega))
+        if tuple(omega.shape) != (M, N, self.D):
+            raise ValueError("omega must have shape %s, got %s" % ((M, N, self.D), tuple(omega.shape)))
+        z = ops.to_device(omega, torch.float32).contiguous()
+        return z, ops.base_logq(z)
+
+    def _slices(self):
+        """[(bijector, first parameter column, count)] in chain order."""
+        out, idx = [], 0
+        for b in self.bijectors:
+            n = b.count_num_params()
+            out.append((b, idx, n))
+            idx += n
+        return out
+
+    def _use_tc(self, b, pd, z):
+        return (config.conditioner_precision() == "bf16" and pd.shape[0] == 1 and z.dtype == torch.float32
+                and b.name == "RealNVP" and z.shape[0] * z.shape[1] >= config.tc_min_rows()
+                and ops.tc_supported(b.D, b.num_units, b.num_layers))
+
+    def _packed(self, b, idx, n, pd):
+        key = (id(b), pd.data_ptr(), pd._version, idx)
+        hit = self._tc_cache.get(id(b))
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        packed = ops.tc_pack(pd[0, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper)
+        self._tc_cache[id(b)] = (key, packed)
+        return packed
+
+    def _forward_plan(self, z, log_q, pd, freeze_bn, home=None):
+        M, N, D = z.shape
+        Mp = pd.shape[0]
+        ld_acc = torch.zeros((M, N), dtype=torch.float32, device=z.device)
+        scal = torch.zeros(Mp, dtype=torch.float32, device=z.device)
+        for (b, idx, n) in self._slices():
+            if b.name == "RealNVP":
+                if self._use_tc(b, pd, z):
+                    z, _ = ops.coupling_tc(z, self._packed(b, idx, n, pd), b.D, b.num_units, b.num_layers,
+                                           b.transform_upper, TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD)
+                else:
+                    z, _ = ops.coupling(z, pd[:, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper,
+                                        TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD)
+            elif b.name == "BatchNorm":
+                if freeze_bn:
+                    mean, alpha = b._state_on(z.device, z.dtype)
+                    ld = b._last_ld.to(device=z.device, dtype=z.dtype)
+                else:
+                    from .bijectors import _reduce_stats
+                    sums = _reduce_stats(ops.colstats(z, D))
+                    mean, alpha, ld = ops.bn_finalize(sums, D, b.eps, z.dtype)
+                    b._set_state(mean, alpha, ld, home)
+                z = ops.bn_apply(z, mean, alpha, D, TNF_FORWARD)
+                ops.accum_bcast(scal, ld.reshape(1), Mp)
+            elif b.name == "Affine":
+                z, ld = ops.affine(z, pd[:, idx:idx + n], D, TNF_FORWARD)
+                ops.accum_bcast(scal, ld, 1)
+            elif b.name == "ToInterval":
+                z, _ = ops.tointerval(z, b._consts(z.device), D, TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD)
+            elif b.name == "ToSimplex":
+                z, _ = ops.tosimplex(z, b.D, ld=ld_acc, accum=TNF_LD_ADD)
+            else:  # MAF or a user-defined bijector: public protocol, log-det folded in by kernel
+                z, ld = b(z, pd[:, idx:idx + n]) if n > 0 else b(z)
+                ld = ld.detach().to(torch.float32)
+                if ld.numel() == M * N:
+                    ops.accum_bcast(ld_acc, ld.contiguous(), 1)
+                else:
+                    ops.accum_bcast(scal, ld.reshape(-1).contiguous(), Mp if ld.numel() == 1 else 1)
+                z = z.detach()
+        ops.finish_logq(log_q, ld_acc, scal, N if Mp == M and M > 1 else M * N)
+        return z, log_q
+
+    def _forward_autograd(self, z, log_q, pd, freeze_bn):
+        """Differentiable sample path: per-bijector autograd functions
+        (density_estimator.py:374-387 verbatim control flow)."""
+        for (b, idx, n) in self._slices():
+            if b.name == "BatchNorm":
+                z, log_det = b(z, use_last=freeze_bn)
+            elif n > 0:
+                z, log_det = b(z, pd[:, idx:idx + n])
+            else:
+                z, log_det = b(z)
+            log_q = log_q - log_det
+        return z, log_q
+
+    # ---- density -------------------------------------------------------
+    def inverse_and_log_det(self, z, params):
+        """Run the chain backwards (density_estimator.py:390-406). Returns
+        ``(z0, sum_log_det (M,N))``."""
+        home = z.device
+        zd = ops.to_device(z if z.dtype in (torch.float32, torch.float64) else z.float())
+        pd = ops.to_device(params, zd.dtype)
+        if torch.is_grad_enabled() and (pd.requires_grad or zd.requires_grad):
+            z0, sld = self._inverse_autograd(zd, pd)
+        else:
+            z0, ld_acc, scal, div = self._inverse_plan(zd.detach().contiguous(), pd.detach())
+            sld = ops.accum_bcast(ld_acc, scal, div)
+        return _to(z0, home), _to(sld, home)
+
+    def _inverse_plan(self, z, pd):
+        M, N, D = z.shape
+        Mp = pd.shape[0]
+        ld_acc = torch.zeros((M, N), dtype=z.dtype, device=z.device)
+        scal = torch.zeros(Mp, dtype=z.dtype, device=z.device)
+        for (b, idx, n) in reversed(self._slices()):
+            if b.name == "RealNVP":
+                if self._use_tc(b, pd, z):
+                    z, _ = ops.coupling_tc(z, self._packed(b, idx, n, pd), b.D, b.num_units, b.num_layers,
+                                           b.transform_upper, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD)
+                else:
+                    z, _ = ops.coupling(z, pd[:, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper,
+                                        TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD)
+            elif b.name == "BatchNorm":
+                mean, alpha = b._state_on(z.device, z.dtype)
+                z = ops.bn_apply(z, mean, alpha, D, TNF_INVERSE)
+                ops.accum_bcast(scal, b._last_ld.to(device=z.device, dtype=z.dtype).reshape(1), Mp)
+            elif b.name == "Affine":
+                z, ld = ops.affine(z, pd[:, idx:idx + n], D, TNF_INVERSE)
+                ops.accum_bcast(scal, ld, 1)
+            elif b.name == "ToInterval":
+                z, _ = ops.tointerval(z, b._consts(z.device), D, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD)
+            else:
+                if n > 0:
+                    z, ld = b.inverse_and_log_det(z, pd[:, idx:idx + n])
+                else:
+                    z, ld = b.inverse_and_log_det(z)   # ToSimplex: TypeError, as in the reference
+                ld = ld.detach().to(z.dtype)
+                if ld.numel() == M * N:
+                    ops.accum_bcast(ld_acc, ld.contiguous(), 1)
+                else:
+                    ops.accum_bcast(scal, ld.reshape(-1).contiguous(), Mp if ld.numel() == 1 else 1)
+                z = z.detach()
+        return z, ld_acc, scal, (N if Mp == M and M > 1 else M * N)
+
+    def _inverse_autograd(self, z, pd):
+        sum_log_det = torch.zeros((z.shape[0], z.shape[1]), dtype=z.dtype, device=z.device)
+        for (b, idx, n) in reversed(self._slices()):
+            if n > 0:
+                z, log_det = b.inverse_and_log_det(z, pd[:, idx:idx + n])
+            else:
+                z, log_det = b.inverse_and_log_det(z)
+            sum_log_det = sum_log_det + log_det
+        return z, sum_log_det
+
+    def log_prob(self, z, params=None):
+        """log q(z) = log N(z0; 0, I) - sum_log_det (density_estimator.py:408-416)."""
+        if not self.conditioner:
+            params = self.params
+        home = z.device
+        zd = ops.to_device(z if z.dtype in (torch.float32, torch.float64) else z.float())
+        pd = ops.to_device(params, zd.dtype)
+        if torch.is_grad_enabled() and (pd.requires_grad or zd.requires_grad):
+            z0, sld = self._inverse_autograd(zd, pd)
+            lp = _BaseLogProbFn.apply(z0) - sld
+        else:
+            z0, ld_acc, scal, div = self._inverse_plan(zd.detach().contiguous(), pd.detach())
+            lp = ops.base_logprob(z0, ld_acc, scal, div)
+        return _to(lp, home)
+
+
+class _BaseLogProbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        ctx.save_for_backward(z)
+        return ops.base_logprob(z)
+
+    @staticmethod
+    def backward(ctx, g):
+        (z,) = ctx.saved_tensors
+        return ops.base_logprob_bwd(z, g)
+
+
+def _to(t, device):
+    return t if t.device == device else t.to(device)

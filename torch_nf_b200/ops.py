@@ -1,0 +1,350 @@
+"""Tensor-level wrappers over the C-ABI kernels (no autograd here).
+
+Every function takes CUDA tensors, validates shape / dtype / contiguity in
+Python (the C side only checks pointers and ranges), enqueues on torch's
+current stream and returns torch tensors it allocated.  torch is used for
+device memory and streams only; all arithmetic happens in ``_C.so``.
+"""
+import torch
+
+from . import _lib
+from ._lib import TNF_F32, TNF_F64, TNF_FORWARD, TNF_INVERSE, TNF_LD_WRITE, TNF_LD_ADD, TNF_LD_SUB  # noqa: F401
+
+_DT = {torch.float32: TNF_F32, torch.float64: TNF_F64}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "torch_nf_b200 computes on a CUDA device (sm_100a) only; no CUDA device is visible "
+            "and there is no CPU fallback")
+
+
+def to_device(t, dtype=None):
+    """Move a tensor to the current CUDA device (the reference's own tests hand
+    CPU tensors to bijectors; they are staged to HBM, never computed on CPU)."""
+    require_cuda()
+    if not t.is_cuda:
+        t = t.cuda()
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError("torch_nf_b200 kernels take float32 or float64 tensors, got %s" % t.dtype)
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _check3(z):
+    if z.dim() != 3:
+        raise ValueError("z must have shape (M, N, D), got %s" % (tuple(z.shape),))
+    return z if z.is_contiguous() else z.contiguous()
+
+
+def param_view(params, n_needed):
+    """(tensor, row_stride) for a parameter slice whose rows may be strided."""
+    if params.dim() != 2:
+        raise ValueError("params must have shape (M, >=|theta|), got %s" % (tuple(params.shape),))
+    if params.shape[1] < n_needed:
+        raise ValueError("params has %d columns, bijector needs %d" % (params.shape[1], n_needed))
+    if params.shape[1] > 1 and params.stride(1) != 1:
+        params = params.contiguous()
+    stride = params.stride(0) if params.shape[0] > 1 else 0
+    return params, stride
+
+
+def _match_rows(z, params):
+    """Reference broadcasting: params with one row serve every m of z."""
+    M = z.shape[0]
+    Mp = params.shape[0]
+    if Mp != M and Mp != 1:
+        raise ValueError("params has %d rows but z has M=%d" % (Mp, M))
+    return Mp
+
+
+# ----------------------------------------------------------------- coupling
+def coupling(z, params, D, U, L, upper, direction, ld=None, accum=TNF_LD_WRITE):
+    """RealNVP layer on the exact CUDA-core path. Returns (z_out, log_det (M,N))."""
+    z = _check3(z)
+    M, N, _ = z.shape
+    params, pstride = param_view(params, 0)
+    Mp = _match_rows(z, params)
+    z_out = torch.empty_like(z)
+    if ld is None:
+        ld = torch.empty((M, N), dtype=z.dtype, device=z.device)
+        accum = TNF_LD_WRITE
+    Mk, Nk = (1, M * N) if Mp == 1 else (M, N)
+    rc = _lib.lib().tnf_coupling(z.data_ptr(), z_out.data_ptr(), ld.data_ptr(), params.data_ptr(), pstride, Mk, Nk,
+                                 D, U, L, int(upper), direction, accum, _dt(z), _stream())
+    _lib.check(rc, "tnf_coupling")
+    return z_out, ld
+
+
+def coupling_bwd(z_in, params, g_z_out, g_ld, g_params, D, U, L, upper, direction):
+    """Accumulates into ``g_params`` (same row layout as ``params``); returns g_z_in."""
+    z_in = _check3(z_in)
+    M, N, _ = z_in.shape
+    params, pstride = param_view(params, 0)
+    Mp = _match_rows(z_in, params)
+    assert g_params.shape[0] == Mp and (g_params.shape[1] <= 1 or g_params.stride(1) == 1)
+    gstride = g_params.stride(0) if Mp > 1 else 0
+    g_z_out = None if g_z_out is None else g_z_out.contiguous()
+    g_ld = None if g_ld is None else g_ld.contiguous()
+    g_z = torch.empty_like(z_in)
+    Mk, Nk = (1, M * N) if Mp == 1 else (M, N)
+    rc = _lib.lib().tnf_coupling_bwd(z_in.data_ptr(), params.data_ptr(), pstride, _ptr(g_z_out), _ptr(g_ld),
+                                     g_z.data_ptr(), g_params.data_ptr(), gstride, Mk, Nk, D, U, L, int(upper),
+                                     direction, _dt(z_in), _stream())
+    _lib.check(rc, "tnf_coupling_bwd")
+    return g_z
+
+
+# ----------------------------------------------------------------- tensor-core coupling
+def tc_supported(D, U, L):
+    return bool(_lib.lib().tnf_tc_supported(D, U, L))
+
+
+def tc_pack(params_row, D, U, L, upper):
+    """fp32 parameter row -> packed bf16 UMMA operand image (+ fp32 biases)."""
+    nbytes = _lib.lib().tnf_tc_packed_bytes(D, U, L)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=params_row.device)
+    p = params_row.reshape(-1)
+    if p.dtype != torch.float32 or not p.is_contiguous():
+        p = p.float().contiguous()
+    rc = _lib.lib().tnf_tc_pack(p.data_ptr(), packed.data_ptr(), D, U, L, int(upper), _stream())
+    _lib.check(rc, "tnf_tc_pack")
+    return packed
+
+
+def coupling_tc(z, packed, D, U, L, upper, direction, ld=None, accum=TNF_LD_WRITE, pre_scale=None, pre_shift=None,
+                col_stats=None, out=None):
+    z2 = z.reshape(-1, D)
+    if z2.dtype != torch.float32 or not z2.is_contiguous():
+        raise TypeError("tensor-core coupling takes contiguous float32 z")
+    rows = z2.shape[0]
+    z_out = torch.empty_like(z2) if out is None else out
+    if ld is None:
+        ld = torch.empty(rows, dtype=torch.float32, device=z.device)
+        accum = TNF_LD_WRITE
+    rc = _lib.lib().tnf_coupling_tc(z2.data_ptr(), z_out.data_ptr(), ld.data_ptr(), packed.data_ptr(), rows, D, U, L,
+                                    int(upper), direction, accum, _ptr(pre_scale), _ptr(pre_shift), _ptr(col_stats),
+                                    _stream())
+    _lib.check(rc, "tnf_coupling_tc")
+    return z_out.view(z.shape), ld
+
+
+# ----------------------------------------------------------------- affine
+def affine(z, params, D, direction, want_ld=True):
+    z = _check3(z)
+    M, N, _ = z.shape
+    params, pstride = param_view(params, 2 * D)
+    Mp = _match_rows(z, params)
+    z_out = torch.empty_like(z)
+    ld = torch.empty((Mp, 1), dtype=z.dtype, device=z.device) if want_ld else None
+    Mk, Nk = (1, M * N) if Mp == 1 else (M, N)
+    rc = _lib.lib().tnf_affine(z.data_ptr(), z_out.data_ptr(), _ptr(ld), params.data_ptr(), pstride, Mk, Nk, D,
+                               direction, _dt(z), _stream())
+    _lib.check(rc, "tnf_affine")
+    return z_out, ld
+
+
+def affine_bwd(z_in, params, g_z_out, g_ld, g_params, D, direction):
+    z_in = _check3(z_in)
+    M, N, _ = z_in.shape
+    params, pstride = param_view(params, 2 * D)
+    Mp = _match_rows(z_in, params)
+    gstride = g_params.stride(0) if Mp > 1 else 0
+    g_z_out = None if g_z_out is None else g_z_out.contiguous()
+    g_ld = None if g_ld is None else g_ld.contiguous()
+    g_z = torch.empty_like(z_in)
+    Mk, Nk = (1, M * N) if Mp == 1 else (M, N)
+    rc = _lib.lib().tnf_affine_bwd(z_in.data_ptr(), params.data_ptr(), pstride, _ptr(g_z_out), _ptr(g_ld),
+                                   g_z.data_ptr(), g_params.data_ptr(), gstride, Mk, Nk, D, direction, _dt(z_in),
+                                   _stream())
+    _lib.check(rc, "tnf_affine_bwd")
+    return g_z
+
+
+# ----------------------------------------------------------------- batch norm
+_ws_cache = {}
+
+
+def _workspace(D, device):
+    key = (D, device)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = torch.empty(_lib.lib().tnf_colstats_workspace_bytes(D), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def colstats(z, D):
+    """[sum (D) | sum of squares (D) | rows] of the flattened (rows, D) batch, float64."""
+    z2 = z.reshape(-1, D)
+    z2 = z2 if z2.is_contiguous() else z2.contiguous()
+    sums = torch.empty(2 * D + 1, dtype=torch.float64, device=z.device)
+    rc = _lib.lib().tnf_colstats(z2.data_ptr(), z2.shape[0], D, sums.data_ptr(), _workspace(D, z.device).data_ptr(),
+                                 _dt(z2), _stream())
+    _lib.check(rc, "tnf_colstats")
+    return sums
+
+
+def bn_finalize(sums, D, eps, dtype):
+    mean = torch.empty(D, dtype=dtype, device=sums.device)
+    alpha = torch.empty(D, dtype=dtype, device=sums.device)
+    ld = torch.empty((), dtype=dtype, device=sums.device)
+    rc = _lib.lib().tnf_bn_finalize(sums.data_ptr(), D, float(eps), mean.data_ptr(), alpha.data_ptr(),
+                                    ld.data_ptr(), _DT[dtype], _stream())
+    _lib.check(rc, "tnf_bn_finalize")
+    return mean, alpha, ld
+
+
+def bn_apply(z, mean, alpha, D, direction):
+    zc = z if z.is_contiguous() else z.contiguous()
+    z_out = torch.empty_like(zc)
+    rows = zc.numel() // D
+    rc = _lib.lib().tnf_bn_apply(zc.data_ptr(), z_out.data_ptr(), mean.data_ptr(), alpha.data_ptr(), rows, D,
+                                 direction, _dt(zc), _stream())
+    _lib.check(rc, "tnf_bn_apply")
+    return z_out
+
+
+def bn_bwd_sums(g_y, y, D):
+    y2 = y.reshape(-1, D)
+    y2 = y2 if y2.is_contiguous() else y2.contiguous()
+    g2 = g_y.reshape(-1, D)
+    g2 = g2 if g2.is_contiguous() else g2.contiguous()
+    gs = torch.empty(2 * D + 1, dtype=torch.float64, device=y.device)
+    rc = _lib.lib().tnf_bn_bwd_sums(g2.data_ptr(), y2.data_ptr(), y2.shape[0], D, gs.data_ptr(),
+                                    _workspace(D, y.device).data_ptr(), _dt(y2), _stream())
+    _lib.check(rc, "tnf_bn_bwd_sums")
+    return gs
+
+
+def bn_bwd_apply(g_y, y, alpha, gsums, g_ld, count, D):
+    """``count``: 1-element float64 device tensor holding the global row count."""
+    yc = y if y.is_contiguous() else y.contiguous()
+    gc = None if g_y is None else (g_y if g_y.is_contiguous() else g_y.contiguous())
+    g_z = torch.empty_like(yc)
+    rows = yc.numel() // D
+    rc = _lib.lib().tnf_bn_bwd_apply(_ptr(gc), yc.data_ptr(), alpha.data_ptr(), gsums.data_ptr(), _ptr(g_ld),
+                                     count.data_ptr(), g_z.data_ptr(), rows, D, _dt(yc), _stream())
+    _lib.check(rc, "tnf_bn_bwd_apply")
+    return g_z
+
+
+# ----------------------------------------------------------------- support layers
+def tointerval(z, consts, D, direction, ld=None, accum=TNF_LD_WRITE):
+    z = _check3(z)
+    M, N, _ = z.shape
+    z_out = torch.empty_like(z)
+    if ld is None:
+        ld = torch.empty((M, N), dtype=z.dtype, device=z.device)
+        accum = TNF_LD_WRITE
+    rc = _lib.lib().tnf_tointerval(z.data_ptr(), z_out.data_ptr(), ld.data_ptr(), consts.data_ptr(), M * N, D,
+                                   direction, accum, _dt(z), _stream())
+    _lib.check(rc, "tnf_tointerval")
+    return z_out, ld
+
+
+def tointerval_bwd(z_in, consts, g_z_out, g_ld, D, direction):
+    z_in = _check3(z_in)
+    M, N, _ = z_in.shape
+    g_z_out = None if g_z_out is None else g_z_out.contiguous()
+    g_ld = None if g_ld is None else g_ld.contiguous()
+    g_z = torch.empty_like(z_in)
+    rc = _lib.lib().tnf_tointerval_bwd(z_in.data_ptr(), consts.data_ptr(), _ptr(g_z_out), _ptr(g_ld), g_z.data_ptr(),
+                                       M * N, D, direction, _dt(z_in), _stream())
+    _lib.check(rc, "tnf_tointerval_bwd")
+    return g_z
+
+
+def tosimplex(z, D_attr, ld=None, accum=TNF_LD_WRITE):
+    z = _check3(z)
+    M, N, Din = z.shape
+    z_out = torch.empty((M, N, Din + 1), dtype=z.dtype, device=z.device)
+    if ld is None:
+        ld = torch.empty((M, N), dtype=z.dtype, device=z.device)
+        accum = TNF_LD_WRITE
+    rc = _lib.lib().tnf_tosimplex(z.data_ptr(), z_out.data_ptr(), ld.data_ptr(), M * N, Din, D_attr, accum, _dt(z),
+                                  _stream())
+    _lib.check(rc, "tnf_tosimplex")
+    return z_out, ld
+
+
+def tosimplex_bwd(z_in, g_z_out, g_ld, D_attr):
+    z_in = _check3(z_in)
+    M, N, Din = z_in.shape
+    g_z_out = None if g_z_out is None else g_z_out.contiguous()
+    g_ld = None if g_ld is None else g_ld.contiguous()
+    g_z = torch.empty_like(z_in)
+    rc = _lib.lib().tnf_tosimplex_bwd(z_in.data_ptr(), _ptr(g_z_out), _ptr(g_ld), g_z.data_ptr(), M * N, Din, D_attr,
+                                      _dt(z_in), _stream())
+    _lib.check(rc, "tnf_tosimplex_bwd")
+    return g_z
+
+
+# ----------------------------------------------------------------- base density
+def accum_bcast(dst, src, div):
+    """dst[i] += src[i // div] (flattened), in place."""
+    rc = _lib.lib().tnf_accum_bcast(dst.data_ptr(), src.data_ptr(), dst.numel(), int(div), _dt(dst), _stream())
+    _lib.check(rc, "tnf_accum_bcast")
+    return dst
+
+
+def base_logprob(z, sub=None, scal=None, scal_div=1):
+    z = _check3(z)
+    M, N, D = z.shape
+    out = torch.empty((M, N), dtype=z.dtype, device=z.device)
+    rc = _lib.lib().tnf_base_logprob(z.data_ptr(), _ptr(sub), _ptr(scal), int(scal_div), out.data_ptr(), M * N, D,
+                                     _dt(z), _stream())
+    _lib.check(rc, "tnf_base_logprob")
+    return out
+
+
+def base_logprob_bwd(z, g_out):
+    z = _check3(z)
+    M, N, D = z.shape
+    g_out = g_out.contiguous()
+    g_z = torch.empty_like(z)
+    rc = _lib.lib().tnf_base_logprob_bwd(z.data_ptr(), g_out.data_ptr(), g_z.data_ptr(), M * N, D, _dt(z), _stream())
+    _lib.check(rc, "tnf_base_logprob_bwd")
+    return g_z
+
+
+def base_sample(M, N, D, seed, offset, device):
+    z = torch.empty((M, N, D), dtype=torch.float32, device=device)
+    log_q = torch.empty((M, N), dtype=torch.float64, device=device)
+    rc = _lib.lib().tnf_base_sample(z.data_ptr(), log_q.data_ptr(), M * N, D, int(seed) & (2 ** 64 - 1),
+                                    int(offset) & (2 ** 64 - 1), _stream())
+    _lib.check(rc, "tnf_base_sample")
+    return z, log_q
+
+
+def base_logq(omega):
+    omega = _check3(omega)
+    M, N, D = omega.shape
+    log_q = torch.empty((M, N), dtype=torch.float64, device=omega.device)
+    rc = _lib.lib().tnf_base_logq(omega.data_ptr(), log_q.data_ptr(), M * N, D, _stream())
+    _lib.check(rc, "tnf_base_logq")
+    return log_q
+
+
+def finish_logq(log_q, ld_acc, scal=None, scal_div=1):
+    rows = log_q.numel()
+    ref = ld_acc if ld_acc is not None else scal
+    rc = _lib.lib().tnf_finish_logq(log_q.data_ptr(), _ptr(ld_acc), _ptr(scal), int(scal_div), rows,
+                                    _dt(ref) if ref is not None else TNF_F32, _stream())
+    _lib.check(rc, "tnf_finish_logq")
+    return log_q
