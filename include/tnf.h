@@ -83,6 +83,10 @@ int tnf_coupling_bwd(const void* z_in, const void* params, int64_t param_row_str
  * col_stats (or NULL): [2*D] doubles, accumulates sum and sum of squares of
  * the OUTPUT columns (the next BatchNorm's batch statistics, :401-410). */
 int tnf_tc_supported(int D, int U, int L);
+/* diagnostic: out[128 x N] = bf16(A[128 x K]) . bf16(W[K x N]) through the same
+ * weight image, UMMA descriptors and TMEM layouts as the fused kernel. */
+int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N,
+                         tnf_stream_t stream);
 size_t tnf_tc_packed_bytes(int D, int U, int L);
 int tnf_tc_pack(const float* params, void* packed, int D, int U, int L, int transform_upper,
                 tnf_stream_t stream);
@@ -130,9 +134,10 @@ int tnf_bn_bwd_apply(const void* g_y, const void* y, const void* alpha, const do
                      int dtype, tnf_stream_t stream);
 
 /* ---- ToInterval: replaces ToInterval.forward_and_log_det /
- * inverse_and_log_det (bijectors.py:509-557).  consts = 6*D floats
- * [tanh_flg | softplus_flg | tanh_m | tanh_c | softplus_m | softplus_c]
- * (the float32 constants the reference builds at :475-480). log_det (rows). */
+ * inverse_and_log_det (bijectors.py:509-557).  consts = 7*D floats
+ * [tanh_flg | softplus_flg | tanh_m | tanh_c | softplus_m | softplus_c | log(tanh_m)]
+ * (the float32 constants the reference builds at :475-480, plus the float32
+ * log(tanh_m) it evaluates at :515). log_det (rows). */
 int tnf_tointerval(const void* z_in, void* z_out, void* log_det, const float* consts,
                    int64_t rows, int D, int direction, int accum, int dtype, tnf_stream_t stream);
 int tnf_tointerval_bwd(const void* z_in, const float* consts, const void* g_z_out,

@@ -356,3 +356,37 @@ def param_net(x, weights):
         if i + 1 < len(weights):
             h = torch.tanh(h)
     return h
+
+
+# ---------------------------------------------------------------------------
+# bf16-conditioner emulation (checker for the tcgen05 path; not reference code)
+# ---------------------------------------------------------------------------
+def _bf16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def coupling_bf16_emulated(z, params, D, num_layers, num_units, transform_upper=True, inverse=False):
+    """Same layer as coupling_forward / coupling_inverse (bijectors.py:145-206) with
+    the conditioner's GEMM operands rounded to bf16 (weights, the conditioning
+    half and every tanh output) and fp32 accumulation, fp32 biases, fp32 affine
+    transform and log-det: what the tensor-core kernel computes, up to the
+    hardware tanh approximation and summation order."""
+    d_in, d_out = coupling_dims(D, transform_upper)
+    z1, z2 = _split(z, D, transform_upper)
+    M = params.shape[0]
+    U = num_units
+    sizes = [(d_in, U, True)] + [(U, U, True)] * (num_layers - 1) + [(U, d_out, False)]
+    t = s = _bf16(z1)
+    off = 0
+    for (K, J, act) in sizes:
+        Wt = _bf16(params[:, off:off + K * J].reshape(M, K, J)); off += K * J
+        Ws = _bf16(params[:, off:off + K * J].reshape(M, K, J)); off += K * J
+        bt = params[:, off:off + J].reshape(M, 1, J); off += J
+        bs = params[:, off:off + J].reshape(M, 1, J); off += J
+        t = torch.matmul(t, Wt) + bt
+        s = torch.matmul(s, Ws) + bs
+        if act:
+            t = _bf16(torch.tanh(t))
+            s = _bf16(torch.tanh(s))
+    z2 = (z2 - t) / torch.exp(s) if inverse else t + z2 * torch.exp(s)
+    return _join(z1, z2, transform_upper), torch.sum(s, dim=2)

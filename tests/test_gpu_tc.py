@@ -1,0 +1,108 @@
+"""GPU tests of the tcgen05 tensor-core coupling kernel (bf16 conditioner).
+
+Tolerances (stated): against the fp32 reference/oracle
+max|dz| <= 5e-2 and |d log_det| <= 2e-3*max(1,|.|)*layers-ish; against the
+bf16-emulating oracle (same operand rounding, exact tanh) the kernel must
+agree to ~1e-2, which separates rounding noise from layout bugs."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow_oracle as O
+import torch_nf_b200 as tnf
+import torch_nf_b200.density_estimator as de
+from torch_nf_b200 import _lib, ops
+from torch_nf_b200.synthetic import chain_spec, synthetic_params, synthetic_noise
+
+pytestmark = pytest.mark.gpu
+T = torch.tensor
+
+
+def _bf16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("K,N", [(16, 16), (32, 128), (32, 32), (64, 128), (256, 128), (256, 32), (128, 256), (256, 64)])
+def test_umma_selftest_gemm(K, N):
+    """One TMEM-A x SMEM-B UMMA GEMM through the kernel's own packing, descriptors and TMEM layouts."""
+    g = torch.Generator().manual_seed(K * 1000 + N)
+    A = torch.randn(128, K, generator=g)
+    W = torch.randn(K, N, generator=g) / np.sqrt(K)
+    out = torch.zeros(128, N, device="cuda")
+    Ad, Wd = A.cuda(), W.cuda()
+    rc = _lib.lib().tnf_tc_selftest_gemm(Ad.data_ptr(), Wd.data_ptr(), out.data_ptr(), K, N,
+                                         torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "tnf_tc_selftest_gemm")
+    torch.cuda.synchronize()
+    ref = _bf16(A).double() @ _bf16(W).double()
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 1e-4, "UMMA GEMM mismatch %g" % err
+
+
+@pytest.mark.parametrize("D,U,L,N", [(64, 256, 2, 128), (64, 256, 2, 1000), (64, 256, 1, 300), (64, 128, 2, 257),
+                                     (64, 64, 3, 129), (128, 256, 2, 384), (256, 256, 2, 200), (64, 256, 5, 140)])
+@pytest.mark.parametrize("upper", [True, False])
+def test_coupling_tc_vs_oracle(D, U, L, N, upper):
+    assert ops.tc_supported(D, U, L)
+    params = T(synthetic_params([("RealNVP", L, U, upper)], D, 1, seed=D + U + L))
+    z_in = T(synthetic_noise(1, N, D, seed=5).astype(np.float32))
+    packed = ops.tc_pack(params.cuda()[0], D, U, L, upper)
+    for inverse in (False, True):
+        direction = ops.TNF_INVERSE if inverse else ops.TNF_FORWARD
+        z, ld = ops.coupling_tc(z_in.cuda(), packed, D, U, L, upper, direction)
+        torch.cuda.synchronize()
+        z, ld = z.cpu(), ld.cpu().view(1, N)
+        ze, lde = O.coupling_bf16_emulated(z_in, params, D, L, U, upper, inverse)
+        zr, ldr = (O.coupling_inverse if inverse else O.coupling_forward)(z_in, params, D, L, U, upper)
+        h = D // 2
+        keep = slice(0, h) if upper else slice(h, D)
+        assert torch.equal(z[:, :, keep], z_in[:, :, keep])          # pass-through half bit-identical
+        assert (z - ze).abs().max().item() < 2e-2 * L, "vs bf16-emulated oracle"
+        assert (ld - lde).abs().max().item() < 2e-2 * L
+        assert (z - zr).abs().max().item() < 5e-2 * L, "vs fp32 oracle (stated bf16 tolerance)"
+        assert (ld - ldr).abs().max().item() < 5e-2 * L
+
+
+def test_coupling_tc_accum_and_preaffine():
+    D, U, L, N = 64, 256, 2, 515
+    params = T(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=9))
+    z_in = T(synthetic_noise(1, N, D, seed=6).astype(np.float32))
+    packed = ops.tc_pack(params.cuda()[0], D, U, L, True)
+    ps = (torch.rand(D) + 0.5).cuda()
+    pb = torch.randn(D).cuda()
+    base = torch.randn(N).cuda()
+    for accum, sign in ((ops.TNF_LD_ADD, 1.0), (ops.TNF_LD_SUB, -1.0)):
+        ld = base.clone()
+        z, _ = ops.coupling_tc(z_in.cuda(), packed, D, U, L, True, ops.TNF_FORWARD, ld=ld, accum=accum,
+                               pre_scale=ps, pre_shift=pb)
+        zin2 = z_in * ps.cpu() + pb.cpu()
+        ze, lde = O.coupling_bf16_emulated(zin2, params, D, L, U, True, False)
+        assert (z.cpu() - ze).abs().max().item() < 4e-2
+        assert (ld.cpu() - (base.cpu() + sign * lde.view(-1))).abs().max().item() < 4e-2
+
+
+def test_normflow_bf16_mode_c3(golden):
+    """Whole chain at the headline shape in bf16-conditioner mode vs the
+    reference's golden vectors, with the stated bf16 tolerance."""
+    g = golden("flow_c3")
+    D, stages, L, U, M, N, pseed, oseed = [int(v) for v in g["cfg"]]
+    nf = de.NormFlow(D, True, "coupling", stages, L, U)
+    params = T(synthetic_params(chain_spec(nf.bijectors), D, M, seed=pseed)).cuda()
+    np.random.seed(oseed)
+    omega = np.random.normal(0.0, 1.0, (M, N, D))
+    tnf.set_conditioner_precision("bf16")
+    try:
+        before = _lib.launch_count()
+        with torch.no_grad():
+            z, lq = nf.forward(params, N, omega=omega)
+            lp = nf.log_prob(T(g["z"]).cuda(), params)
+        assert _lib.launch_count() - before > 16
+    finally:
+        tnf.set_conditioner_precision("fp32")
+    dz = np.abs(z.cpu().numpy() - g["z"]).max()
+    dlq = np.abs(lq.cpu().numpy() - g["log_q_z"]) / np.maximum(1.0, np.abs(g["log_q_z"]))
+    dlp = np.abs(lp.cpu().numpy() - g["log_prob"]) / np.maximum(1.0, np.abs(g["log_prob"]))
+    assert dz <= 1e-1, dz                 # 8 coupling layers + BatchNorm amplification
+    assert dlq.max() <= 4e-3 and dlp.max() <= 4e-3, (dlq.max(), dlp.max())

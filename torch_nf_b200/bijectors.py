@@ -413,7 +413,8 @@ class ToInterval(Bijector):
         self.tanh_flg, self.softplus_flg = c32[0][None, None, :], c32[1][None, None, :]
         self.tanh_m, self.tanh_c = c32[2][None, None, :], c32[3][None, None, :]
         self.softplus_m, self.softplus_c = c32[4][None, None, :], c32[5][None, None, :]
-        self._consts_cpu = c32.contiguous()
+        # 7th row: log(tanh_m) in float32, evaluated once on the host exactly as the reference does (:515)
+        self._consts_cpu = torch.cat([c32, torch.log(c32[2])[None, :]], dim=0).contiguous()
         self._consts_dev = {}
 
     @property

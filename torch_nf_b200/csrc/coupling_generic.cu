@@ -395,10 +395,10 @@ extern "C" {
 int tnf_coupling(const void* z_in, void* z_out, void* log_det, const void* params, int64_t pstride, int64_t M,
                  int64_t N, int D, int U, int L, int transform_upper, int direction, int accum, int dtype,
                  tnf_stream_t stream) {
-  TNF_REQUIRE(z_in && z_out && log_det && params, TNF_ERR_ARG, "tnf_coupling: null pointer");
   int rc = validate("tnf_coupling", M, N, D, U, L);
   if (rc) return rc;
-  if (M == 0 || N == 0) return 0;
+  if (M == 0 || N == 0) return 0;  // empty batch: nothing to do, pointers may be null
+  TNF_REQUIRE(z_in && z_out && log_det && params, TNF_ERR_ARG, "tnf_coupling: null pointer");
   TNF_DISPATCH(dtype, return launch_fwd<T>(z_in, z_out, log_det, params, pstride, M, N, D, U, L, transform_upper != 0,
                                            direction, accum, (cudaStream_t)stream));
   return 0;
@@ -407,10 +407,10 @@ int tnf_coupling(const void* z_in, void* z_out, void* log_det, const void* param
 int tnf_coupling_bwd(const void* z_in, const void* params, int64_t pstride, const void* g_z_out,
                      const void* g_log_det, void* g_z_in, void* g_params, int64_t gstride, int64_t M, int64_t N, int D,
                      int U, int L, int transform_upper, int direction, int dtype, tnf_stream_t stream) {
-  TNF_REQUIRE(z_in && params && g_z_in && g_params, TNF_ERR_ARG, "tnf_coupling_bwd: null pointer");
   int rc = validate("tnf_coupling_bwd", M, N, D, U, L);
   if (rc) return rc;
   if (M == 0 || N == 0) return 0;
+  TNF_REQUIRE(z_in && params && g_z_in && g_params, TNF_ERR_ARG, "tnf_coupling_bwd: null pointer");
   TNF_DISPATCH(dtype, return launch_bwd<T>(z_in, params, pstride, g_z_out, g_log_det, g_z_in, g_params, gstride, M, N,
                                            D, U, L, transform_upper != 0, direction, (cudaStream_t)stream));
   return 0;

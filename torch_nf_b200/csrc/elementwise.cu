@@ -317,7 +317,7 @@ template <typename T, int G>
 __global__ void tointerval_kernel(const T* __restrict__ z_in, T* __restrict__ z_out, T* __restrict__ log_det,
                                   const float* __restrict__ c, int64_t rows, int D, int inverse, int accum) {
   const float *tanh_flg = c, *sp_flg = c + D, *tanh_m = c + 2 * D, *tanh_c = c + 3 * D, *sp_m = c + 4 * D,
-              *sp_c = c + 5 * D;
+              *sp_c = c + 5 * D, *log_m = c + 6 * D;
   const T eps = TiEps<T>::v();
   int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
   int lane = threadIdx.x % G;
@@ -331,7 +331,7 @@ __global__ void tointerval_kernel(const T* __restrict__ z_in, T* __restrict__ z_
         if (!inverse) {
           if (tanh_flg[d] != 0.f) {
             T th = t_tanh<T>(z);
-            ld += t_log<T>((T)tanh_m[d]) + t_log<T>(T(1) - th * th + eps);
+            ld += (T)log_m[d] + t_log<T>(T(1) - th * th + eps);
             z = add_rn(mul_rn((T)tanh_m[d], th), (T)tanh_c[d]);
           } else if (sp_flg[d] != 0.f) {
             ld += logsigmoid_t<T>(z);
@@ -345,7 +345,7 @@ __global__ void tointerval_kernel(const T* __restrict__ z_in, T* __restrict__ z_
             T x = (z - (T)tanh_c[d]) / (T)tanh_m[d];
             z = T(0.5) * (t_log<T>(T(1) + x + eps) - t_log<T>(T(1) - x + eps));
             T th = t_tanh<T>(z);
-            ld += t_log<T>((T)tanh_m[d]) + t_log<T>(T(1) - th * th + eps);
+            ld += (T)log_m[d] + t_log<T>(T(1) - th * th + eps);
           }
         }
         z_out[r * D + d] = z;
@@ -603,10 +603,10 @@ int64_t tnf_launch_count(void) { return tnf::g_launches.load(std::memory_order_r
 
 int tnf_affine(const void* z_in, void* z_out, void* log_det, const void* params, int64_t pstride, int64_t M,
                int64_t N, int D, int direction, int dtype, tnf_stream_t stream) {
-  TNF_REQUIRE(z_in && z_out && params, TNF_ERR_ARG, "tnf_affine: null pointer");
   TNF_REQUIRE(M >= 0 && N >= 0 && D >= 1, TNF_ERR_ARG, "tnf_affine: bad shape M=%lld N=%lld D=%d", (long long)M,
               (long long)N, D);
   if (M == 0 || N == 0) return 0;
+  TNF_REQUIRE(z_in && z_out && params, TNF_ERR_ARG, "tnf_affine: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (N <= 16) {
     TNF_DISPATCH(dtype, {
@@ -637,8 +637,8 @@ int tnf_affine(const void* z_in, void* z_out, void* log_det, const void* params,
 int tnf_affine_bwd(const void* z_in, const void* params, int64_t pstride, const void* g_z_out, const void* g_log_det,
                    void* g_z_in, void* g_params, int64_t gstride, int64_t M, int64_t N, int D, int direction,
                    int dtype, tnf_stream_t stream) {
-  TNF_REQUIRE(z_in && params && g_z_in && g_params, TNF_ERR_ARG, "tnf_affine_bwd: null pointer");
   if (M == 0 || N == 0) return 0;
+  TNF_REQUIRE(z_in && params && g_z_in && g_params, TNF_ERR_ARG, "tnf_affine_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   int nt = 256;
   int grid = (int)(M < (int64_t)num_sms() * 8 ? M : (int64_t)num_sms() * 8);
@@ -694,8 +694,8 @@ int tnf_bn_finalize(const double* sums, int D, double eps, void* mean, void* alp
 
 int tnf_bn_apply(const void* z_in, void* z_out, const void* mean, const void* alpha, int64_t rows, int D,
                  int direction, int dtype, tnf_stream_t stream) {
-  TNF_REQUIRE(z_in && z_out && mean && alpha, TNF_ERR_ARG, "tnf_bn_apply: null pointer");
   if (rows == 0) return 0;
+  TNF_REQUIRE(z_in && z_out && mean && alpha, TNF_ERR_ARG, "tnf_bn_apply: null pointer");
   int64_t n_el = rows * D;
   TNF_DISPATCH(dtype, {
     bn_apply_kernel<T><<<grid_for(n_el, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
@@ -706,8 +706,8 @@ int tnf_bn_apply(const void* z_in, void* z_out, const void* mean, const void* al
 
 int tnf_bn_bwd_apply(const void* g_y, const void* y, const void* alpha, const double* gsums, const void* g_log_det,
                      const double* count, void* g_z, int64_t rows, int D, int dtype, tnf_stream_t stream) {
-  TNF_REQUIRE(y && alpha && gsums && g_z && count, TNF_ERR_ARG, "tnf_bn_bwd_apply: null pointer");
   if (rows == 0) return 0;
+  TNF_REQUIRE(y && alpha && gsums && g_z && count, TNF_ERR_ARG, "tnf_bn_bwd_apply: null pointer");
   int64_t n_el = rows * D;
   TNF_DISPATCH(dtype, {
     bn_bwd_apply_kernel<T><<<grid_for(n_el, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
@@ -718,8 +718,8 @@ int tnf_bn_bwd_apply(const void* g_y, const void* y, const void* alpha, const do
 
 int tnf_tointerval(const void* z_in, void* z_out, void* log_det, const float* consts, int64_t rows, int D,
                    int direction, int accum, int dtype, tnf_stream_t stream) {
-  TNF_REQUIRE(z_in && z_out && log_det && consts, TNF_ERR_ARG, "tnf_tointerval: null pointer");
   if (rows == 0) return 0;
+  TNF_REQUIRE(z_in && z_out && log_det && consts, TNF_ERR_ARG, "tnf_tointerval: null pointer");
   TNF_DISPATCH(dtype, TNF_ROWGROUP(D, {
     tointerval_kernel<T, G><<<rowgroup_grid(rows, G), 256, 0, (cudaStream_t)stream>>>(
         (const T*)z_in, (T*)z_out, (T*)log_det, consts, rows, D, direction == TNF_INVERSE, accum);
@@ -729,8 +729,8 @@ int tnf_tointerval(const void* z_in, void* z_out, void* log_det, const float* co
 
 int tnf_tointerval_bwd(const void* z_in, const float* consts, const void* g_z_out, const void* g_log_det,
                        void* g_z_in, int64_t rows, int D, int direction, int dtype, tnf_stream_t stream) {
-  TNF_REQUIRE(z_in && consts && g_z_in, TNF_ERR_ARG, "tnf_tointerval_bwd: null pointer");
   if (rows == 0) return 0;
+  TNF_REQUIRE(z_in && consts && g_z_in, TNF_ERR_ARG, "tnf_tointerval_bwd: null pointer");
   TNF_DISPATCH(dtype, {
     tointerval_bwd_kernel<T, 1><<<grid_for(rows * D, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
         (const T*)z_in, consts, (const T*)g_z_out, (const T*)g_log_det, (T*)g_z_in, rows, D,
@@ -741,8 +741,8 @@ int tnf_tointerval_bwd(const void* z_in, const float* consts, const void* g_z_ou
 
 int tnf_tosimplex(const void* z_in, void* z_out, void* log_det, int64_t rows, int D_in, int D_attr, int accum,
                   int dtype, tnf_stream_t stream) {
-  TNF_REQUIRE(z_in && z_out && log_det, TNF_ERR_ARG, "tnf_tosimplex: null pointer");
   if (rows == 0) return 0;
+  TNF_REQUIRE(z_in && z_out && log_det, TNF_ERR_ARG, "tnf_tosimplex: null pointer");
   TNF_DISPATCH(dtype, TNF_ROWGROUP(D_in, {
     tosimplex_kernel<T, G><<<rowgroup_grid(rows, G), 256, 0, (cudaStream_t)stream>>>(
         (const T*)z_in, (T*)z_out, (T*)log_det, rows, D_in, D_attr, accum);
@@ -752,8 +752,8 @@ int tnf_tosimplex(const void* z_in, void* z_out, void* log_det, int64_t rows, in
 
 int tnf_tosimplex_bwd(const void* z_in, const void* g_z_out, const void* g_log_det, void* g_z_in, int64_t rows,
                       int D_in, int D_attr, int dtype, tnf_stream_t stream) {
-  TNF_REQUIRE(z_in && g_z_in, TNF_ERR_ARG, "tnf_tosimplex_bwd: null pointer");
   if (rows == 0) return 0;
+  TNF_REQUIRE(z_in && g_z_in, TNF_ERR_ARG, "tnf_tosimplex_bwd: null pointer");
   TNF_DISPATCH(dtype, TNF_ROWGROUP(D_in, {
     tosimplex_bwd_kernel<T, G><<<rowgroup_grid(rows, G), 256, 0, (cudaStream_t)stream>>>(
         (const T*)z_in, (const T*)g_z_out, (const T*)g_log_det, (T*)g_z_in, rows, D_in, D_attr);
@@ -773,9 +773,9 @@ int tnf_accum_bcast(void* dst, const void* src, int64_t n_dst, int64_t div, int 
 
 int tnf_base_logprob(const void* z, const void* sub, const void* scal, int64_t scal_div, void* out, int64_t rows,
                      int D, int dtype, tnf_stream_t stream) {
-  TNF_REQUIRE(z && out, TNF_ERR_ARG, "tnf_base_logprob: null pointer");
   TNF_REQUIRE(!scal || scal_div >= 1, TNF_ERR_ARG, "tnf_base_logprob: scal_div must be >= 1");
   if (rows == 0) return 0;
+  TNF_REQUIRE(z && out, TNF_ERR_ARG, "tnf_base_logprob: null pointer");
   TNF_DISPATCH(dtype, TNF_ROWGROUP(D, {
     base_logprob_kernel<T, G><<<rowgroup_grid(rows, G), 256, 0, (cudaStream_t)stream>>>(
         (const T*)z, (const T*)sub, (const T*)scal, scal_div, (T*)out, rows, D);
@@ -785,8 +785,8 @@ int tnf_base_logprob(const void* z, const void* sub, const void* scal, int64_t s
 
 int tnf_base_logprob_bwd(const void* z, const void* g_out, void* g_z, int64_t rows, int D, int dtype,
                          tnf_stream_t stream) {
-  TNF_REQUIRE(z && g_out && g_z, TNF_ERR_ARG, "tnf_base_logprob_bwd: null pointer");
   if (rows == 0) return 0;
+  TNF_REQUIRE(z && g_out && g_z, TNF_ERR_ARG, "tnf_base_logprob_bwd: null pointer");
   TNF_DISPATCH(dtype, {
     base_logprob_bwd_kernel<T><<<grid_for(rows * D, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
         (const T*)z, (const T*)g_out, (T*)g_z, rows * D, D);
@@ -796,9 +796,9 @@ int tnf_base_logprob_bwd(const void* z, const void* g_out, void* g_z, int64_t ro
 
 int tnf_base_sample(float* z, double* log_q, int64_t rows, int D, uint64_t seed, uint64_t offset,
                     tnf_stream_t stream) {
-  TNF_REQUIRE(z && log_q, TNF_ERR_ARG, "tnf_base_sample: null pointer");
   TNF_REQUIRE(((uintptr_t)z & 15) == 0, TNF_ERR_ALIGN, "tnf_base_sample: z must be 16-byte aligned");
   if (rows == 0) return 0;
+  TNF_REQUIRE(z && log_q, TNF_ERR_ARG, "tnf_base_sample: null pointer");
   int64_t n_el = rows * D;
   base_sample_kernel<<<grid_for((n_el + 3) / 4, 256 * 2), 256, 0, (cudaStream_t)stream>>>(z, n_el, seed, offset);
   int rc = check_launch("tnf_base_sample");
@@ -807,8 +807,8 @@ int tnf_base_sample(float* z, double* log_q, int64_t rows, int D, uint64_t seed,
 }
 
 int tnf_base_logq(const float* omega, double* log_q, int64_t rows, int D, tnf_stream_t stream) {
-  TNF_REQUIRE(omega && log_q, TNF_ERR_ARG, "tnf_base_logq: null pointer");
   if (rows == 0) return 0;
+  TNF_REQUIRE(omega && log_q, TNF_ERR_ARG, "tnf_base_logq: null pointer");
   TNF_ROWGROUP(D, {
     base_logq_kernel<G><<<rowgroup_grid(rows, G), 256, 0, (cudaStream_t)stream>>>(omega, log_q, rows, D);
   });
@@ -817,9 +817,9 @@ int tnf_base_logq(const float* omega, double* log_q, int64_t rows, int D, tnf_st
 
 int tnf_finish_logq(double* log_q, const void* ld_acc, const void* scal, int64_t scal_div, int64_t rows, int dtype,
                     tnf_stream_t stream) {
-  TNF_REQUIRE(log_q, TNF_ERR_ARG, "tnf_finish_logq: null pointer");
   TNF_REQUIRE(!scal || scal_div >= 1, TNF_ERR_ARG, "tnf_finish_logq: scal_div must be >= 1");
   if (rows == 0) return 0;
+  TNF_REQUIRE(log_q, TNF_ERR_ARG, "tnf_finish_logq: null pointer");
   TNF_DISPATCH(dtype, {
     finish_logq_kernel<T><<<grid_for(rows, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
         log_q, (const T*)ld_acc, (const T*)scal, scal_div, rows);
