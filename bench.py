@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Headline benchmark: flow log_prob+sample samples/sec at D=64, 8 coupling layers.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one batch: ``NormFlow.forward``
+(draw base noise, run the chain, accumulate the log-density) followed by
+``NormFlow.log_prob`` on the samples just produced, for the configuration
+BASELINE.json quotes the metric on: ``NormFlow(64, False, 'coupling', 4, 2, 256)``
+(C3: D=64, 8 RealNVP layers with 256-wide 2-layer conditioners, 8 BatchNorm, 4
+Affine), batch 2^20 per GPU (weak scaling; BatchNorm statistics are all-reduced
+so every rank normalises with the global batch).  Prints ONE JSON line.
+
+`value`   device-resident throughput (weights and samples stay in HBM),
+          conditioner GEMMs in bf16 on tcgen05 (dtype "bf16"; affine transform,
+          log-det and BatchNorm in fp32).
+`e2e`     the same step through the public API with HOST tensors (pinned):
+          parameters and samples cross PCIe inside the timed region.
+`--impl reference`  times the reference's CPU algorithm (the oracle port, torch
+          CPU ops on all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, STAGES, L, U = 64, 4, 2, 256
+N_LAYERS = 2 * STAGES
+BATCH_PER_GPU = 1 << 20
+FLOP_PER_SAMPLE_LAYER = 4 * (32 * U + (L - 1) * U * U + U * 32)       # 327 680
+BYTES_PER_SAMPLE_LAYER = 2 * D * 4 + 8                                 # 520
+METRIC = "flow log_prob+sample samples/sec at D=64,L=8"
+WORKLOAD = "C3: NormFlow(64,False,'coupling',4,2,256) sample(N)+log_prob, batch 2^20 per GPU"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(source="measured", tflops_burst=p["bf16_tflops"], tflops_sustained=p["bf16_tflops_sustained"],
+                    hbm_gbs=p["hbm_gbs"])
+    return dict(source="fallback", tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        # under load = the upper half of the samples (the sampler also sees the idle edges)
+        hot = sorted(sm)[len(sm) // 2:]
+        return dict(sm_mhz=statistics.median(hot), sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+def cpu_port_throughput(n_rows, repeats, threads):
+    """The reference's CPU algorithm (oracle port) on `n_rows` samples of the same
+    workload: one forward (incl. the reference's host numpy draw and float64 base
+    density) + one log_prob.  Returns (best samples/s, seconds of the best pass)."""
+    import numpy as np
+    import torch
+    from oracle import flow_oracle as O
+    from torch_nf_b200.synthetic import synthetic_params
+    torch.set_num_threads(threads)
+    chain = O.build_chain(D, "coupling", STAGES, L, U)
+    spec = [(b["kind"], b.get("L", 0), b.get("U", 0), b.get("upper", False)) for b in chain]
+    params = torch.tensor(synthetic_params(spec, D, 1, seed=0))
+    best = None
+    with torch.no_grad():
+        for i in range(repeats + 1):            # first pass is the warm-up
+            t0 = time.perf_counter()
+            omega = np.random.normal(0.0, 1.0, (1, n_rows, D))     # density_estimator.py:366
+            z, lq, st = O.normflow_forward(chain, D, params, omega)
+            lp = O.normflow_log_prob(chain, D, z, params, st)
+            dt = time.perf_counter() - t0
+            if i > 0 and (best is None or dt < best):
+                best = dt
+    assert torch.isfinite(lp).all()
+    return n_rows / best, best
+
+
+def run_reference(args):
+    """Reference arm: rank 0 only, host cores only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    n_rows = 1 << 14
+    import numpy as np
+    from oracle import flow_oracle as O
+    from torch_nf_b200.synthetic import synthetic_params
+    torch.set_num_threads(threads)
+    chain = O.build_chain(D, "coupling", STAGES, L, U)
+    spec = [(b["kind"], b.get("L", 0), b.get("U", 0), b.get("upper", False)) for b in chain]
+    params = torch.tensor(synthetic_params(spec, D, 1, seed=0))
+
+    def step():
+        omega = np.random.normal(0.0, 1.0, (1, n_rows, D))
+        z, lq, st = O.normflow_forward(chain, D, params, omega)
+        return O.normflow_log_prob(chain, D, z, params, st)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+    value = n_rows * args.steps / dt
+    sample = "%d of 2^20 rows per step, torch CPU ops, %d threads" % (n_rows, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_sample_rows_per_step": n_rows},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="samples per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as td
+    import torch_nf_b200 as tnf
+    import torch_nf_b200.density_estimator as de
+    from torch_nf_b200 import _lib, dist, ops
+    from torch_nf_b200.synthetic import chain_spec, synthetic_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+        dist.enable()
+    tnf.set_conditioner_precision(args.precision)
+    _lib.lib()
+
+    B = args.batch
+    nf = de.NormFlow(D, True, "coupling", STAGES, L, U)
+    params_host = torch.tensor(synthetic_params(chain_spec(nf.bijectors), D, 1, seed=0)).pin_memory()
+    params = params_host.to(dev)
+    np.random.seed(1234 + rank)          # per-rank Philox sub-stream
+
+    def step_resident():
+        z, lq = nf.forward(params, B)
+        lp = nf.log_prob(z, params)
+        return z, lq, lp
+
+    def step_host():
+        z, lq = nf.forward(params_host, B)            # CPU tensors in, CPU (pinned) tensors out
+        lp = nf.log_prob(z, params_host)
+        return z, lq, lp
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, timer=None):
+        with torch.no_grad():
+            for _ in range(warmup):
+                out = fn()
+            barrier()
+            if timer is not None:
+                ops.kernel_timer = timer
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = _lib.launch_count()
+            e0.record()
+            for _ in range(steps):
+                out = fn()
+            e1.record()
+            barrier()
+            ops.kernel_timer = None
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, _lib.launch_count() - l0, out
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    timer = []
+    ms, launches, out = timed(step_resident, args.steps, args.warmup, timer)
+    clock_info = clocks.stop() if rank == 0 else None
+    z, lq, lp = out
+    finite = bool(torch.isfinite(lp).all().item())
+    # size-independent property at full size: log_prob(sample) == the sampler's own log-density
+    consistency = float((lq.float() - lp).abs().max().item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # dominant kernel: CUDA events recorded around every tensor-core coupling launch of the timed region
+    kern_ms = [a.elapsed_time(b) for (a, b) in timer]
+    pk = peaks()
+    roofline = None
+    if kern_ms:
+        avg = sum(kern_ms) / len(kern_ms)
+        achieved = FLOP_PER_SAMPLE_LAYER * B / (avg * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "tc_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
+                    "kernel": "coupling_tc_kernel", "launches_timed": len(kern_ms), "avg_launch_ms": avg,
+                    "peak_source": pk["source"] + " (sustained bf16 GEMM; burst %.1f -> frac %.3f)" % (
+                        pk["tflops_burst"], achieved / pk["tflops_burst"]),
+                    "kernel_share_of_step": sum(kern_ms) / ms,
+                    "hbm_gbs_at_algorithmic_bytes": BYTES_PER_SAMPLE_LAYER * B / (avg * 1e-3) / 1e9}
+
+    e2e = None
+    if not args.no_e2e:
+        e_steps = max(2, min(args.steps, 5))
+        ms_h, _, out_h = timed(step_host, e_steps, 1)
+        zh, lqh, lph = out_h
+        assert not zh.is_cuda and not lph.is_cuda
+        h2d = 2 * params_host.numel() * 4 + zh.numel() * 4
+        d2h = zh.numel() * 4 + lqh.numel() * 8 + lph.numel() * 4
+        e2e = {"value": world * B * e_steps / (ms_h * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_h / e_steps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        v, secs = cpu_port_throughput(1 << 14, 3, threads)
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": "2^14 of 2^20 rows, 1 warm-up + best of 3 (%.2f s/pass), oracle port on torch CPU ops" % secs}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "l2": "inputs_larger_than_l2 (z = 268 MB per pass)",
+                       "parallelism": "dp%d over sample rows" % world, "weights": "fan-in scaled synthetic, seed 0",
+                       "noise": "device Philox4x32-10"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
+            "clocks": clock_info,
+            "checks": {"finite": finite, "max_abs_logq_minus_logprob": consistency},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

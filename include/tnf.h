@@ -74,7 +74,8 @@ int tnf_coupling_bwd(const void* z_in, const void* params, int64_t param_row_str
 /* ---- RealNVP coupling layer, tcgen05 tensor-core path (bf16 conditioner) --
  * Same math as tnf_coupling for shared weights (regime A: one parameter row),
  * fp32 z / log_det, conditioner GEMMs in bf16 on tcgen05 with fp32 TMEM
- * accumulation, affine transform and log-det in fp32.
+ * accumulation, affine transform and log-det in fp32.  D in {64,128,256},
+ * U in {64,128,256}, 1 <= L <= 5 (tnf_tc_supported).
  * Weights are repacked once per parameter update by tnf_tc_pack (fp32 flat
  * params -> bf16 UMMA operand images + fp32 biases).
  * pre_scale/pre_shift (D floats each, or NULL): per-column affine
@@ -84,8 +85,9 @@ int tnf_coupling_bwd(const void* z_in, const void* params, int64_t param_row_str
  * the OUTPUT columns (the next BatchNorm's batch statistics, :401-410). */
 int tnf_tc_supported(int D, int U, int L);
 /* diagnostic: out[128 x N] = bf16(A[128 x K]) . bf16(W[K x N]) through the same
- * weight image, UMMA descriptors and TMEM layouts as the fused kernel. */
-int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N,
+ * operand images, UMMA descriptors and TMEM accumulator layout as the fused
+ * kernel; a_in_tmem selects the A operand source (1: TMEM, 0: SMEM image). */
+int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N, int a_in_tmem,
                          tnf_stream_t stream);
 size_t tnf_tc_packed_bytes(int D, int U, int L);
 int tnf_tc_pack(const float* params, void* packed, int D, int U, int L, int transform_upper,

@@ -204,7 +204,9 @@ def test_ToInterval(golden):
     ti = ToInterval(6, g["ti_lb"], g["ti_ub"])
     for tag, tol in (("f64", 1e-11), ("f32", 5e-6)):
         z, ld = ti(T(g["ti_%s_z_in" % tag]))
-        close(z, g["ti_%s_z_fwd" % tag], tol, tol); close(ld, g["ti_%s_ld" % tag], tol, tol * 4)
+        # fp32 log(1 - tanh(z)^2 + eps) cancels catastrophically for |z| >~ 4: a 1-ulp tanh difference
+        # moves the log-det by ~1e-4 there (the reference has the same conditioning)
+        close(z, g["ti_%s_z_fwd" % tag], tol, tol); close(ld, g["ti_%s_ld" % tag], tol, tol * 4 if tag == "f64" else 3e-4)
         zi, ldi = ti.inverse_and_log_det(T(g["ti_%s_z_fwd" % tag]))
         zr, lr = g["ti_%s_z_inv" % tag], g["ti_%s_ld_inv" % tag]
         if tag == "f64":

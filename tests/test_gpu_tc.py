@@ -24,15 +24,16 @@ def _bf16(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
-@pytest.mark.parametrize("K,N", [(16, 16), (32, 128), (32, 32), (64, 128), (256, 128), (256, 32), (128, 256), (256, 64)])
-def test_umma_selftest_gemm(K, N):
-    """One TMEM-A x SMEM-B UMMA GEMM through the kernel's own packing, descriptors and TMEM layouts."""
+@pytest.mark.parametrize("a_in_tmem", [0, 1])
+@pytest.mark.parametrize("K,N", [(16, 16), (32, 256), (32, 32), (64, 128), (256, 256), (256, 32), (128, 256), (256, 64)])
+def test_umma_selftest_gemm(K, N, a_in_tmem):
+    """One UMMA GEMM (A from SMEM image or from TMEM) through the kernel's own packing, descriptors and TMEM layouts."""
     g = torch.Generator().manual_seed(K * 1000 + N)
     A = torch.randn(128, K, generator=g)
     W = torch.randn(K, N, generator=g) / np.sqrt(K)
     out = torch.zeros(128, N, device="cuda")
     Ad, Wd = A.cuda(), W.cuda()
-    rc = _lib.lib().tnf_tc_selftest_gemm(Ad.data_ptr(), Wd.data_ptr(), out.data_ptr(), K, N,
+    rc = _lib.lib().tnf_tc_selftest_gemm(Ad.data_ptr(), Wd.data_ptr(), out.data_ptr(), K, N, a_in_tmem,
                                          torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "tnf_tc_selftest_gemm")
     torch.cuda.synchronize()

@@ -31,7 +31,7 @@ def _stage(z, params=None):
 
 
 def _home(t, home):
-    return t if t.device == home else t.to(home)
+    return ops.to_like(t, home)
 
 
 class Bijector(object):

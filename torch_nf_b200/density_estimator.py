@@ -383,4 +383,4 @@ class _BaseLogProbFn(torch.autograd.Function):
 
 
 def _to(t, device):
-    return t if t.device == device else t.to(device)
+    return ops.to_like(t, device)

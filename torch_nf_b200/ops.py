@@ -31,6 +31,32 @@ def to_device(t, dtype=None):
     return t
 
 
+def to_host(t):
+    """Device -> host through pinned memory (PyTorch's caching host allocator
+    recycles the pinned blocks, so steady-state calls do not re-pin)."""
+    if not t.is_cuda:
+        return t
+    if t.requires_grad:            # keep the autograd edge for differentiable results
+        return t.cpu()
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out
+
+
+def to_like(t, device):
+    if t.device == device:
+        return t
+    if device.type == "cpu":
+        return to_host(t)
+    return t.to(device)
+
+
+# bench.py hook: when set to a list, (start, end) CUDA events are recorded around
+# every tensor-core coupling launch on the launching stream.
+kernel_timer = None
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -137,9 +163,16 @@ def coupling_tc(z, packed, D, U, L, upper, direction, ld=None, accum=TNF_LD_WRIT
     if ld is None:
         ld = torch.empty(rows, dtype=torch.float32, device=z.device)
         accum = TNF_LD_WRITE
+    timer = kernel_timer
+    if timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = _lib.lib().tnf_coupling_tc(z2.data_ptr(), z_out.data_ptr(), ld.data_ptr(), packed.data_ptr(), rows, D, U, L,
                                     int(upper), direction, accum, _ptr(pre_scale), _ptr(pre_shift), _ptr(col_stats),
                                     _stream())
+    if timer is not None:
+        e1.record()
+        timer.append((e0, e1))
     _lib.check(rc, "tnf_coupling_tc")
     return z_out.view(z.shape), ld
 
