@@ -87,6 +87,9 @@ int tnf_tc_supported(int D, int U, int L);
 /* diagnostic: out[128 x N] = bf16(A[128 x K]) . bf16(W[K x N]) through the same
  * operand images, UMMA descriptors and TMEM accumulator layout as the fused
  * kernel; a_in_tmem selects the A operand source (1: TMEM, 0: SMEM image). */
+/* diagnostic: when set to a device buffer of 2048 int64, CTA 0 of tnf_coupling_tc records
+ * (tag, clock64) stamps of its epilogue phases (group g at offset 512*g*2); NULL disables. */
+void tnf_tc_set_debug(void* dev_buffer);
 int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N, int a_in_tmem,
                          tnf_stream_t stream);
 size_t tnf_tc_packed_bytes(int D, int U, int L);

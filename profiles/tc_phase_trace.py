@@ -1,0 +1,41 @@
+"""Per-phase cycle trace of the tensor-core coupling kernel (CTA 0, lane 0 of each epilogue group).
+Run on the GPU box:  python profiles/tc_phase_trace.py"""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from torch_nf_b200 import _lib, ops
+from torch_nf_b200.synthetic import synthetic_params
+
+D, U, L, N = 64, 256, 2, 1 << 20
+params = torch.tensor(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=0)).cuda()
+packed = ops.tc_pack(params[0], D, U, L, True)
+z = torch.randn(1, N, D, device="cuda")
+for _ in range(3):
+    ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)
+dbg = torch.zeros(2048, dtype=torch.int64, device="cuda")
+_lib.lib().tnf_tc_set_debug(dbg.data_ptr())
+ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)
+torch.cuda.synchronize()
+_lib.lib().tnf_tc_set_debug(None)
+raw = dbg.cpu().numpy()
+print("MMA warp (CTA 0): cycles waiting on epilogue %d, on weights %d, total %d" % (raw[2040], raw[2041], raw[2042]))
+d = raw.reshape(2, 512, 2)  # group g at int64 offset 1024*g
+names = {100: "tile start", 101: "A1 published", 600: "tile end", 601: "y computed", 602: "next A1 published"}
+for g in range(2):
+    ev = [(int(t), int(c)) for t, c in d[g] if t != 0]
+    if not ev:
+        continue
+    t0 = ev[0][1]
+    print("group", g, "events", len(ev))
+    prev = t0
+    for i, (t, c) in enumerate(ev[40:72]):
+        nm = names.get(t) or ("wait H net%d l%d" % ((t - 200) // 10, (t - 200) % 10) if 200 <= t < 300 else
+                              "got  H net%d l%d" % ((t - 300) // 10, (t - 300) % 10) if 300 <= t < 400 else
+                              "wait F net%d" % (t - 400) if 400 <= t < 500 else "got  F net%d" % (t - 500))
+        print("  %8d  +%6d  %s" % (c - t0, c - prev, nm))
+        prev = c
+    # per-tile totals
+    starts = [c for t, c in ev if t == 100]
+    if len(starts) > 2:
+        print("  cycles per tile (steady):", np.diff(starts)[1:].mean())

@@ -16,15 +16,15 @@
 // through a ring of 16 KB stages by one producer warp (cp.async.bulk + mbarrier
 // complete_tx).
 //
-// The two nets are independent, so they ping-pong: while the epilogue warps turn
-// H_t of layer l into the next A_t, the tensor pipe computes H_s of layer l (and
-// vice versa).  TMEM: H_t = columns [0,256), H_s = [256,512); the final t / s
-// outputs reuse the first columns of their own region.
+// Tile ping-pong: the 8 epilogue warps form two groups of 4 (one warp per TMEM
+// lane quadrant); each group owns a tile, 256 TMEM columns for its accumulator
+// and its own A images.  The MMA warp serves the two groups alternately in a
+// static order, so while one group runs its MUFU-bound tanh epilogue (or waits
+// on HBM), the tensor pipe computes the other group's next layer.
 //
-// Warp roles (320 threads): warps 0-7 epilogue (warp w owns TMEM lane quadrant
-// w%4, i.e. rows 32*(w%4)..+31 of the tile, and the 32-column chunks c with
-// c%2 == w/4); warp 8 MMA issuer (warp-uniform control flow, one elected lane
-// issues); warp 9 weight producer.
+// Warp roles (320 threads): warps 0-7 epilogue (group = w/4, rows 32*(w%4)..+31
+// of the group's tile, thread = one sample row); warp 8 MMA issuer (warp-uniform
+// control flow, one elected lane issues); warp 9 weight producer.
 //
 // Reference semantics: torch_nf/bijectors.py:145-242 (RealNVP).
 #include <cuda_bf16.h>
@@ -45,17 +45,26 @@ constexpr int kChunk = 32;  // accumulator columns handled per epilogue step
 struct Shape {
   int D, U, L, upper;
   int d_in, d_out, c_off, t_off;
+  int Nh, nh;  // hidden layers are issued as nh column blocks of width Nh
   __host__ __device__ Shape(int D_, int U_, int L_, int upper_) : D(D_), U(U_), L(L_), upper(upper_) {
     int h = D / 2;
     d_in = h; d_out = h;
     c_off = upper ? 0 : h;
     t_off = upper ? h : 0;
+    // Full-width jobs: splitting a layer into column halves would let the epilogue of the low half
+    // overwrite the (single) A image while the high-half MMAs still read it.
+    Nh = U;
+    nh = 1;
   }
   __host__ __device__ int K_of(int l) const { return l == 0 ? d_in : U; }
   __host__ __device__ int J_of(int l) const { return l == L ? d_out : U; }
-  // K rows of one weight stage for an N-wide layer (a stage never exceeds 16 KB)
-  __host__ __device__ static int stage_k(int K, int N) {
-    int ks = kStageElems / N;
+  __host__ __device__ int N_of(int l) const { return l == L ? d_out : Nh; }      // MMA N of one job
+  __host__ __device__ int halves(int l) const { return l == L ? 1 : nh; }
+  // weight stage capacity: 16 KB, or 8 KB when the A images leave too little shared memory (D = 256, U = 256)
+  __host__ __device__ int stage_elems() const { return (D >= 256 && U >= 256) ? kStageElems / 2 : kStageElems; }
+  // K rows of one weight stage for an N-wide layer
+  __host__ __device__ int stage_k(int K, int N) const {
+    int ks = stage_elems() / N;
     return ks < K ? ks : K;
   }
   __host__ __device__ int64_t net_weight_elems() const {
@@ -218,7 +227,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 // ---------------------------------------------------------------- weight packing
 // Packed buffer = the weight stream in consumption order:
-//   for layer l in 0..L: for net in {t, s}: for stage s: image of stage_k(K,N) x N bf16 (see img_off, rows = N)
+//   for layer l in 0..L: for net in {t, s}: for column half hb: for stage s:
+//     image of stage_k(K,N) x N bf16 (N = N_of(l); see img_off, rows = N)
 // followed by the fp32 biases [net][layer][unit].
 __global__ void pack_kernel(const float* __restrict__ params, unsigned char* __restrict__ packed, Shape sh) {
   const int64_t per_net = sh.net_weight_elems();
@@ -237,15 +247,17 @@ __global__ void pack_kernel(const float* __restrict__ params, unsigned char* __r
       src_off += 2 * n_el + 2 * sh.J_of(l);
       dst_off += 2 * n_el;
     }
-    const int K = sh.K_of(l), N = sh.J_of(l);
-    const int64_t n_el = (int64_t)K * N;
+    const int K = sh.K_of(l), J = sh.J_of(l), N = sh.N_of(l);
+    const int64_t n_el = (int64_t)K * J;
     const int net = rem >= n_el;
     rem -= net * n_el;
-    const int k = (int)(rem / N), j = (int)(rem % N);
-    const float w = params[src_off + net * n_el + rem];   // W_t then W_s, (K, N) row-major, x @ W
-    const int ks = Shape::stage_k(K, N);
+    const int k = (int)(rem / J), j = (int)(rem % J);
+    const float w = params[src_off + net * n_el + rem];   // W_t then W_s, (K, J) row-major, x @ W
+    const int hb = j / N, n = j % N;
+    const int ks = sh.stage_k(K, N);
     const int st = k / ks, kk = k % ks;
-    unsigned char* dst = packed + (dst_off + net * n_el + (int64_t)st * ks * N) * 2 + img_off(j, kk, N);
+    unsigned char* dst =
+        packed + (dst_off + net * n_el + (int64_t)hb * K * N + (int64_t)st * ks * N) * 2 + img_off(n, kk, N);
     *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(w);
   }
   const int nb = sh.net_bias_elems();
@@ -271,35 +283,46 @@ struct Args {
   const float* pre_scale; const float* pre_shift;
   int64_t rows;
   int D, U, L, upper, inverse, accum, n_stages;
+  long long* dbg;   // diagnostics: per-phase clock64 stamps of CTA 0 (NULL = off)
 };
 
 struct __align__(16) Ctrl {
   uint64_t w_full[kMaxStages];
   uint64_t w_empty[kMaxStages];
-  uint64_t a1_ready;     // 8 epilogue warps: A1 image written (and last tile's outputs drained)
-  uint64_t e_done[2];    // 8 epilogue warps: net's accumulator drained and next A image written
-  uint64_t h_ready[2];   // MMA commit: net's accumulator complete
+  uint64_t a1_ready[2];  // per group, 4 epilogue warps: A1 image written, last tile's outputs drained
+  uint64_t e_done[2];    // per group, 4 epilogue warps: accumulator drained (and next A image written)
+  uint64_t h_ready[2][2];  // per group and column half, MMA commit: accumulator (half) complete
   uint32_t tmem_base;
   uint32_t pad;
-  float ld_xchg[kTileM];
 };
-// dynamic shared memory: [ring: n_stages x 16 KB][A1][A_t][A_s][Ctrl][bias 2 x nb][pre_scale D][pre_shift D]
+// dynamic shared memory:
+//   [ring: n_stages x 16 KB][A1 g0][A1 g1][Act g0][Act g1][Ctrl][bias 2 x nb][pre_scale D][pre_shift D]
 
 __host__ __device__ inline size_t smem_bytes(const Shape& sh, int n_stages) {
-  return (size_t)n_stages * kStageBytes + sh.a1_bytes() + 2 * sh.act_bytes() + sizeof(Ctrl) +
+  return (size_t)n_stages * sh.stage_elems() * 2 + 2 * sh.a1_bytes() + 2 * sh.act_bytes() + sizeof(Ctrl) +
          (size_t)(2 * sh.net_bias_elems() + 2 * sh.D) * sizeof(float);
 }
 
+__device__ __forceinline__ float exp2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Tile ping-pong: epilogue group g (warps 4g..4g+3, one warp per TMEM lane quadrant) owns tile
+// (2*it+g)*grid + cta of every iteration, TMEM columns [256g, 256g+256) and the A images of group g.
+// The MMA warp issues the GEMMs in the static order  for net: for layer: for group  so that while one
+// group runs its MUFU-bound epilogue the tensor pipe works for the other group.
 template <bool kInverse, int DH>   // DH = D/2 = d_in = d_out
 __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Shape sh(a.D, a.U, a.L, a.upper);
   const int S = a.n_stages;
   unsigned char* ring = smem_raw;
-  unsigned char* sA1 = ring + (size_t)S * kStageBytes;
-  unsigned char* sAct0 = sA1 + sh.a1_bytes();
-  unsigned char* sAct1 = sAct0 + sh.act_bytes();
-  Ctrl& ct = *reinterpret_cast<Ctrl*>(sAct1 + sh.act_bytes());
+  const uint32_t stage_bytes = (uint32_t)sh.stage_elems() * 2;
+  unsigned char* sA1 = ring + (size_t)S * stage_bytes;           // 2 images
+  unsigned char* sAct = sA1 + 2 * sh.a1_bytes();                  // 2 images
+  Ctrl& ct = *reinterpret_cast<Ctrl*>(sAct + 2 * sh.act_bytes());
   float* s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl));
   const int nb = sh.net_bias_elems();
   float* s_pscale = s_bias + 2 * nb;
@@ -307,16 +330,18 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
+  const int64_t iters = (n_tiles + 2 * (int64_t)gridDim.x - 1) / (2 * (int64_t)gridDim.x);
   const int64_t weight_bytes = 2 * sh.net_weight_elems() * 2;
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&ct.w_full[i], 1); mbar_init(&ct.w_empty[i], 1); }
-    mbar_init(&ct.a1_ready, kEpiWarps);
-    mbar_init(&ct.e_done[0], kEpiWarps);
-    mbar_init(&ct.e_done[1], kEpiWarps);
-    mbar_init(&ct.h_ready[0], 1);
-    mbar_init(&ct.h_ready[1], 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&ct.a1_ready[g], 4);
+      mbar_init(&ct.e_done[g], 4);
+      mbar_init(&ct.h_ready[g][0], 1);
+      mbar_init(&ct.h_ready[g][1], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kEpiWarps) tmem_alloc(&ct.tmem_base, 512);
@@ -332,24 +357,28 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ct.tmem_base;
-
   if (warp == kEpiWarps + 1) {
     // =============================== weight producer (one elected lane) ===============================
     if (elect_one()) {
       uint32_t slot = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned char* src = a.packed;
-        for (int l = 0; l <= sh.L; ++l) {
-          const int K = sh.K_of(l), N = sh.J_of(l);
-          const int ks = Shape::stage_k(K, N);
-          const uint32_t bytes = (uint32_t)(ks * N * 2);
-          const int n_st = 2 * (K / ks);   // both nets
-          for (int s = 0; s < n_st; ++s) {
-            mbar_wait(&ct.w_empty[slot], phase ^ 1);
-            mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
-            bulk_g2s(ring + (size_t)slot * kStageBytes, src, bytes, &ct.w_full[slot]);
-            src += bytes;
-            if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+      for (int64_t it = 0; it < iters; ++it) {
+        for (int net = 0; net < 2; ++net) {
+          const unsigned char* lsrc = a.packed;
+          for (int l = 0; l <= sh.L; ++l) {
+            const int K = sh.K_of(l), J = sh.J_of(l), N = sh.N_of(l);
+            const int ks = sh.stage_k(K, N);
+            const uint32_t bytes = (uint32_t)(ks * N * 2);
+            const int n_st = sh.halves(l) * (K / ks);
+            const unsigned char* nsrc = lsrc + (size_t)net * K * J * 2;
+            for (int g = 0; g < 2; ++g) {        // the same weights once per group
+              for (int s = 0; s < n_st; ++s) {
+                mbar_wait(&ct.w_empty[slot], phase ^ 1);
+                mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
+                bulk_g2s(ring + (size_t)slot * stage_bytes, nsrc + (size_t)s * bytes, bytes, &ct.w_full[slot]);
+                if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+              }
+            }
+            lsrc += (size_t)2 * K * J * 2;
           }
         }
       }
@@ -358,192 +387,311 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
     // =============================== MMA issuer (warp-uniform, elected lane issues) ===============================
     const bool leader = elect_one();
     uint32_t slot = 0, phase = 0, a1_phase = 0, e_phase = 0;
+    long long t_dep = 0, t_w = 0, t_all = clock64();   // diagnostics: cycles waiting on epilogue / on weights
     const uint32_t ring_addr = smem_u32(ring);
-    const uint32_t a1_addr = smem_u32(sA1);
-    const uint32_t act0_addr = smem_u32(sAct0), act1_addr = smem_u32(sAct1);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      mbar_wait(&ct.a1_ready, a1_phase);
-      a1_phase ^= 1;
-      tc_fence_after();
-      for (int l = 0; l <= sh.L; ++l) {
-        const int K = sh.K_of(l), N = sh.J_of(l);
-        const int ks = Shape::stage_k(K, N);
-        const uint32_t idesc = make_idesc(N);
-        for (int net = 0; net < 2; ++net) {
-          if (l > 0) {  // previous layer of this net drained to the A image
-            mbar_wait(&ct.e_done[net], (e_phase >> net) & 1);
-            e_phase ^= 1u << net;
-            tc_fence_after();
-          }
-          const uint32_t a_addr = (l == 0) ? a1_addr : (net ? act1_addr : act0_addr);
-          const uint32_t d_tmem = tmem + (net ? 256u : 0u);
-          for (int k0 = 0; k0 < K; k0 += ks) {
-            mbar_wait(&ct.w_full[slot], phase);
-            tc_fence_after();
-            const uint32_t b_addr = ring_addr + slot * kStageBytes;
-            if (leader) {
-              for (int kk = 0; kk < ks; kk += 16) {
-                const uint64_t adesc = make_desc(a_addr + (uint32_t)((k0 + kk) >> 3) * (kTileM * 16u), kTileM);
-                const uint64_t bdesc = make_desc(b_addr + (uint32_t)(kk >> 3) * (uint32_t)N * 16u, N);
-                umma_ss(d_tmem, adesc, bdesc, idesc, (k0 + kk) > 0 ? 1u : 0u);
-              }
-              tc_commit(&ct.w_empty[slot]);
+    const uint32_t a1_addr = smem_u32(sA1), act_addr = smem_u32(sAct);
+    const uint32_t a1_sz = (uint32_t)sh.a1_bytes(), act_sz = (uint32_t)sh.act_bytes();
+    for (int64_t it = 0; it < iters; ++it) {
+      for (int net = 0; net < 2; ++net) {
+        for (int l = 0; l <= sh.L; ++l) {
+          const int K = sh.K_of(l), N = sh.N_of(l), halves = sh.halves(l);
+          const int ks = sh.stage_k(K, N);
+          const uint32_t idesc = make_idesc(N);
+          for (int g = 0; g < 2; ++g) {
+            const long long c0 = clock64();
+            if (net == 0 && l == 0) {
+              mbar_wait(&ct.a1_ready[g], (a1_phase >> g) & 1);
+              a1_phase ^= 1u << g;
+            } else {
+              mbar_wait(&ct.e_done[g], (e_phase >> g) & 1);
+              e_phase ^= 1u << g;
             }
-            __syncwarp();
-            if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+            tc_fence_after();
+            t_dep += clock64() - c0;
+            const uint32_t a_addr = (l == 0) ? a1_addr + g * a1_sz : act_addr + g * act_sz;
+            for (int hb = 0; hb < halves; ++hb) {
+              const uint32_t d_tmem = tmem + (uint32_t)g * 256u + (uint32_t)(hb * sh.Nh);
+              for (int k0 = 0; k0 < K; k0 += ks) {
+                const long long c1 = clock64();
+                mbar_wait(&ct.w_full[slot], phase);
+                tc_fence_after();
+                t_w += clock64() - c1;
+                const uint32_t b_addr = ring_addr + slot * stage_bytes;
+                if (leader) {
+                  for (int kk = 0; kk < ks; kk += 16) {
+                    const uint64_t adesc = make_desc(a_addr + (uint32_t)((k0 + kk) >> 3) * (kTileM * 16u), kTileM);
+                    const uint64_t bdesc = make_desc(b_addr + (uint32_t)(kk >> 3) * (uint32_t)N * 16u, N);
+                    umma_ss(d_tmem, adesc, bdesc, idesc, (k0 + kk) > 0 ? 1u : 0u);
+                  }
+                  tc_commit(&ct.w_empty[slot]);
+                }
+                __syncwarp();
+                if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+              }
+              if (leader) tc_commit(&ct.h_ready[g][hb]);
+              __syncwarp();
+            }
           }
-          if (leader) tc_commit(&ct.h_ready[net]);
-          __syncwarp();
         }
       }
+    }
+    if (a.dbg != nullptr && blockIdx.x == 0 && leader) {
+      a.dbg[2040] = t_dep; a.dbg[2041] = t_w; a.dbg[2042] = clock64() - t_all;
     }
   } else {
     // =============================== epilogue warps ===============================
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, g = warp >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int r_tile = q * 32 + lane;            // row inside the tile
-    uint32_t h_phase = 0;                        // bit net = parity to wait for on h_ready[net]
-    constexpr int nc = DH / 2;                   // columns of each half handled by this thread
-    const int col_c = sh.c_off + half * nc;      // first conditioning column of this thread
-    const int col_t = sh.t_off + half * nc;      // first transformed column of this thread
-    const int n_chunks = sh.U / kChunk;
+    const uint32_t hcol = tmem + lane_addr + (uint32_t)g * 256u;
+    unsigned char* myA1 = sA1 + (size_t)g * sh.a1_bytes();
+    unsigned char* myAct = sAct + (size_t)g * sh.act_bytes();
+    uint64_t* my_h = &ct.h_ready[g][0];
+    uint32_t h_phase = 0;
+    const int n_pairs = sh.U / (2 * kChunk);     // accumulator chunks are processed two at a time
+    const float kLog2e = 1.4426950408889634f;
+    constexpr bool kRegs = DH <= 32;             // small D: keep z rows / t outputs in registers
+    constexpr int kR = kRegs ? DH : 4;
 
-    float zc[nc];  // conditioning part of the CURRENT tile (prefetched during the previous tile)
-    {
-      const int64_t row = (int64_t)blockIdx.x * kTileM + r_tile;
-      const bool valid = blockIdx.x < n_tiles && row < a.rows;
+    int dbg_n = 0;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;
+    long long* dbg = a.dbg + g * 1024;
+#define TNF_STAMP(tag)                                                                     \
+  do {                                                                                     \
+    if (dbg_on && dbg_n < 500) { dbg[2 * dbg_n] = (tag); dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; } \
+  } while (0)
+
+    // one accumulator chunk: bias + tanh + bf16 pack + store into the A image (columns c*32 .. c*32+31)
+    auto process_chunk = [&](const uint32_t (&acc)[32], const float* bl, int c) {
+      const float4* b4 = reinterpret_cast<const float4*>(bl + c * kChunk);
 #pragma unroll
-      for (int j = 0; j < nc; j += 4) {
-        float4 v = valid ? *reinterpret_cast<const float4*>(a.z_in + row * sh.D + col_c + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        zc[j] = v.x; zc[j + 1] = v.y; zc[j + 2] = v.z; zc[j + 3] = v.w;
+      for (int j = 0; j < 32; j += 8) {
+        const float4 b0 = b4[j / 4], b1 = b4[j / 4 + 1];
+        uint4 p;
+        p.x = pack_bf16(tanh_fast(__uint_as_float(acc[j]) + b0.x), tanh_fast(__uint_as_float(acc[j + 1]) + b0.y));
+        p.y = pack_bf16(tanh_fast(__uint_as_float(acc[j + 2]) + b0.z), tanh_fast(__uint_as_float(acc[j + 3]) + b0.w));
+        p.z = pack_bf16(tanh_fast(__uint_as_float(acc[j + 4]) + b1.x), tanh_fast(__uint_as_float(acc[j + 5]) + b1.y));
+        p.w = pack_bf16(tanh_fast(__uint_as_float(acc[j + 6]) + b1.z), tanh_fast(__uint_as_float(acc[j + 7]) + b1.w));
+        *reinterpret_cast<uint4*>(myAct + img_off(r_tile, c * kChunk + j, kTileM)) = p;
       }
-    }
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t row = tile * kTileM + r_tile;
-      const bool valid = row < a.rows;
-      float* orow = a.z_out + row * sh.D;
-      // ---- conditioning half: pre-affine, pass through, bf16 image A1 (this thread: nc columns of its row)
+    };
+    // conditioning half -> pre-affine -> bf16 A1 image -> publish; returns the pre-affined values in v
+    auto publish_a1 = [&](const float* zin_regs, const float* zrow, bool valid, float (&v)[DH]) {
 #pragma unroll
-      for (int j = 0; j < nc; j += 8) {
-        float v[8];
+      for (int j = 0; j < DH; j += 4) {
+        float4 in;
+        if (kRegs) in = make_float4(zin_regs[kRegs ? j : 0], zin_regs[kRegs ? j + 1 : 0], zin_regs[kRegs ? j + 2 : 0],
+                                    zin_regs[kRegs ? j + 3 : 0]);
+        else in = valid ? *reinterpret_cast<const float4*>(zrow + sh.c_off + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[j] = fmaf(in.x, s_pscale[sh.c_off + j], s_pshift[sh.c_off + j]);
+        v[j + 1] = fmaf(in.y, s_pscale[sh.c_off + j + 1], s_pshift[sh.c_off + j + 1]);
+        v[j + 2] = fmaf(in.z, s_pscale[sh.c_off + j + 2], s_pshift[sh.c_off + j + 2]);
+        v[j + 3] = fmaf(in.w, s_pscale[sh.c_off + j + 3], s_pshift[sh.c_off + j + 3]);
+      }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = fmaf(zc[j + e], s_pscale[col_c + j + e], s_pshift[col_c + j + e]);
-        if (valid) {
-          *reinterpret_cast<float4*>(orow + col_c + j) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(orow + col_c + j + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        uint4 p = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        *reinterpret_cast<uint4*>(sA1 + img_off(r_tile, half * nc + j, kTileM)) = p;
+      for (int j = 0; j < DH; j += 8) {
+        uint4 p = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                             pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+        *reinterpret_cast<uint4*>(myA1 + img_off(r_tile, j, kTileM)) = p;
       }
       fence_async_smem();
-      tc_fence_before();   // orders this thread's earlier tcgen05.ld of the previous tile's outputs
+      tc_fence_before();   // also orders this thread's tcgen05.ld of the previous tile's outputs
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ct.a1_ready);
-      // ---- prefetch: transformed part of this tile, conditioning part of the next tile
-      float zt[nc];
+      if (lane == 0) mbar_arrive(&ct.a1_ready[g]);
+    };
+
+    // ---- first tile of this group: load and publish A1, store the pass-through half
+    {
+      const int64_t tile = (int64_t)g * gridDim.x + blockIdx.x;
+      const int64_t row = tile * kTileM + r_tile;
+      const bool valid = tile < n_tiles && row < a.rows;
+      float zc[kR];
+      if (kRegs) {
 #pragma unroll
-      for (int j = 0; j < nc; j += 4) {
-        float4 v = valid ? *reinterpret_cast<const float4*>(a.z_in + row * sh.D + col_t + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        zt[j] = v.x; zt[j + 1] = v.y; zt[j + 2] = v.z; zt[j + 3] = v.w;
-      }
-      {
-        const int64_t nrow = row + (int64_t)gridDim.x * kTileM;
-        const bool nvalid = (tile + gridDim.x) < n_tiles && nrow < a.rows;
-#pragma unroll
-        for (int j = 0; j < nc; j += 4) {
-          float4 v = nvalid ? *reinterpret_cast<const float4*>(a.z_in + nrow * sh.D + col_c + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          zc[j] = v.x; zc[j + 1] = v.y; zc[j + 2] = v.z; zc[j + 3] = v.w;
+        for (int j = 0; j < kR; j += 4) {
+          float4 t4 = valid ? *reinterpret_cast<const float4*>(a.z_in + row * sh.D + sh.c_off + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          zc[j] = t4.x; zc[j + 1] = t4.y; zc[j + 2] = t4.z; zc[j + 3] = t4.w;
         }
       }
-      // ---- hidden layers: H_net -> tanh -> A_net image, nets alternate with the tensor pipe
-      for (int l = 0; l < sh.L; ++l) {
+      float v[DH];
+      publish_a1(zc, a.z_in + row * sh.D, valid, v);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < DH; j += 4)
+          *reinterpret_cast<float4*>(a.z_out + row * sh.D + sh.c_off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    for (int64_t it = 0; it < iters; ++it) {
+      const int64_t tile = (it * 2 + g) * (int64_t)gridDim.x + blockIdx.x;
+      const int64_t row = tile * kTileM + r_tile;
+      const bool valid = tile < n_tiles && row < a.rows;
+      const int64_t nrow = row + 2 * (int64_t)gridDim.x * kTileM;      // this thread's row in the next iteration
+      const bool has_next = it + 1 < iters;
+      const bool nvalid = has_next && (tile + 2 * (int64_t)gridDim.x) < n_tiles && nrow < a.rows;
+      const float* zrow = a.z_in + row * sh.D;
+      float* orow = a.z_out + row * sh.D;
+      TNF_STAMP(100);
+      if (nvalid) {   // pull the next tile's row and log-det into L2 a whole tile ahead of their use
+        for (int b = 0; b < sh.D * 4; b += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.z_in + nrow * sh.D) + b));
+        if (a.accum != TNF_LD_WRITE) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.log_det + nrow));
+      }
+      float tv[kR];   // t-net output (registers when it fits; else parked in z_out)
+      float zt[kR];   // transformed half of this tile
+      float zn[kR];   // conditioning half of the next tile
+      float ld_old = 0.f, ld_sum = 0.f;
+#pragma unroll
+      for (int net = 0; net < 2; ++net) {
+        const float* bias = s_bias + net * nb;
+        // ---- hidden layers: accumulator -> tanh -> A image
 #pragma unroll 1
-        for (int net = 0; net < 2; ++net) {
-          const float* bl = s_bias + net * nb + l * sh.U;
-          unsigned char* dstA = net ? sAct1 : sAct0;
-          mbar_wait(&ct.h_ready[net], (h_phase >> net) & 1);
-          h_phase ^= 1u << net;
+        for (int l = 0; l < sh.L; ++l) {
+          const float* bl = bias + l * sh.U;
+          TNF_STAMP(200 + net * 10 + l);
+          mbar_wait(my_h, h_phase);
+          h_phase ^= 1;
           tc_fence_after();
-          const uint32_t src = tmem + lane_addr + (net ? 256u : 0u);
-          uint32_t acc[32];
-          tmem_ld32(src + (uint32_t)(half * kChunk), acc);
+          TNF_STAMP(300 + net * 10 + l);
+          uint32_t accA[32], accB[32];
+          tmem_ld32(hcol, accA);
 #pragma unroll 1
-          for (int c = half; c < n_chunks; c += 2) {
+          for (int pr = 0; pr < n_pairs; ++pr) {      // U is a multiple of 64: chunks come in pairs
+            const int c = 2 * pr;
             tc_wait_ld();
-            float x[32];
-            const float4* b4 = reinterpret_cast<const float4*>(bl + c * kChunk);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = b4[j / 4];
-              x[j] = __uint_as_float(acc[j]) + b.x;
-              x[j + 1] = __uint_as_float(acc[j + 1]) + b.y;
-              x[j + 2] = __uint_as_float(acc[j + 2]) + b.z;
-              x[j + 3] = __uint_as_float(acc[j + 3]) + b.w;
-            }
-            if (c + 2 < n_chunks) tmem_ld32(src + (uint32_t)((c + 2) * kChunk), acc);  // next chunk in flight
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 p;
-              p.x = pack_bf16(tanh_fast(x[j]), tanh_fast(x[j + 1]));
-              p.y = pack_bf16(tanh_fast(x[j + 2]), tanh_fast(x[j + 3]));
-              p.z = pack_bf16(tanh_fast(x[j + 4]), tanh_fast(x[j + 5]));
-              p.w = pack_bf16(tanh_fast(x[j + 6]), tanh_fast(x[j + 7]));
-              *reinterpret_cast<uint4*>(dstA + img_off(r_tile, c * kChunk + j, kTileM)) = p;
-            }
+            tmem_ld32(hcol + (uint32_t)((c + 1) * kChunk), accB);
+            process_chunk(accA, bl, c);
+            tc_wait_ld();
+            // the last pair re-reads its own chunk (harmless) so that the loop body stays branch-free
+            tmem_ld32(hcol + (uint32_t)((pr + 1 < n_pairs ? c + 2 : c) * kChunk), accA);
+            process_chunk(accB, bl, c + 1);
           }
+          tc_wait_ld();
           fence_async_smem();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&ct.e_done[net]);
+          if (lane == 0) mbar_arrive(&ct.e_done[g]);
         }
-      }
-      // ---- final layer: t, then s and the affine transform of this thread's columns
-      float tv[nc];
-      float ld_part = 0.f;
+        // ---- while the final-layer MMAs of the s-net run: issue every global load still needed
+        if (net == 1) {
+          if (valid && a.accum != TNF_LD_WRITE) ld_old = a.log_det[row];
+          if (kRegs) {
 #pragma unroll
-      for (int net = 0; net < 2; ++net) {
-        const float* bL = s_bias + net * nb + sh.L * sh.U + half * nc;
-        mbar_wait(&ct.h_ready[net], (h_phase >> net) & 1);
-        h_phase ^= 1u << net;
+            for (int j = 0; j < kR; j += 4) {
+              float4 t4 = valid ? *reinterpret_cast<const float4*>(zrow + sh.t_off + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              zt[j] = t4.x; zt[j + 1] = t4.y; zt[j + 2] = t4.z; zt[j + 3] = t4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < kR; j += 4) {
+              float4 t4 = nvalid ? *reinterpret_cast<const float4*>(a.z_in + nrow * sh.D + sh.c_off + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              zn[j] = t4.x; zn[j + 1] = t4.y; zn[j + 2] = t4.z; zn[j + 3] = t4.w;
+            }
+          }
+        }
+        // ---- final layer of this net
+        const float* bL = bias + sh.L * sh.U;
+        TNF_STAMP(400 + net);
+        mbar_wait(my_h, h_phase);
+        h_phase ^= 1;
         tc_fence_after();
+        TNF_STAMP(500 + net);
+        if (net == 0) {
 #pragma unroll
-        for (int j0 = 0; j0 < nc; j0 += 16) {
-          uint32_t o[16];
-          tmem_ld16(tmem + lane_addr + (net ? 256u : 0u) + (uint32_t)(half * nc + j0), o);
-          tc_wait_ld();
-          if (net == 0) {
+          for (int j0 = 0; j0 < DH; j0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(hcol + (uint32_t)j0, o);
+            tc_wait_ld();
+            if (kRegs) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) tv[j0 + j] = __uint_as_float(o[j]) + bL[j0 + j];
-          } else {
+              for (int j = 0; j < 16; ++j) tv[kRegs ? j0 + j : 0] = __uint_as_float(o[j]) + bL[j0 + j];
+            } else if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(orow + sh.t_off + j0 + j) =
+                    make_float4(__uint_as_float(o[j]) + bL[j0 + j], __uint_as_float(o[j + 1]) + bL[j0 + j + 1],
+                                __uint_as_float(o[j + 2]) + bL[j0 + j + 2], __uint_as_float(o[j + 3]) + bL[j0 + j + 3]);
+            }
+          }
+          tc_fence_before();   // t read out: the accumulator may be overwritten by the s-net
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ct.e_done[g]);
+        } else if (kRegs) {
+          // s read out; y kept in registers so that the next tile's A1 can be published BEFORE any global
+          // store is issued (the async-proxy fence would otherwise wait for those stores to drain)
+          float y[kR];
+#pragma unroll
+          for (int j0 = 0; j0 < kR; j0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(hcol + (uint32_t)j0, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = sh.t_off + j0 + j;
+              const float zin = fmaf(zt[j0 + j], s_pscale[col], s_pshift[col]);
+              const float sv = __uint_as_float(o[j]) + bL[j0 + j];
+              ld_sum += sv;
+              y[j0 + j] = kInverse ? (zin - tv[j0 + j]) * exp2_fast(-sv * kLog2e)
+                                   : fmaf(zin, exp2_fast(sv * kLog2e), tv[j0 + j]);
+            }
+          }
+          float v[DH];
+          TNF_STAMP(601);
+          if (has_next) publish_a1(zn, nullptr, nvalid, v);
+          TNF_STAMP(602);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < kR; j += 4)
+              *reinterpret_cast<float4*>(orow + sh.t_off + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          }
+          if (nvalid) {
+#pragma unroll
+            for (int j = 0; j < DH; j += 4)
+              *reinterpret_cast<float4*>(a.z_out + nrow * sh.D + sh.c_off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        } else {
+          // large D: stream the transformed half in 16-column pieces (t was parked in z_out)
+#pragma unroll 1
+          for (int j0 = 0; j0 < DH; j0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(hcol + (uint32_t)j0, o);
+            tc_wait_ld();
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
+              const int col = sh.t_off + j0 + j;
+              float4 zv = valid ? *reinterpret_cast<const float4*>(zrow + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+              float4 tq = valid ? *reinterpret_cast<const float4*>(orow + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+              const float tt[4] = {tq.x, tq.y, tq.z, tq.w};
               float yy[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int col = col_t + j0 + j + e;
-                const float zin = fmaf(zt[j0 + j + e], s_pscale[col], s_pshift[col]);
-                const float s = __uint_as_float(o[j + e]) + bL[j0 + j + e];
-                const float t = tv[j0 + j + e];
-                ld_part += s;
-                yy[e] = kInverse ? __fdiv_rn(zin - t, expf(s)) : fmaf(zin, expf(s), t);
+                const float zin = fmaf(zz[e], s_pscale[col + e], s_pshift[col + e]);
+                const float sv = __uint_as_float(o[j + e]) + bL[j0 + j + e];
+                ld_sum += sv;
+                yy[e] = kInverse ? (zin - tt[e]) * exp2_fast(-sv * kLog2e) : fmaf(zin, exp2_fast(sv * kLog2e), tt[e]);
               }
-              if (valid) *reinterpret_cast<float4*>(orow + col_t + j0 + j) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+              if (valid) *reinterpret_cast<float4*>(orow + col) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+            }
+          }
+          if (has_next) {
+            float v[DH];
+            publish_a1(nullptr, a.z_in + nrow * sh.D, nvalid, v);
+            if (nvalid) {
+#pragma unroll
+              for (int j = 0; j < DH; j += 4)
+                *reinterpret_cast<float4*>(a.z_out + nrow * sh.D + sh.c_off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           }
         }
       }
-      // ---- log-det: combine the two column halves of a row, one writer per row
-      if (half == 1) ct.ld_xchg[r_tile] = ld_part;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      if (half == 0 && valid) {
-        const float ld = ld_part + ct.ld_xchg[r_tile];
+      if (valid) {
         float* o = a.log_det + row;
-        if (a.accum == TNF_LD_WRITE) *o = ld;
-        else if (a.accum == TNF_LD_ADD) *o += ld;
-        else *o -= ld;
+        if (a.accum == TNF_LD_WRITE) *o = ld_sum;
+        else if (a.accum == TNF_LD_ADD) *o = ld_old + ld_sum;
+        else *o = ld_old - ld_sum;
       }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      TNF_STAMP(600);
     }
+#undef TNF_STAMP
   }
   // ---- teardown
   tc_fence_before();
@@ -562,7 +710,7 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
   uint64_t* bar = reinterpret_cast<uint64_t*>(aimg + (size_t)kTileM * K * 2);
   uint32_t* tbase = reinterpret_cast<uint32_t*>(bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ks = Shape::stage_k(K, N);
+  const int ks = (kStageElems / N) < K ? (kStageElems / N) : K;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -626,7 +774,11 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
 
 using namespace tnf;
 
+static long long* g_tc_debug = nullptr;
+
 extern "C" {
+
+void tnf_tc_set_debug(void* dev_buffer) { g_tc_debug = (long long*)dev_buffer; }
 
 int tnf_tc_supported(int D, int U, int L) { return tc::shape_supported(D, U, L) ? 1 : 0; }
 
@@ -663,7 +815,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   const size_t smem = tc::smem_bytes(sh, n_stages);
   TNF_REQUIRE(smem <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem);
   tc::Args a{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
-             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages};
+             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_debug};
   const int64_t n_tiles = (rows + tc::kTileM - 1) / tc::kTileM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;
