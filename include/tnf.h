@@ -138,6 +138,22 @@ int tnf_bn_bwd_apply(const void* g_y, const void* y, const void* alpha, const do
                      const void* g_log_det, const double* count, void* g_z, int64_t rows, int D,
                      int dtype, tnf_stream_t stream);
 
+/* ---- per-column affine maps: how BatchNorm / Affine (shared weights) are folded into the
+ * neighbouring coupling kernel instead of costing an HBM pass each.
+ * tnf_fold_colaffine composes a pending map z -> z*ps_in + pb_in (NULL = identity) with one more
+ * bijector and writes the composed (ps_out, pb_out), D floats each:
+ *   TNF_FOLD_BN_FWD   (z - a)/b        a = mean, b = alpha        bijectors.py:399
+ *   TNF_FOLD_BN_INV   z*b + a                                     bijectors.py:423-424
+ *   TNF_FOLD_AFF_FWD  exp(a)*z + b     a = alpha(D), b = shift(D)  bijectors.py:292
+ *   TNF_FOLD_AFF_INV  (z - b)/exp(a)                              bijectors.py:312
+ * For the Affine kinds ld_accum[0] += sum(alpha) when ld_accum is non-NULL (its log-det, :293,313).
+ * tnf_colaffine applies a map to z (rows, D) when no coupling kernel follows. */
+enum { TNF_FOLD_BN_FWD = 0, TNF_FOLD_BN_INV = 1, TNF_FOLD_AFF_FWD = 2, TNF_FOLD_AFF_INV = 3 };
+int tnf_fold_colaffine(const float* ps_in, const float* pb_in, int kind, const float* a, const float* b,
+                       float* ps_out, float* pb_out, float* ld_accum, int D, tnf_stream_t stream);
+int tnf_colaffine(const float* z_in, float* z_out, const float* scale, const float* shift, int64_t rows,
+                  int D, tnf_stream_t stream);
+
 /* ---- ToInterval: replaces ToInterval.forward_and_log_det /
  * inverse_and_log_det (bijectors.py:509-557).  consts = 7*D floats
  * [tanh_flg | softplus_flg | tanh_m | tanh_c | softplus_m | softplus_c | log(tanh_m)]

@@ -39,6 +39,8 @@ PROTOTYPES = {
     "tnf_bn_apply": (I, [P, P, P, P, L, I, I, I, P]),
     "tnf_bn_bwd_sums": (I, [P, P, L, I, P, P, I, P]),
     "tnf_bn_bwd_apply": (I, [P, P, P, P, P, P, P, L, I, I, P]),
+    "tnf_fold_colaffine": (I, [P, P, I, P, P, P, P, P, I, P]),
+    "tnf_colaffine": (I, [P, P, P, P, L, I, P]),
     "tnf_tointerval": (I, [P, P, P, P, L, I, I, I, I, P]),
     "tnf_tointerval_bwd": (I, [P, P, P, P, P, L, I, I, I, P]),
     "tnf_tosimplex": (I, [P, P, P, L, I, I, I, I, P]),

@@ -581,6 +581,37 @@ __global__ void accum_bcast_kernel(T* __restrict__ dst, const T* __restrict__ sr
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i / div];
 }
 
+__global__ void fold_colaffine_kernel(const float* __restrict__ ps_in, const float* __restrict__ pb_in, int kind,
+                                      const float* __restrict__ a, const float* __restrict__ b,
+                                      float* __restrict__ ps_out, float* __restrict__ pb_out,
+                                      float* __restrict__ ld_accum, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d == 0 && ld_accum != nullptr && kind >= TNF_FOLD_AFF_FWD) {
+    float s = 0.f;
+    for (int k = 0; k < D; ++k) s += a[k];
+    ld_accum[0] += s;
+  }
+  if (d >= D) return;
+  float ps = ps_in ? ps_in[d] : 1.0f, pb = pb_in ? pb_in[d] : 0.0f;
+  float s, t;   // the new map z -> z*s + t
+  if (kind == TNF_FOLD_BN_FWD) { s = 1.0f / b[d]; t = -a[d] / b[d]; }
+  else if (kind == TNF_FOLD_BN_INV) { s = b[d]; t = a[d]; }
+  else if (kind == TNF_FOLD_AFF_FWD) { s = exp_cr(a[d]); t = b[d]; }
+  else { s = 1.0f / exp_cr(a[d]); t = -b[d] * s; }
+  ps_out[d] = ps * s;
+  pb_out[d] = fmaf(pb, s, t);
+}
+
+__global__ void colaffine_kernel(const float* __restrict__ z_in, float* __restrict__ z_out,
+                                 const float* __restrict__ scale, const float* __restrict__ shift, int64_t n_el,
+                                 int D) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += stride) {
+    int d = (int)(e % D);
+    z_out[e] = fmaf(z_in[e], scale[d], shift[d]);
+  }
+}
+
 // launch helper for the row-group kernels
 #define TNF_ROWGROUP(D, ...)                       \
   do {                                             \
@@ -714,6 +745,24 @@ int tnf_bn_bwd_apply(const void* g_y, const void* y, const void* alpha, const do
         (const T*)g_y, (const T*)y, (const T*)alpha, gsums, (const T*)g_log_det, count, (T*)g_z, n_el, D);
   });
   return check_launch("tnf_bn_bwd_apply");
+}
+
+int tnf_fold_colaffine(const float* ps_in, const float* pb_in, int kind, const float* a, const float* b, float* ps_out,
+                       float* pb_out, float* ld_accum, int D, tnf_stream_t stream) {
+  TNF_REQUIRE(a && b && ps_out && pb_out && D >= 1, TNF_ERR_ARG, "tnf_fold_colaffine: bad argument");
+  TNF_REQUIRE(kind >= 0 && kind <= 3, TNF_ERR_ARG, "tnf_fold_colaffine: bad kind %d", kind);
+  fold_colaffine_kernel<<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ps_in, pb_in, kind, a, b, ps_out, pb_out,
+                                                                       ld_accum, D);
+  return check_launch("tnf_fold_colaffine");
+}
+
+int tnf_colaffine(const float* z_in, float* z_out, const float* scale, const float* shift, int64_t rows, int D,
+                  tnf_stream_t stream) {
+  if (rows == 0) return 0;
+  TNF_REQUIRE(z_in && z_out && scale && shift, TNF_ERR_ARG, "tnf_colaffine: null pointer");
+  colaffine_kernel<<<grid_for(rows * D, 256 * 4), 256, 0, (cudaStream_t)stream>>>(z_in, z_out, scale, shift, rows * D,
+                                                                                  D);
+  return check_launch("tnf_colaffine");
 }
 
 int tnf_tointerval(const void* z_in, void* z_out, void* log_det, const float* consts, int64_t rows, int D,

@@ -240,20 +240,32 @@ class NormFlow(DensityEstimator):
         self._tc_cache[id(b)] = (key, packed)
         return packed
 
+    def _can_fold(self, pd, z):
+        """BatchNorm / Affine are folded into the next tensor-core coupling kernel when every coupling
+        layer of the chain runs on that path (shared weights, fp32, bf16-conditioner mode)."""
+        cps = [b for b in self.bijectors if b.name == "RealNVP"]
+        return bool(cps) and all(self._use_tc(b, pd, z) for b in cps)
+
     def _forward_plan(self, z, log_q, pd, freeze_bn, home=None):
         M, N, D = z.shape
         Mp = pd.shape[0]
         ld_acc = torch.zeros((M, N), dtype=torch.float32, device=z.device)
         scal = torch.zeros(Mp, dtype=torch.float32, device=z.device)
+        fold = self._can_fold(pd, z)
+        pend = None     # per-column map (scale, shift) owed to z; consumed by the next coupling kernel
         for (b, idx, n) in self._slices():
             if b.name == "RealNVP":
                 if self._use_tc(b, pd, z):
                     z, _ = ops.coupling_tc(z, self._packed(b, idx, n, pd), b.D, b.num_units, b.num_layers,
-                                           b.transform_upper, TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD)
+                                           b.transform_upper, TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD,
+                                           pre_scale=pend[0] if pend else None, pre_shift=pend[1] if pend else None)
+                    pend = None
                 else:
                     z, _ = ops.coupling(z, pd[:, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper,
                                         TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD)
             elif b.name == "BatchNorm":
+                if pend is not None:       # statistics are taken on the materialised tensor
+                    z, pend = ops.colaffine(z, pend, D), None
                 if freeze_bn:
                     mean, alpha = b._state_on(z.device, z.dtype)
                     ld = b._last_ld.to(device=z.device, dtype=z.dtype)
@@ -262,23 +274,35 @@ class NormFlow(DensityEstimator):
                     sums = _reduce_stats(ops.colstats(z, D))
                     mean, alpha, ld = ops.bn_finalize(sums, D, b.eps, z.dtype)
                     b._set_state(mean, alpha, ld, home)
-                z = ops.bn_apply(z, mean, alpha, D, TNF_FORWARD)
+                if fold:
+                    pend = ops.fold_colaffine(pend, ops.FOLD_BN_FWD, mean, alpha, D)
+                else:
+                    z = ops.bn_apply(z, mean, alpha, D, TNF_FORWARD)
                 ops.accum_bcast(scal, ld.reshape(1), Mp)
             elif b.name == "Affine":
-                z, ld = ops.affine(z, pd[:, idx:idx + n], D, TNF_FORWARD)
-                ops.accum_bcast(scal, ld, 1)
-            elif b.name == "ToInterval":
-                z, _ = ops.tointerval(z, b._consts(z.device), D, TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD)
-            elif b.name == "ToSimplex":
-                z, _ = ops.tosimplex(z, b.D, ld=ld_acc, accum=TNF_LD_ADD)
-            else:  # MAF or a user-defined bijector: public protocol, log-det folded in by kernel
-                z, ld = b(z, pd[:, idx:idx + n]) if n > 0 else b(z)
-                ld = ld.detach().to(torch.float32)
-                if ld.numel() == M * N:
-                    ops.accum_bcast(ld_acc, ld.contiguous(), 1)
+                if fold:
+                    pend = ops.fold_colaffine(pend, ops.FOLD_AFF_FWD, pd[0, idx:idx + D].contiguous(),
+                                              pd[0, idx + D:idx + 2 * D].contiguous(), D, ld_accum=scal)
                 else:
-                    ops.accum_bcast(scal, ld.reshape(-1).contiguous(), Mp if ld.numel() == 1 else 1)
-                z = z.detach()
+                    z, ld = ops.affine(z, pd[:, idx:idx + n], D, TNF_FORWARD)
+                    ops.accum_bcast(scal, ld, 1)
+            else:
+                if pend is not None:
+                    z, pend = ops.colaffine(z, pend, D), None
+                if b.name == "ToInterval":
+                    z, _ = ops.tointerval(z, b._consts(z.device), D, TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD)
+                elif b.name == "ToSimplex":
+                    z, _ = ops.tosimplex(z, b.D, ld=ld_acc, accum=TNF_LD_ADD)
+                else:  # MAF or a user-defined bijector: public protocol, log-det folded in by kernel
+                    z, ld = b(z, pd[:, idx:idx + n]) if n > 0 else b(z)
+                    ld = ld.detach().to(torch.float32)
+                    if ld.numel() == M * N:
+                        ops.accum_bcast(ld_acc, ld.contiguous(), 1)
+                    else:
+                        ops.accum_bcast(scal, ld.reshape(-1).contiguous(), Mp if ld.numel() == 1 else 1)
+                    z = z.detach()
+        if pend is not None:
+            z = ops.colaffine(z, pend, D)
         ops.finish_logq(log_q, ld_acc, scal, N if Mp == M and M > 1 else M * N)
         return z, log_q
 
@@ -314,34 +338,50 @@ class NormFlow(DensityEstimator):
         Mp = pd.shape[0]
         ld_acc = torch.zeros((M, N), dtype=z.dtype, device=z.device)
         scal = torch.zeros(Mp, dtype=z.dtype, device=z.device)
+        fold = self._can_fold(pd, z)
+        pend = None
         for (b, idx, n) in reversed(self._slices()):
             if b.name == "RealNVP":
                 if self._use_tc(b, pd, z):
                     z, _ = ops.coupling_tc(z, self._packed(b, idx, n, pd), b.D, b.num_units, b.num_layers,
-                                           b.transform_upper, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD)
+                                           b.transform_upper, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD,
+                                           pre_scale=pend[0] if pend else None, pre_shift=pend[1] if pend else None)
+                    pend = None
                 else:
                     z, _ = ops.coupling(z, pd[:, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper,
                                         TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD)
             elif b.name == "BatchNorm":
                 mean, alpha = b._state_on(z.device, z.dtype)
-                z = ops.bn_apply(z, mean, alpha, D, TNF_INVERSE)
+                if fold:
+                    pend = ops.fold_colaffine(pend, ops.FOLD_BN_INV, mean, alpha, D)
+                else:
+                    z = ops.bn_apply(z, mean, alpha, D, TNF_INVERSE)
                 ops.accum_bcast(scal, b._last_ld.to(device=z.device, dtype=z.dtype).reshape(1), Mp)
             elif b.name == "Affine":
-                z, ld = ops.affine(z, pd[:, idx:idx + n], D, TNF_INVERSE)
-                ops.accum_bcast(scal, ld, 1)
-            elif b.name == "ToInterval":
-                z, _ = ops.tointerval(z, b._consts(z.device), D, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD)
+                if fold:
+                    pend = ops.fold_colaffine(pend, ops.FOLD_AFF_INV, pd[0, idx:idx + D].contiguous(),
+                                              pd[0, idx + D:idx + 2 * D].contiguous(), D, ld_accum=scal)
+                else:
+                    z, ld = ops.affine(z, pd[:, idx:idx + n], D, TNF_INVERSE)
+                    ops.accum_bcast(scal, ld, 1)
             else:
-                if n > 0:
-                    z, ld = b.inverse_and_log_det(z, pd[:, idx:idx + n])
+                if pend is not None:
+                    z, pend = ops.colaffine(z, pend, D), None
+                if b.name == "ToInterval":
+                    z, _ = ops.tointerval(z, b._consts(z.device), D, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD)
                 else:
-                    z, ld = b.inverse_and_log_det(z)   # ToSimplex: TypeError, as in the reference
-                ld = ld.detach().to(z.dtype)
-                if ld.numel() == M * N:
-                    ops.accum_bcast(ld_acc, ld.contiguous(), 1)
-                else:
-                    ops.accum_bcast(scal, ld.reshape(-1).contiguous(), Mp if ld.numel() == 1 else 1)
-                z = z.detach()
+                    if n > 0:
+                        z, ld = b.inverse_and_log_det(z, pd[:, idx:idx + n])
+                    else:
+                        z, ld = b.inverse_and_log_det(z)   # ToSimplex: TypeError, as in the reference
+                    ld = ld.detach().to(z.dtype)
+                    if ld.numel() == M * N:
+                        ops.accum_bcast(ld_acc, ld.contiguous(), 1)
+                    else:
+                        ops.accum_bcast(scal, ld.reshape(-1).contiguous(), Mp if ld.numel() == 1 else 1)
+                    z = z.detach()
+        if pend is not None:
+            z = ops.colaffine(z, pend, D)
         return z, ld_acc, scal, (N if Mp == M and M > 1 else M * N)
 
     def _inverse_autograd(self, z, pd):

@@ -277,6 +277,31 @@ def bn_bwd_apply(g_y, y, alpha, gsums, g_ld, count, D):
     return g_z
 
 
+# ----------------------------------------------------------------- folded per-column affine maps
+FOLD_BN_FWD, FOLD_BN_INV, FOLD_AFF_FWD, FOLD_AFF_INV = 0, 1, 2, 3
+
+
+def fold_colaffine(pend, kind, a, b, D, ld_accum=None):
+    """Compose the pending map ``pend`` = (scale, shift) or None with one more BatchNorm / Affine.
+    For Affine kinds ``ld_accum[0] += sum(alpha)`` when given."""
+    ps = torch.empty(D, dtype=torch.float32, device=a.device)
+    pb = torch.empty(D, dtype=torch.float32, device=a.device)
+    rc = _lib.lib().tnf_fold_colaffine(_ptr(pend[0]) if pend else 0, _ptr(pend[1]) if pend else 0, kind,
+                                       a.data_ptr(), b.data_ptr(), ps.data_ptr(), pb.data_ptr(), _ptr(ld_accum), D,
+                                       _stream())
+    _lib.check(rc, "tnf_fold_colaffine")
+    return ps, pb
+
+
+def colaffine(z, pend, D):
+    zc = z if z.is_contiguous() else z.contiguous()
+    out = torch.empty_like(zc)
+    rc = _lib.lib().tnf_colaffine(zc.data_ptr(), out.data_ptr(), pend[0].data_ptr(), pend[1].data_ptr(),
+                                  zc.numel() // D, D, _stream())
+    _lib.check(rc, "tnf_colaffine")
+    return out
+
+
 # ----------------------------------------------------------------- support layers
 def tointerval(z, consts, D, direction, ld=None, accum=TNF_LD_WRITE):
     z = _check3(z)
