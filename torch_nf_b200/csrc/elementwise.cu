@@ -198,12 +198,30 @@ __global__ void colstats_kernel(const T* __restrict__ a, const T* __restrict__ b
     const int d = t % D, sub = t / D;
     double s1 = 0.0, s2 = 0.0;
     if (sub < lanes) {
-      for (int64_t r = r0 + sub; r < r1; r += lanes) {
+      // four independent row streams per thread: more loads in flight, shorter dependent add chains
+      double p1[4] = {0.0, 0.0, 0.0, 0.0}, p2[4] = {0.0, 0.0, 0.0, 0.0};
+      int64_t r = r0 + sub;
+      for (; r + 3 * (int64_t)lanes < r1; r += 4 * (int64_t)lanes) {
+        T va[4], vb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          va[u] = a[(r + u * (int64_t)lanes) * D + d];
+          vb[u] = b ? b[(r + u * (int64_t)lanes) * D + d] : va[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          p1[u] += (double)va[u];
+          p2[u] += (double)va[u] * (double)vb[u];
+        }
+      }
+      for (; r < r1; r += lanes) {
         double v = (double)a[r * D + d];
         double w = b ? (double)b[r * D + d] : v;
-        s1 += v;
-        s2 += v * w;
+        p1[0] += v;
+        p2[0] += v * w;
       }
+      s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
+      s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
     }
     red[0][t] = s1;
     red[1][t] = s2;
@@ -232,14 +250,20 @@ __global__ void colstats_kernel(const T* __restrict__ a, const T* __restrict__ b
   }
 }
 
+// one warp per output element: lanes stride over the per-block partials, fixed-order shuffle tree
 __global__ void colstats_reduce_kernel(const double* __restrict__ partial, int nblocks, int D,
                                        double* __restrict__ sums, double rows) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 2 * D) sums[i] = rows;
-  if (i >= 2 * D) return;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i > 2 * D) return;
+  if (i == 2 * D) {
+    if (lane == 0) sums[i] = rows;
+    return;
+  }
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * 2 * D + i];
-  sums[i] = s;
+  for (int b = lane; b < nblocks; b += 32) s += partial[(int64_t)b * 2 * D + i];
+  s = warp_sum(s);
+  if (lane == 0) sums[i] = s;
 }
 
 template <typename T>
@@ -698,8 +722,7 @@ static int colstats_launch(const void* a, const void* b, int64_t rows, int D, do
   });
   int rc = check_launch(what);
   if (rc) return rc;
-  colstats_reduce_kernel<<<(2 * D + 1 + 127) / 128, 128, 0, st>>>((const double*)workspace, grid, D, sums,
-                                                                  (double)rows);
+  colstats_reduce_kernel<<<(2 * D + 1 + 7) / 8, 256, 0, st>>>((const double*)workspace, grid, D, sums, (double)rows);
   return check_launch(what);
 }
 
