@@ -90,6 +90,8 @@ int tnf_tc_supported(int D, int U, int L);
 /* diagnostic: when set to a device buffer of 2048 int64, CTA 0 of tnf_coupling_tc records
  * (tag, clock64) stamps of its epilogue phases (group g at offset 512*g*2); NULL disables. */
 void tnf_tc_set_debug(void* dev_buffer);
+/* diagnostic: 1 = only one epilogue group works (no tile ping-pong), 2 = default. */
+void tnf_tc_set_groups(int n_groups);
 int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N, int a_in_tmem,
                          tnf_stream_t stream);
 size_t tnf_tc_packed_bytes(int D, int U, int L);

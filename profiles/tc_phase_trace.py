@@ -11,8 +11,16 @@ D, U, L, N = 64, 256, 2, 1 << 20
 params = torch.tensor(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=0)).cuda()
 packed = ops.tc_pack(params[0], D, U, L, True)
 z = torch.randn(1, N, D, device="cuda")
+if len(sys.argv) > 1 and sys.argv[1] == "solo":
+    _lib.lib().tnf_tc_set_groups(1)
 for _ in range(3):
     ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)
+e1.record(); torch.cuda.synchronize()
+print("ms per launch: %.4f" % (e0.elapsed_time(e1) / 5))
 dbg = torch.zeros(2048, dtype=torch.int64, device="cuda")
 _lib.lib().tnf_tc_set_debug(dbg.data_ptr())
 ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)

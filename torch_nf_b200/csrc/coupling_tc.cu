@@ -282,7 +282,7 @@ struct Args {
   const float* z_in; float* z_out; float* log_det; const unsigned char* packed;
   const float* pre_scale; const float* pre_shift;
   int64_t rows;
-  int D, U, L, upper, inverse, accum, n_stages;
+  int D, U, L, upper, inverse, accum, n_stages, n_groups;
   long long* dbg;   // diagnostics: per-phase clock64 stamps of CTA 0 (NULL = off)
 };
 
@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
-  const int64_t iters = (n_tiles + 2 * (int64_t)gridDim.x - 1) / (2 * (int64_t)gridDim.x);
+  const int G = a.n_groups;   // epilogue groups in use (2; 1 = diagnostic solo mode)
+  const int64_t iters = (n_tiles + G * (int64_t)gridDim.x - 1) / (G * (int64_t)gridDim.x);
   const int64_t weight_bytes = 2 * sh.net_weight_elems() * 2;
 
   // ---- one-time setup
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
             const uint32_t bytes = (uint32_t)(ks * N * 2);
             const int n_st = sh.halves(l) * (K / ks);
             const unsigned char* nsrc = lsrc + (size_t)net * K * J * 2;
-            for (int g = 0; g < 2; ++g) {        // the same weights once per group
+            for (int g = 0; g < G; ++g) {        // the same weights once per group
               for (int s = 0; s < n_st; ++s) {
                 mbar_wait(&ct.w_empty[slot], phase ^ 1);
                 mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
           const int K = sh.K_of(l), N = sh.N_of(l), halves = sh.halves(l);
           const int ks = sh.stage_k(K, N);
           const uint32_t idesc = make_idesc(N);
-          for (int g = 0; g < 2; ++g) {
+          for (int g = 0; g < G; ++g) {
             const long long c0 = clock64();
             if (net == 0 && l == 0) {
               mbar_wait(&ct.a1_ready[g], (a1_phase >> g) & 1);
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
     if (a.dbg != nullptr && blockIdx.x == 0 && leader) {
       a.dbg[2040] = t_dep; a.dbg[2041] = t_w; a.dbg[2042] = clock64() - t_all;
     }
-  } else {
+  } else if ((warp >> 2) < G) {
     // =============================== epilogue warps ===============================
     const int q = warp & 3, g = warp >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -461,19 +462,35 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
     if (dbg_on && dbg_n < 500) { dbg[2 * dbg_n] = (tag); dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; } \
   } while (0)
 
-    // one accumulator chunk: bias + tanh + bf16 pack + store into the A image (columns c*32 .. c*32+31)
-    auto process_chunk = [&](const uint32_t (&acc)[32], const float* bl, int c) {
-      const float4* b4 = reinterpret_cast<const float4*>(bl + c * kChunk);
+    // Software-pipelined epilogue step.  `cur` holds chunk c's pre-activations (accumulator + bias), `acc` the raw
+    // accumulator of the NEXT chunk.  In source order, per group of 8 columns: 8 MUFU.TANH of chunk c, 8 bias adds
+    // preparing the next chunk, pack + st.shared of the previous group - so the MUFU pipe (8 cycles per warp
+    // instruction) never waits for the FMA-pipe / LSU work of a single in-order warp.
+    auto epi_step = [&](float (&cur)[32], float (&nxt)[32], const uint32_t (&acc)[32], const float* bias_next, int c) {
+      const float4* b4 = reinterpret_cast<const float4*>(bias_next);
+      unsigned char* dst = myAct + img_off(r_tile, c * kChunk, kTileM);
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cur[j + e] = tanh_fast(cur[j + e]);
         const float4 b0 = b4[j / 4], b1 = b4[j / 4 + 1];
-        uint4 p;
-        p.x = pack_bf16(tanh_fast(__uint_as_float(acc[j]) + b0.x), tanh_fast(__uint_as_float(acc[j + 1]) + b0.y));
-        p.y = pack_bf16(tanh_fast(__uint_as_float(acc[j + 2]) + b0.z), tanh_fast(__uint_as_float(acc[j + 3]) + b0.w));
-        p.z = pack_bf16(tanh_fast(__uint_as_float(acc[j + 4]) + b1.x), tanh_fast(__uint_as_float(acc[j + 5]) + b1.y));
-        p.w = pack_bf16(tanh_fast(__uint_as_float(acc[j + 6]) + b1.z), tanh_fast(__uint_as_float(acc[j + 7]) + b1.w));
-        *reinterpret_cast<uint4*>(myAct + img_off(r_tile, c * kChunk + j, kTileM)) = p;
+        nxt[j] = __uint_as_float(acc[j]) + b0.x;         nxt[j + 1] = __uint_as_float(acc[j + 1]) + b0.y;
+        nxt[j + 2] = __uint_as_float(acc[j + 2]) + b0.z; nxt[j + 3] = __uint_as_float(acc[j + 3]) + b0.w;
+        nxt[j + 4] = __uint_as_float(acc[j + 4]) + b1.x; nxt[j + 5] = __uint_as_float(acc[j + 5]) + b1.y;
+        nxt[j + 6] = __uint_as_float(acc[j + 6]) + b1.z; nxt[j + 7] = __uint_as_float(acc[j + 7]) + b1.w;
+        if (j > 0) {
+          const int k = j - 8;
+          *reinterpret_cast<uint4*>(dst + (k >> 3) * (kTileM * 16)) =
+              make_uint4(pack_bf16(cur[k], cur[k + 1]), pack_bf16(cur[k + 2], cur[k + 3]),
+                         pack_bf16(cur[k + 4], cur[k + 5]), pack_bf16(cur[k + 6], cur[k + 7]));
+        }
       }
+    };
+    auto epi_flush = [&](const float (&cur)[32], int c) {   // pack + store the last group of chunk c
+      unsigned char* dst = myAct + img_off(r_tile, c * kChunk, kTileM);
+      *reinterpret_cast<uint4*>(dst + 3 * (kTileM * 16)) =
+          make_uint4(pack_bf16(cur[24], cur[25]), pack_bf16(cur[26], cur[27]), pack_bf16(cur[28], cur[29]),
+                     pack_bf16(cur[30], cur[31]));
     };
     // conditioning half -> pre-affine -> bf16 A1 image -> publish; returns the pre-affined values in v
     auto publish_a1 = [&](const float* zin_regs, const float* zrow, bool valid, float (&v)[DH]) {
@@ -522,12 +539,12 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
       }
     }
     for (int64_t it = 0; it < iters; ++it) {
-      const int64_t tile = (it * 2 + g) * (int64_t)gridDim.x + blockIdx.x;
+      const int64_t tile = (it * G + g) * (int64_t)gridDim.x + blockIdx.x;
       const int64_t row = tile * kTileM + r_tile;
       const bool valid = tile < n_tiles && row < a.rows;
-      const int64_t nrow = row + 2 * (int64_t)gridDim.x * kTileM;      // this thread's row in the next iteration
+      const int64_t nrow = row + G * (int64_t)gridDim.x * kTileM;      // this thread's row in the next iteration
       const bool has_next = it + 1 < iters;
-      const bool nvalid = has_next && (tile + 2 * (int64_t)gridDim.x) < n_tiles && nrow < a.rows;
+      const bool nvalid = has_next && (tile + G * (int64_t)gridDim.x) < n_tiles && nrow < a.rows;
       const float* zrow = a.z_in + row * sh.D;
       float* orow = a.z_out + row * sh.D;
       TNF_STAMP(100);
@@ -552,18 +569,36 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
           h_phase ^= 1;
           tc_fence_after();
           TNF_STAMP(300 + net * 10 + l);
-          uint32_t accA[32], accB[32];
-          tmem_ld32(hcol, accA);
+          const int n_chunks = 2 * n_pairs;
+          uint32_t acc[32];
+          float xa[32], xb[32];
+          tmem_ld32(hcol, acc);
+          tc_wait_ld();
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(bl);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = b4[j / 4];
+              xa[j] = __uint_as_float(acc[j]) + b.x;         xa[j + 1] = __uint_as_float(acc[j + 1]) + b.y;
+              xa[j + 2] = __uint_as_float(acc[j + 2]) + b.z; xa[j + 3] = __uint_as_float(acc[j + 3]) + b.w;
+            }
+          }
+          tmem_ld32(hcol + (uint32_t)kChunk, acc);
 #pragma unroll 1
-          for (int pr = 0; pr < n_pairs; ++pr) {      // U is a multiple of 64: chunks come in pairs
-            const int c = 2 * pr;
+          for (int c = 0; c < n_chunks; c += 2) {
+            // chunk c (xa) while chunk c+1 is prepared into xb
             tc_wait_ld();
-            tmem_ld32(hcol + (uint32_t)((c + 1) * kChunk), accB);
-            process_chunk(accA, bl, c);
+            epi_step(xa, xb, acc, bl + (c + 1) * kChunk, c);
+            // the last iteration re-reads its own last chunk (harmless) so that the loop stays branch-free
+            const int c2 = (c + 2 < n_chunks) ? c + 2 : c + 1;
+            tmem_ld32(hcol + (uint32_t)(c2 * kChunk), acc);
+            epi_flush(xa, c);
+            // chunk c+1 (xb) while chunk c+2 is prepared into xa
             tc_wait_ld();
-            // the last pair re-reads its own chunk (harmless) so that the loop body stays branch-free
-            tmem_ld32(hcol + (uint32_t)((pr + 1 < n_pairs ? c + 2 : c) * kChunk), accA);
-            process_chunk(accB, bl, c + 1);
+            epi_step(xb, xa, acc, bl + c2 * kChunk, c + 1);
+            const int c3 = (c + 3 < n_chunks) ? c + 3 : c + 1;
+            tmem_ld32(hcol + (uint32_t)(c3 * kChunk), acc);
+            epi_flush(xb, c + 1);
           }
           tc_wait_ld();
           fence_async_smem();
@@ -775,10 +810,12 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
 using namespace tnf;
 
 static long long* g_tc_debug = nullptr;
+static int g_tc_groups = 2;
 
 extern "C" {
 
 void tnf_tc_set_debug(void* dev_buffer) { g_tc_debug = (long long*)dev_buffer; }
+void tnf_tc_set_groups(int n_groups) { g_tc_groups = n_groups == 1 ? 1 : 2; }
 
 int tnf_tc_supported(int D, int U, int L) { return tc::shape_supported(D, U, L) ? 1 : 0; }
 
@@ -815,7 +852,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   const size_t smem = tc::smem_bytes(sh, n_stages);
   TNF_REQUIRE(smem <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem);
   tc::Args a{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
-             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_debug};
+             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_groups, g_tc_debug};
   const int64_t n_tiles = (rows + tc::kTileM - 1) / tc::kTileM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;
