@@ -71,6 +71,20 @@ int tnf_coupling_bwd(const void* z_in, const void* params, int64_t param_row_str
                      int64_t g_param_row_stride, int64_t M, int64_t N, int D, int U, int L,
                      int transform_upper, int direction, int dtype, tnf_stream_t stream);
 
+/* ---- MAF: replaces MAF.forward_and_log_det / inverse_and_log_det (bijectors.py:742-796).
+ * params row = per layer [W_mu (K*J), W_alpha (K*J)], no biases (:698-738); `mask` = the binary masks
+ * Ms (:663-696) flattened in the same layout (each layer's mask twice), D_params floats, shared by all m.
+ * TNF_INVERSE: one pass z' = (z - mu(z))/exp(alpha(z)).  TNF_FORWARD: D-1 passes z <- u*exp(alpha(z)) + mu(z)
+ * with u the input (:751-756); log_det = sum alpha of the last pass.  The backward exists for the inverse
+ * (log_prob / training) direction only. */
+int tnf_maf(const void* z_in, void* z_out, void* log_det, const void* params, int64_t param_row_stride,
+            const float* mask, int64_t M, int64_t N, int D, int U, int L, int direction, int accum,
+            int dtype, tnf_stream_t stream);
+int tnf_maf_bwd(const void* z_in, const void* params, int64_t param_row_stride, const float* mask,
+                const void* g_z_out, const void* g_log_det, void* g_z_in, void* g_params,
+                int64_t g_param_row_stride, int64_t M, int64_t N, int D, int U, int L, int direction,
+                int dtype, tnf_stream_t stream);
+
 /* ---- RealNVP coupling layer, tcgen05 tensor-core path (bf16 conditioner) --
  * Same math as tnf_coupling for shared weights (regime A: one parameter row),
  * fp32 z / log_det, conditioner GEMMs in bf16 on tcgen05 with fp32 TMEM

@@ -390,3 +390,45 @@ def coupling_bf16_emulated(z, params, D, num_layers, num_units, transform_upper=
             s = _bf16(torch.tanh(s))
     z2 = (z2 - t) / torch.exp(s) if inverse else t + z2 * torch.exp(s)
     return _join(z1, z2, transform_upper), torch.sum(s, dim=2)
+
+
+# ---------------------------------------------------------------------------
+# MAF                                    (torch_nf/bijectors.py:597-806)
+# ---------------------------------------------------------------------------
+def maf_num_params(D, num_layers, num_units):
+    """torch_nf/bijectors.py:804-806."""
+    return 2 * (2 * D * num_units + (num_layers - 1) * num_units ** 2)
+
+
+def _maf_nets(z, params, masks, D, num_layers, U):
+    """Masked, bias-free shift / log-scale nets (bijectors.py:698-740, 766-796).
+    ``masks``: list of (1, K, J) 0/1 tensors, one per layer (shared by both nets)."""
+    M = params.shape[0]
+    sizes = [(D, U)] + [(U, U)] * (num_layers - 1) + [(U, D)]
+    mu = al = z
+    off = 0
+    for i, (K, J) in enumerate(sizes):
+        Wm = masks[i].to(params.dtype) * params[:, off:off + K * J].reshape(M, K, J); off += K * J
+        Wa = masks[i].to(params.dtype) * params[:, off:off + K * J].reshape(M, K, J); off += K * J
+        mu = torch.matmul(mu, Wm)
+        al = torch.matmul(al, Wa)
+        if i + 1 < len(sizes):
+            mu = torch.tanh(mu)
+            al = torch.tanh(al)
+    return mu, al
+
+
+def maf_forward(z, params, masks, D, num_layers, num_units):
+    """D-1 passes z <- u*exp(alpha(z)) + mu(z); log-det of the last pass (bijectors.py:742-756)."""
+    u = z
+    al = None
+    for _ in range(D - 1):
+        mu, al = _maf_nets(z, params, masks, D, num_layers, num_units)
+        z = u * torch.exp(al) + mu
+    return z, torch.sum(al, dim=2)
+
+
+def maf_inverse(z, params, masks, D, num_layers, num_units):
+    """bijectors.py:758-764."""
+    mu, al = _maf_nets(z, params, masks, D, num_layers, num_units)
+    return (z - mu) / torch.exp(al), torch.sum(al, dim=2)

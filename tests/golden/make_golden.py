@@ -200,7 +200,42 @@ def golden_flows():
     golden_flow("flow_c5", 256, 8, 2, 256, 1, 64, 51, 52)
 
 
+def golden_maf():
+    """MAF bijector (bijectors.py:597-806) and the 'AR' NormFlow (density_estimator.py:271-274).
+    Masks are drawn from numpy's global stream at construction: the seed is stored with them."""
+    out = {}
+    rs = np.random.RandomState(7)
+    for nm, D, L, U, M, N, dt, seed in (("d4_f64", 4, 2, 20, 10, 5, np.float64, 100), ("d20_f64", 20, 2, 20, 3, 4, np.float64, 101),
+                                        ("d6_f32", 6, 3, 17, 40, 1, np.float32, 102), ("d5_a_f32", 5, 1, 9, 1, 200, np.float32, 103)):
+        np.random.seed(seed)
+        b = rb.MAF(D, L, U)
+        P = b.count_num_params()
+        params = torch.tensor((rs.standard_normal((M, P)) * 0.3).astype(dt))
+        z_in = torch.tensor(rs.standard_normal((M, N, D)).astype(dt))
+        z, ld = b(z_in, params)
+        zi, ldi = b.inverse_and_log_det(z_in, params)
+        out.update({nm + "_cfg": np.array([D, L, b.num_units, M, N, seed]), nm + "_params": params, nm + "_z_in": z_in,
+                    nm + "_z_fwd": z, nm + "_ld_fwd": ld, nm + "_z_inv": zi, nm + "_ld_inv": ldi})
+        for i, Mi in enumerate(b.Ms):
+            out["%s_mask%d" % (nm, i)] = Mi
+    save("maf", **out)
+    # AR flow: MAF -> BatchNorm -> Affine, conditional weights (scripts/lfi_mat.py shape at test size)
+    D, L, U, M, N, seed = 6, 2, 20, 32, 4, 104
+    np.random.seed(seed)
+    nf = rde.NormFlow(D, True, "AR", 1, L, U)
+    params = torch.tensor((np.random.RandomState(8).standard_normal((M, nf.D_params)) * 0.3).astype(np.float32))
+    omega, z, lq = ref_forward(nf, params, 105, N)
+    means, alphas = bn_stats(nf)
+    out = dict(cfg=np.array([D, L, U, M, N, seed]), params=params, omega=omega, z=z, log_q_z=lq, bn_mean=means,
+               bn_alpha=alphas, log_prob=nf.log_prob(z, params))
+    for i, Mi in enumerate(nf.bijectors[0].Ms):
+        out["mask%d" % i] = Mi
+    save("flow_ar", **out)
+
+
 if __name__ == "__main__":
+    golden_maf()
+    sys.exit(0) if "--maf-only" in sys.argv else None
     golden_realnvp()
     golden_elementwise()
     golden_flows()

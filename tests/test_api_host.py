@@ -76,8 +76,21 @@ def test_MAF_ctor():
     conn = maf.Ms[0][0] @ maf.Ms[1][0] @ maf.Ms[2][0]
     assert torch.equal(torch.triu(conn, diagonal=1) > 0, conn > 0)
     assert maf.count_num_params() == 2 * (2 * 4 * 20 + 20 * 20)
-    with raises(NotImplementedError):
-        maf(torch.zeros(1, 1, 4), torch.zeros(1, maf.count_num_params()))
+    assert maf.count_num_params() == O.maf_num_params(4, 2, 20)
+
+
+def test_MAF_masks_follow_the_reference_stream(golden):
+    """Masks are drawn from numpy's global stream in the reference's order (bijectors.py:663-696):
+    the same seed reproduces the reference object's masks bit for bit."""
+    g = golden("maf")
+    for nm in ("d4_f64", "d20_f64", "d6_f32", "d5_a_f32"):
+        D, L, U, M, N, seed = [int(v) for v in g[nm + "_cfg"]]
+        np.random.seed(seed)
+        maf = MAF(D, L, U)
+        for i, Mi in enumerate(maf.Ms):
+            assert np.array_equal(Mi.numpy(), g["%s_mask%d" % (nm, i)])
+        flat = maf._mask_flat(torch.device("cpu"))
+        assert flat.numel() == maf.count_num_params()
 
 
 def test_Affine_BatchNorm_ctor():

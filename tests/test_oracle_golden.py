@@ -135,3 +135,20 @@ def test_param_net(golden):
     g = golden("flow_c2b_net")
     ws = [(T(g["pn_linear1_weight"]), T(g["pn_linear1_bias"])), (T(g["pn_linear2_weight"]), T(g["pn_linear2_bias"]))]
     close(O.param_net(T(g["x"]), ws), g["params_unscaled"], 1e-5, 1e-6)
+
+
+MAF_CASES = ["d4_f64", "d20_f64", "d6_f32", "d5_a_f32"]
+
+
+def test_maf(golden):
+    g = golden("maf")
+    for nm in MAF_CASES:
+        D, L, U, M, N, seed = [int(v) for v in g[nm + "_cfg"]]
+        masks = [T(g["%s_mask%d" % (nm, i)]) for i in range(L + 1)]
+        params, z_in = T(g[nm + "_params"]), T(g[nm + "_z_in"])
+        tol = 1e-11 if params.dtype == torch.float64 else 5e-6
+        assert O.maf_num_params(D, L, U) == params.shape[1]
+        z, ld = O.maf_forward(z_in, params, masks, D, L, U)
+        close(z, g[nm + "_z_fwd"], tol, tol); close(ld, g[nm + "_ld_fwd"], tol, tol)
+        z, ld = O.maf_inverse(z_in, params, masks, D, L, U)
+        close(z, g[nm + "_z_inv"], tol, tol); close(ld, g[nm + "_ld_inv"], tol, tol)

@@ -510,12 +510,12 @@ class ToSimplex(Bijector):
 class MAF(Bijector):
     """Masked autoregressive flow (reference bijectors.py:597-806).
 
-    Host-side state (clamps, random masks drawn from numpy's global stream,
-    parameter count, packing ``[W_mu, W_alpha]`` per layer without biases) is
-    mirrored here so that ``NormFlow(arch_type='AR')`` constructs and counts
-    parameters exactly as the reference does.  The compute path is SURVEY 8f
-    row 1 ("next"): it is not built yet, and calling it raises rather than
-    falling back to a CPU implementation.
+    Clamps, the random masks drawn from numpy's global stream, the parameter
+    count and the packing ``[W_mu, W_alpha]`` per layer (no biases) follow the
+    reference, so ``NormFlow(arch_type='AR')`` constructs identically.  Both
+    directions run on the exact CUDA-core coupling kernel in its MAF mode
+    (every column conditions and is transformed; weights multiplied by the
+    masks on load); the backward exists for the inverse (log_prob) direction.
     """
 
     def __init__(self, D, num_layers, num_units, fwd_fac=True):
@@ -524,6 +524,7 @@ class MAF(Bijector):
         self.num_layers = num_layers
         self.num_units = num_units
         self.fwd_fac = fwd_fac
+        self._mask_dev = {}
         self._get_masks()
 
     @property
@@ -590,8 +591,51 @@ class MAF(Bijector):
         """bijectors.py:804-806."""
         return 2 * (2 * self.D * self.num_units + (self.num_layers - 1) * (self.num_units ** 2))
 
+    def _mask_flat(self, device):
+        """The masks in the parameter-row layout: per layer [mask, mask] (W_mu and W_alpha share it)."""
+        m = self._mask_dev.get(device)
+        if m is None:
+            parts = []
+            for Mi in self.Ms:
+                flat = Mi.reshape(-1).float()
+                parts += [flat, flat]
+            m = torch.cat(parts).contiguous().to(device)
+            self._mask_dev[device] = m
+        return m
+
+    def _run(self, z, params, direction):
+        zd, pd, home = _stage(z, params)
+        if zd.dim() != 3 or zd.shape[2] != self.D:
+            raise ValueError("MAF expects z of shape (M, N, %d), got %s" % (self.D, tuple(z.shape)))
+        if pd.dim() != 2 or pd.shape[1] < self.count_num_params():
+            raise ValueError("MAF needs %d parameters per row, got %s" % (self.count_num_params(), tuple(params.shape)))
+        z_out, ld = _MafFn.apply(zd, pd, self._mask_flat(zd.device), self.D, self.num_units, self.num_layers, direction)
+        return _home(z_out, home), _home(ld, home)
+
     def forward_and_log_det(self, z, params):
-        raise NotImplementedError("MAF compute path is not built yet (SURVEY 8f row 1); no CPU fallback")
+        """D-1 passes z <- u*exp(alpha(z)) + mu(z) (bijectors.py:742-756)."""
+        return self._run(z, params, TNF_FORWARD)
 
     def inverse_and_log_det(self, z, params):
-        raise NotImplementedError("MAF compute path is not built yet (SURVEY 8f row 1); no CPU fallback")
+        """z' = (z - mu(z))/exp(alpha(z)) in one pass (bijectors.py:758-764)."""
+        return self._run(z, params, TNF_INVERSE)
+
+
+class _MafFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, params, mask, D, U, L, direction):
+        ctx.set_materialize_grads(False)
+        z_out, ld = ops.maf(z, params, mask, D, U, L, direction)
+        ctx.save_for_backward(z, params, mask)
+        ctx.cfg = (D, U, L, direction)
+        return z_out, ld
+
+    @staticmethod
+    def backward(ctx, g_z, g_ld):
+        z, params, mask = ctx.saved_tensors
+        D, U, L, direction = ctx.cfg
+        if direction != TNF_INVERSE:
+            raise NotImplementedError("MAF backward is built for the inverse (log_prob) direction only")
+        g_params = torch.zeros(params.shape, dtype=params.dtype, device=params.device)
+        g_in = ops.maf_bwd(z, params, mask, g_z, g_ld, g_params, D, U, L, direction)
+        return g_in, g_params, None, None, None, None, None

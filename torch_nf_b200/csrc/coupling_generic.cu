@@ -19,11 +19,15 @@
 namespace tnf {
 
 struct CouplingShape {
-  int D, U, L, upper;
+  int D, U, L, upper, maf;
   int h, d_in, d_out, c_off, t_off, W;  // c_off: first conditioning column; t_off: first transformed column
-  __host__ __device__ CouplingShape(int D_, int U_, int L_, int upper_) : D(D_), U(U_), L(L_), upper(upper_) {
+  // maf != 0: masked autoregressive layer (reference bijectors.py:742-796): every column conditions and is
+  // transformed (d_in = d_out = D), the nets have no biases and their weights are multiplied by fixed masks.
+  __host__ __device__ CouplingShape(int D_, int U_, int L_, int upper_, int maf_ = 0)
+      : D(D_), U(U_), L(L_), upper(upper_), maf(maf_) {
     h = D / 2;
-    if (upper) { d_in = h; d_out = D - h; c_off = 0; t_off = h; }
+    if (maf) { d_in = D; d_out = D; c_off = 0; t_off = 0; }
+    else if (upper) { d_in = h; d_out = D - h; c_off = 0; t_off = h; }
     else { d_in = D - h; d_out = h; c_off = h; t_off = 0; }
     W = U > d_out ? U : d_out;
   }
@@ -37,6 +41,8 @@ struct CouplingArgs {
   const T* z_in; T* z_out; T* log_det; const T* params;
   int64_t pstride, M, N;
   int D, U, L, upper, inverse, accum, RB;
+  const float* mask;   // MAF: flat 0/1 mask in the parameter-row layout (NULL = RealNVP)
+  int passes;          // MAF forward: D-1 fixed-point passes (reference bijectors.py:751-756); else 1
 };
 
 // y[r][j] = act(sum_k in[r][k] W[k][j] + b[j]) for both nets; rows 0..RB-1 (RB % RT == 0)
@@ -44,14 +50,15 @@ template <typename T, int RT>
 __device__ __forceinline__ void mlp_layer(const T* __restrict__ in_t, const T* __restrict__ in_s, int in_stride,
                                           int K, int J, const T* __restrict__ Wt, const T* __restrict__ Ws,
                                           const T* __restrict__ bt, const T* __restrict__ bs, T* __restrict__ out_t,
-                                          T* __restrict__ out_s, int out_stride, int RB, bool act) {
+                                          T* __restrict__ out_s, int out_stride, int RB, bool act,
+                                          const float* __restrict__ mk = nullptr) {
   for (int c = threadIdx.x; c < 2 * J; c += blockDim.x) {
     const int net = c >= J;
     const int j = c - net * J;
     const T* W = net ? Ws : Wt;
     const T* in = net ? in_s : in_t;
     T* out = net ? out_s : out_t;
-    const T bias = (net ? bs : bt)[j];
+    const T bias = bt ? (net ? bs : bt)[j] : T(0);
     for (int r0 = 0; r0 < RB; r0 += RT) {
       T acc[RT];
 #pragma unroll
@@ -59,7 +66,8 @@ __device__ __forceinline__ void mlp_layer(const T* __restrict__ in_t, const T* _
       const T* inr = in + (size_t)r0 * in_stride;
 #pragma unroll 4
       for (int k = 0; k < K; ++k) {
-        const T w = W[(size_t)k * J + j];
+        T w = W[(size_t)k * J + j];
+        if (mk) w *= (T)mk[(size_t)k * J + j];
 #pragma unroll
         for (int r = 0; r < RT; ++r) acc[r] += inr[r * in_stride + k] * w;
       }
@@ -75,54 +83,67 @@ __device__ __forceinline__ void mlp_layer(const T* __restrict__ in_t, const T* _
 template <typename T, int RT>
 __global__ void coupling_generic_kernel(CouplingArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const CouplingShape sh(a.D, a.U, a.L, a.upper);
+  const CouplingShape sh(a.D, a.U, a.L, a.upper, a.mask != nullptr);
   const int RB = a.RB, D = a.D, U = a.U;
   T* bufA = reinterpret_cast<T*>(smem_raw);    // [2][RB][W]
   T* bufB = bufA + (size_t)2 * RB * sh.W;      // [2][RB][W]
   T* zt = bufB + (size_t)2 * RB * sh.W;        // [RB][D]
+  T* ut = zt + (size_t)RB * D;                 // [RB][D]  MAF forward: the fixed input u
 
   const int64_t tiles_per_m = (a.N + RB - 1) / RB;
   const int64_t m = blockIdx.x / tiles_per_m;
   const int64_t n0 = (blockIdx.x % tiles_per_m) * RB;
   const int rows = (int)((a.N - n0) < RB ? (a.N - n0) : RB);
-  const T* p = a.params + m * a.pstride;
+  const T* p0 = a.params + m * a.pstride;
   const T* zin = a.z_in + (m * a.N + n0) * D;
   T* zout = a.z_out + (m * a.N + n0) * D;
 
-  for (int e = threadIdx.x; e < RB * D; e += blockDim.x) zt[e] = e < rows * D ? zin[e] : T(0);
+  for (int e = threadIdx.x; e < RB * D; e += blockDim.x) {
+    const T v = e < rows * D ? zin[e] : T(0);
+    zt[e] = v;
+    if (sh.maf) ut[e] = v;
+  }
   __syncthreads();
 
-  // layer 0: d_in -> U on the conditioning half, both nets read the same input
-  const T* src_t = zt + sh.c_off;
-  const T* src_s = zt + sh.c_off;
-  int src_stride = D, K = sh.d_in;
-  T* cur = bufA;
-  T* nxt = bufB;
-  for (int l = 0; l <= a.L; ++l) {
-    const int J = (l == a.L) ? sh.d_out : U;
-    const T* Wt = p;
-    const T* Ws = p + (size_t)K * J;
-    const T* bt = Ws + (size_t)K * J;
-    const T* bs = bt + J;
-    mlp_layer<T, RT>(src_t, src_s, src_stride, K, J, Wt, Ws, bt, bs, cur, cur + (size_t)RB * sh.W, sh.W, RB,
-                     l < a.L);
+  const T* tt = nullptr;
+  const T* ss = nullptr;
+  for (int pass = 0; pass < a.passes; ++pass) {
+    // layer 0: d_in -> U on the conditioning columns, both nets read the same input
+    const T* p = p0;
+    const float* mk = a.mask;
+    const T* src_t = zt + sh.c_off;
+    const T* src_s = zt + sh.c_off;
+    int src_stride = D, K = sh.d_in;
+    T* cur = bufA;
+    T* nxt = bufB;
+    for (int l = 0; l <= a.L; ++l) {
+      const int J = (l == a.L) ? sh.d_out : U;
+      const T* Wt = p;
+      const T* Ws = p + (size_t)K * J;
+      const T* bt = sh.maf ? nullptr : Ws + (size_t)K * J;
+      const T* bs = sh.maf ? nullptr : bt + J;
+      mlp_layer<T, RT>(src_t, src_s, src_stride, K, J, Wt, Ws, bt, bs, cur, cur + (size_t)RB * sh.W, sh.W, RB,
+                       l < a.L, mk);
+      __syncthreads();
+      p = sh.maf ? Ws + (size_t)K * J : bs + J;
+      if (mk) mk += (size_t)2 * K * J;
+      src_t = cur;
+      src_s = cur + (size_t)RB * sh.W;
+      src_stride = sh.W;
+      K = J;
+      T* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    // src_t / src_s now hold t and s ([RB][W], first d_out columns)
+    tt = src_t;
+    ss = src_s;
+    for (int e = threadIdx.x; e < rows * sh.d_out; e += blockDim.x) {
+      const int r = e / sh.d_out, j = e - r * sh.d_out;
+      const T t = tt[(size_t)r * sh.W + j], sv = ss[(size_t)r * sh.W + j];
+      T* zp = &zt[r * D + sh.t_off + j];
+      const T z2 = (sh.maf && !a.inverse) ? ut[r * D + j] : *zp;
+      *zp = a.inverse ? (z2 - t) / t_exp<T>(sv) : t + z2 * t_exp<T>(sv);
+    }
     __syncthreads();
-    p = bs + J;
-    src_t = cur;
-    src_s = cur + (size_t)RB * sh.W;
-    src_stride = sh.W;
-    K = J;
-    T* tmp = cur; cur = nxt; nxt = tmp;
-  }
-  // src_t / src_s now hold t and s ([RB][W], first d_out columns)
-  const T* tt = src_t;
-  const T* ss = src_s;
-  for (int e = threadIdx.x; e < rows * sh.d_out; e += blockDim.x) {
-    const int r = e / sh.d_out, j = e - r * sh.d_out;
-    const T t = tt[(size_t)r * sh.W + j], s = ss[(size_t)r * sh.W + j];
-    T* zp = &zt[r * D + sh.t_off + j];
-    const T z2 = *zp;
-    *zp = a.inverse ? (z2 - t) / t_exp<T>(s) : t + z2 * t_exp<T>(s);
   }
   for (int r = threadIdx.x; r < rows; r += blockDim.x) {
     T ld = T(0);
@@ -132,7 +153,6 @@ __global__ void coupling_generic_kernel(CouplingArgs<T> a) {
     else if (a.accum == TNF_LD_ADD) *o += ld;
     else *o -= ld;
   }
-  __syncthreads();
   for (int e = threadIdx.x; e < rows * D; e += blockDim.x) zout[e] = zt[e];
 }
 
@@ -142,6 +162,7 @@ struct CouplingBwdArgs {
   const T* z_in; const T* params; const T* g_y; const T* g_ld; T* g_z; T* g_params;
   int64_t pstride, gstride, M, N;
   int D, U, L, upper, inverse, RB, atomic_params;
+  const float* mask;   // MAF (inverse direction only); NULL = RealNVP
 };
 
 template <typename T>
@@ -157,12 +178,14 @@ __device__ __forceinline__ void grad_add(T* addr, T v, int use_atomic) {
 template <typename T, int RT>
 __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const CouplingShape sh(a.D, a.U, a.L, a.upper);
+  const CouplingShape sh(a.D, a.U, a.L, a.upper, a.mask != nullptr);
   const int RB = a.RB, D = a.D, U = a.U, L = a.L, W = sh.W;
+  const int nbias = sh.maf ? 0 : 1;   // MAF nets have no biases
   T* zt = reinterpret_cast<T*>(smem_raw);
   T* act = zt + (size_t)RB * D;
   T* dl = act + (size_t)2 * L * RB * U;
   T* gz1 = dl + (size_t)4 * RB * W;  // [RB][d_in]
+  T* gdir = gz1 + (size_t)RB * sh.d_in;  // [RB][D]  MAF: direct part of g_z (zt must stay intact: it is the layer-0 input)
   auto ACT = [&](int net, int l) { return act + ((size_t)(net * L + l) * RB) * U; };  // output of layer l
   auto DL = [&](int buf, int net) { return dl + ((size_t)(buf * 2 + net) * RB) * W; };
 
@@ -183,18 +206,22 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
   // ---- recompute the conditioner, keeping every hidden activation
   {
     const T* p = p0;
+    const float* mk = a.mask;
     const T* src_t = zt + sh.c_off;
     const T* src_s = src_t;
     int src_stride = D, K = sh.d_in;
     for (int l = 0; l < L; ++l) {
-      const T* Wt = p; const T* Ws = p + (size_t)K * U; const T* bt = Ws + (size_t)K * U; const T* bs = bt + U;
-      mlp_layer<T, RT>(src_t, src_s, src_stride, K, U, Wt, Ws, bt, bs, ACT(0, l), ACT(1, l), U, RB, true);
+      const T* Wt = p; const T* Ws = p + (size_t)K * U;
+      const T* bt = nbias ? Ws + (size_t)K * U : nullptr; const T* bs = nbias ? bt + U : nullptr;
+      mlp_layer<T, RT>(src_t, src_s, src_stride, K, U, Wt, Ws, bt, bs, ACT(0, l), ACT(1, l), U, RB, true, mk);
       __syncthreads();
-      p = bs + U; src_t = ACT(0, l); src_s = ACT(1, l); src_stride = U; K = U;
+      p = Ws + (size_t)K * U + (size_t)nbias * 2 * U;
+      if (mk) mk += (size_t)2 * K * U;
+      src_t = ACT(0, l); src_s = ACT(1, l); src_stride = U; K = U;
     }
-    const T* Wt = p; const T* Ws = p + (size_t)K * sh.d_out; const T* bt = Ws + (size_t)K * sh.d_out;
-    const T* bs = bt + sh.d_out;
-    mlp_layer<T, RT>(src_t, src_s, src_stride, K, sh.d_out, Wt, Ws, bt, bs, DL(1, 0), DL(1, 1), W, RB, false);
+    const T* Wt = p; const T* Ws = p + (size_t)K * sh.d_out;
+    const T* bt = nbias ? Ws + (size_t)K * sh.d_out : nullptr; const T* bs = nbias ? bt + sh.d_out : nullptr;
+    mlp_layer<T, RT>(src_t, src_s, src_stride, K, sh.d_out, Wt, Ws, bt, bs, DL(1, 0), DL(1, 1), W, RB, false, mk);
     __syncthreads();
   }
   // ---- output deltas: DL(0,net) <- d loss / d (t, s); g_z2 into zt
@@ -210,13 +237,14 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
         const T g2 = gy ? gy[r * D + sh.t_off + j] : T(0);
         const T gl = gld ? gld[r] : T(0);
         const T es = t_exp<T>(s);
+        T* direct = sh.maf ? &gdir[r * D + j] : &zt[r * D + sh.t_off + j];
         if (!a.inverse) {
           g_t = g2; g_s = g2 * z2 * es + gl;
-          zt[r * D + sh.t_off + j] = g2 * es;
+          *direct = g2 * es;
         } else {
           const T y2 = (z2 - t) / es;
           g_t = -g2 / es; g_s = -g2 * y2 + gl;
-          zt[r * D + sh.t_off + j] = g2 / es;
+          *direct = g2 / es;
         }
       }
       dt[(size_t)r * W + j] = g_t;
@@ -230,11 +258,12 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
   for (int l = L; l >= 0; --l) {
     const int K = (l == 0) ? sh.d_in : U;
     const int J = (l == L) ? sh.d_out : U;
-    // offset of layer l inside the parameter row
+    // offset of layer l inside the parameter row (MAF rows carry no biases)
     int64_t off = 0;
-    if (l >= 1) off += 2 * ((int64_t)sh.d_in * U + U);
-    if (l >= 2) off += (int64_t)(l - 1) * 2 * ((int64_t)U * U + U);
+    if (l >= 1) off += 2 * ((int64_t)sh.d_in * U + nbias * U);
+    if (l >= 2) off += (int64_t)(l - 1) * 2 * ((int64_t)U * U + nbias * U);
     const T* Wt = p0 + off; const T* Ws = Wt + (size_t)K * J;
+    const float* mk = a.mask ? a.mask + off : nullptr;
     T* gWt = gp0 + off; T* gWs = gWt + (size_t)K * J; T* gbt = gWs + (size_t)K * J; T* gbs = gbt + J;
     const T* in_t = (l == 0) ? zt + sh.c_off : ACT(0, l - 1);
     const T* in_s = (l == 0) ? zt + sh.c_off : ACT(1, l - 1);
@@ -247,16 +276,19 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
       const int k = (int)(kj / J), j = (int)(kj - (int64_t)k * J);
       const T* in = net ? in_s : in_t;
       const T* dd = net ? ds : dt;
-      T s = T(0);
-      for (int r = 0; r < rows; ++r) s += in[(size_t)r * in_stride + k] * dd[(size_t)r * W + j];
-      grad_add<T>((net ? gWs : gWt) + kj, s, a.atomic_params);
+      T sacc = T(0);
+      for (int r = 0; r < rows; ++r) sacc += in[(size_t)r * in_stride + k] * dd[(size_t)r * W + j];
+      if (mk) sacc *= (T)mk[kj];
+      grad_add<T>((net ? gWs : gWt) + kj, sacc, a.atomic_params);
     }
-    for (int c = threadIdx.x; c < 2 * J; c += blockDim.x) {
-      const int net = c >= J; const int j = c - net * J;
-      const T* dd = net ? ds : dt;
-      T s = T(0);
-      for (int r = 0; r < rows; ++r) s += dd[(size_t)r * W + j];
-      grad_add<T>((net ? gbs : gbt) + j, s, a.atomic_params);
+    if (nbias) {
+      for (int c = threadIdx.x; c < 2 * J; c += blockDim.x) {
+        const int net = c >= J; const int j = c - net * J;
+        const T* dd = net ? ds : dt;
+        T sacc = T(0);
+        for (int r = 0; r < rows; ++r) sacc += dd[(size_t)r * W + j];
+        grad_add<T>((net ? gbs : gbt) + j, sacc, a.atomic_params);
+      }
     }
     // input deltas
     if (l > 0) {
@@ -271,7 +303,8 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
 #pragma unroll
           for (int r = 0; r < RT; ++r) acc[r] = T(0);
           for (int j = 0; j < J; ++j) {
-            const T w = Wn[(size_t)k * J + j];
+            T w = Wn[(size_t)k * J + j];
+            if (mk) w *= (T)mk[(size_t)k * J + j];
 #pragma unroll
             for (int r = 0; r < RT; ++r) acc[r] += dd[(size_t)(r0 + r) * W + j] * w;
           }
@@ -289,7 +322,8 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
 #pragma unroll
           for (int r = 0; r < RT; ++r) acc[r] = T(0);
           for (int j = 0; j < J; ++j) {
-            const T wt = Wt[(size_t)k * J + j], ws = Ws[(size_t)k * J + j];
+            T wt = Wt[(size_t)k * J + j], ws = Ws[(size_t)k * J + j];
+            if (mk) { const T mm = (T)mk[(size_t)k * J + j]; wt *= mm; ws *= mm; }
 #pragma unroll
             for (int r = 0; r < RT; ++r)
               acc[r] += dt[(size_t)(r0 + r) * W + j] * wt + ds[(size_t)(r0 + r) * W + j] * ws;
@@ -306,7 +340,8 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
   for (int e = threadIdx.x; e < rows * D; e += blockDim.x) {
     const int r = e / D, d = e - r * D;
     T v;
-    if (d >= sh.t_off && d < sh.t_off + sh.d_out) v = zt[e];
+    if (sh.maf) v = gdir[e] + gz1[(size_t)r * sh.d_in + d];     // every column is transformed AND conditions
+    else if (d >= sh.t_off && d < sh.t_off + sh.d_out) v = zt[e];
     else v = (gy ? gy[e] : T(0)) + gz1[(size_t)r * sh.d_in + (d - sh.c_off)];
     gz[e] = v;
   }
@@ -329,15 +364,17 @@ static int validate(const char* what, int64_t M, int64_t N, int D, int U, int L)
 
 template <typename T>
 static int launch_fwd(const void* z_in, void* z_out, void* log_det, const void* params, int64_t pstride, int64_t M,
-                      int64_t N, int D, int U, int L, int upper, int direction, int accum, cudaStream_t st) {
-  CouplingShape sh(D, U, L, upper);
+                      int64_t N, int D, int U, int L, int upper, int direction, int accum, cudaStream_t st,
+                      const float* mask = nullptr) {
+  CouplingShape sh(D, U, L, upper, mask != nullptr);
   const size_t budget = 200 * 1024;
-  size_t per_row = ((size_t)4 * sh.W + D) * sizeof(T);
+  size_t per_row = ((size_t)4 * sh.W + 2 * D) * sizeof(T);
   int RB = pick_rb<T>(N, per_row, 0, budget);
   TNF_REQUIRE(per_row * RB <= budget, TNF_ERR_UNSUPPORTED, "tnf_coupling: shape needs %zu B smem", per_row * RB);
   size_t smem = per_row * RB;
   CouplingArgs<T> a{(const T*)z_in, (T*)z_out, (T*)log_det, (const T*)params, pstride, M, N,
-                    D, U, L, upper, direction == TNF_INVERSE, accum, RB};
+                    D, U, L, upper, direction == TNF_INVERSE, accum, RB, mask,
+                    (mask != nullptr && direction != TNF_INVERSE) ? (D - 1 > 0 ? D - 1 : 1) : 1};
   int64_t tiles = M * ((N + RB - 1) / RB);
   TNF_REQUIRE(tiles < (int64_t)1 << 31, TNF_ERR_UNSUPPORTED, "tnf_coupling: too many tiles");
   int nt = 2 * sh.W;
@@ -358,17 +395,17 @@ static int launch_fwd(const void* z_in, void* z_out, void* log_det, const void* 
 template <typename T>
 static int launch_bwd(const void* z_in, const void* params, int64_t pstride, const void* g_y, const void* g_ld,
                       void* g_z, void* g_params, int64_t gstride, int64_t M, int64_t N, int D, int U, int L,
-                      int upper, int direction, cudaStream_t st) {
-  CouplingShape sh(D, U, L, upper);
+                      int upper, int direction, cudaStream_t st, const float* mask = nullptr) {
+  CouplingShape sh(D, U, L, upper, mask != nullptr);
   const size_t budget = 200 * 1024;
-  size_t per_row = ((size_t)D + (size_t)2 * L * U + (size_t)4 * sh.W + sh.d_in) * sizeof(T);
+  size_t per_row = ((size_t)2 * D + (size_t)2 * L * U + (size_t)4 * sh.W + sh.d_in) * sizeof(T);
   int RB = pick_rb<T>(N, per_row, 0, budget);
   TNF_REQUIRE(per_row * RB <= budget, TNF_ERR_UNSUPPORTED, "tnf_coupling_bwd: shape needs %zu B smem", per_row * RB);
   size_t smem = per_row * RB;
   int64_t tiles_per_m = (N + RB - 1) / RB;
   int atomic_params = (gstride == 0 && M * tiles_per_m > 1) || tiles_per_m > 1;
   CouplingBwdArgs<T> a{(const T*)z_in, (const T*)params, (const T*)g_y, (const T*)g_ld, (T*)g_z, (T*)g_params,
-                       pstride, gstride, M, N, D, U, L, upper, direction == TNF_INVERSE, RB, atomic_params};
+                       pstride, gstride, M, N, D, U, L, upper, direction == TNF_INVERSE, RB, atomic_params, mask};
   int64_t tiles = M * tiles_per_m;
   TNF_REQUIRE(tiles < (int64_t)1 << 31, TNF_ERR_UNSUPPORTED, "tnf_coupling_bwd: too many tiles");
   int nt = 2 * sh.W;
@@ -413,6 +450,31 @@ int tnf_coupling_bwd(const void* z_in, const void* params, int64_t pstride, cons
   TNF_REQUIRE(z_in && params && g_z_in && g_params, TNF_ERR_ARG, "tnf_coupling_bwd: null pointer");
   TNF_DISPATCH(dtype, return launch_bwd<T>(z_in, params, pstride, g_z_out, g_log_det, g_z_in, g_params, gstride, M, N,
                                            D, U, L, transform_upper != 0, direction, (cudaStream_t)stream));
+  return 0;
+}
+
+int tnf_maf(const void* z_in, void* z_out, void* log_det, const void* params, int64_t pstride, const float* mask,
+            int64_t M, int64_t N, int D, int U, int L, int direction, int accum, int dtype, tnf_stream_t stream) {
+  int rc = validate("tnf_maf", M, N, D, U, L);
+  if (rc) return rc;
+  if (M == 0 || N == 0) return 0;
+  TNF_REQUIRE(z_in && z_out && log_det && params && mask, TNF_ERR_ARG, "tnf_maf: null pointer");
+  TNF_DISPATCH(dtype, return launch_fwd<T>(z_in, z_out, log_det, params, pstride, M, N, D, U, L, 1, direction, accum,
+                                           (cudaStream_t)stream, mask));
+  return 0;
+}
+
+int tnf_maf_bwd(const void* z_in, const void* params, int64_t pstride, const float* mask, const void* g_z_out,
+                const void* g_log_det, void* g_z_in, void* g_params, int64_t gstride, int64_t M, int64_t N, int D,
+                int U, int L, int direction, int dtype, tnf_stream_t stream) {
+  int rc = validate("tnf_maf_bwd", M, N, D, U, L);
+  if (rc) return rc;
+  TNF_REQUIRE(direction == TNF_INVERSE, TNF_ERR_UNSUPPORTED,
+              "tnf_maf_bwd: only the inverse (log_prob) direction has a backward");
+  if (M == 0 || N == 0) return 0;
+  TNF_REQUIRE(z_in && params && mask && g_z_in && g_params, TNF_ERR_ARG, "tnf_maf_bwd: null pointer");
+  TNF_DISPATCH(dtype, return launch_bwd<T>(z_in, params, pstride, g_z_out, g_log_det, g_z_in, g_params, gstride, M, N,
+                                           D, U, L, 1, direction, (cudaStream_t)stream, mask));
   return 0;
 }
 

@@ -136,6 +136,40 @@ def coupling_bwd(z_in, params, g_z_out, g_ld, g_params, D, U, L, upper, directio
     return g_z
 
 
+# ----------------------------------------------------------------- MAF
+def maf(z, params, mask, D, U, L, direction, ld=None, accum=TNF_LD_WRITE):
+    z = _check3(z)
+    M, N, _ = z.shape
+    params, pstride = param_view(params, mask.numel())
+    Mp = _match_rows(z, params)
+    z_out = torch.empty_like(z)
+    if ld is None:
+        ld = torch.empty((M, N), dtype=z.dtype, device=z.device)
+        accum = TNF_LD_WRITE
+    Mk, Nk = (1, M * N) if Mp == 1 else (M, N)
+    rc = _lib.lib().tnf_maf(z.data_ptr(), z_out.data_ptr(), ld.data_ptr(), params.data_ptr(), pstride,
+                            mask.data_ptr(), Mk, Nk, D, U, L, direction, accum, _dt(z), _stream())
+    _lib.check(rc, "tnf_maf")
+    return z_out, ld
+
+
+def maf_bwd(z_in, params, mask, g_z_out, g_ld, g_params, D, U, L, direction):
+    z_in = _check3(z_in)
+    M, N, _ = z_in.shape
+    params, pstride = param_view(params, mask.numel())
+    Mp = _match_rows(z_in, params)
+    gstride = g_params.stride(0) if Mp > 1 else 0
+    g_z_out = None if g_z_out is None else g_z_out.contiguous()
+    g_ld = None if g_ld is None else g_ld.contiguous()
+    g_z = torch.empty_like(z_in)
+    Mk, Nk = (1, M * N) if Mp == 1 else (M, N)
+    rc = _lib.lib().tnf_maf_bwd(z_in.data_ptr(), params.data_ptr(), pstride, mask.data_ptr(), _ptr(g_z_out),
+                                _ptr(g_ld), g_z.data_ptr(), g_params.data_ptr(), gstride, Mk, Nk, D, U, L,
+                                direction, _dt(z_in), _stream())
+    _lib.check(rc, "tnf_maf_bwd")
+    return g_z
+
+
 # ----------------------------------------------------------------- tensor-core coupling
 def tc_supported(D, U, L):
     return bool(_lib.lib().tnf_tc_supported(D, U, L))
