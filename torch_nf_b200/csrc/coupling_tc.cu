@@ -360,26 +360,33 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
   const uint32_t tmem = ct.tmem_base;
   if (warp == kEpiWarps + 1) {
     // =============================== weight producer (one elected lane) ===============================
+    // Job j of a group = (iteration, net, layer) = (j / JT, (j % JT) / (L+1), j % (L+1)), JT = 2(L+1) jobs per tile.
+    // Static service order: group 1 runs half a tile (L+1 jobs) behind group 0, so one group's tile tail / head
+    // (global loads and stores, no MUFU work) coincides with the other group's mid-tile tanh epilogues.
     if (elect_one()) {
       uint32_t slot = 0, phase = 0;
-      for (int64_t it = 0; it < iters; ++it) {
-        for (int net = 0; net < 2; ++net) {
-          const unsigned char* lsrc = a.packed;
-          for (int l = 0; l <= sh.L; ++l) {
-            const int K = sh.K_of(l), J = sh.J_of(l), N = sh.N_of(l);
-            const int ks = sh.stage_k(K, N);
-            const uint32_t bytes = (uint32_t)(ks * N * 2);
-            const int n_st = sh.halves(l) * (K / ks);
-            const unsigned char* nsrc = lsrc + (size_t)net * K * J * 2;
-            for (int g = 0; g < G; ++g) {        // the same weights once per group
-              for (int s = 0; s < n_st; ++s) {
-                mbar_wait(&ct.w_empty[slot], phase ^ 1);
-                mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
-                bulk_g2s(ring + (size_t)slot * stage_bytes, nsrc + (size_t)s * bytes, bytes, &ct.w_full[slot]);
-                if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
-              }
-            }
-            lsrc += (size_t)2 * K * J * 2;
+      const int JT = 2 * (sh.L + 1);
+      const int64_t n_jobs = iters * JT;
+      const int shift = (G > 1) ? sh.L + 1 : 0;
+      for (int64_t n = 0; n < n_jobs + shift; ++n) {
+        for (int g = 0; g < G; ++g) {
+          const int64_t j = n - (g ? shift : 0);
+          if (j < 0 || j >= n_jobs) continue;
+          const int jj = (int)(j % JT);
+          const int net = jj / (sh.L + 1), l = jj % (sh.L + 1);
+          // byte offset of (layer l, net) in the packed stream
+          size_t off = 0;
+          for (int i = 0; i < l; ++i) off += (size_t)2 * sh.K_of(i) * sh.J_of(i) * 2;
+          const int K = sh.K_of(l), J = sh.J_of(l), N = sh.N_of(l);
+          const int ks = sh.stage_k(K, N);
+          const uint32_t bytes = (uint32_t)(ks * N * 2);
+          const int n_st = sh.halves(l) * (K / ks);
+          const unsigned char* nsrc = a.packed + off + (size_t)net * K * J * 2;
+          for (int st = 0; st < n_st; ++st) {
+            mbar_wait(&ct.w_empty[slot], phase ^ 1);
+            mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
+            bulk_g2s(ring + (size_t)slot * stage_bytes, nsrc + (size_t)st * bytes, bytes, &ct.w_full[slot]);
+            if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
           }
         }
       }
@@ -388,51 +395,64 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
     // =============================== MMA issuer (warp-uniform, elected lane issues) ===============================
     const bool leader = elect_one();
     uint32_t slot = 0, phase = 0, a1_phase = 0, e_phase = 0;
-    long long t_dep = 0, t_w = 0, t_all = clock64();   // diagnostics: cycles waiting on epilogue / on weights
+    const bool diag = a.dbg != nullptr;   // diagnostics: cycles waiting on epilogue / on weights
+    long long t_dep = 0, t_w = 0, t_all = diag ? clock64() : 0;
     const uint32_t ring_addr = smem_u32(ring);
     const uint32_t a1_addr = smem_u32(sA1), act_addr = smem_u32(sAct);
     const uint32_t a1_sz = (uint32_t)sh.a1_bytes(), act_sz = (uint32_t)sh.act_bytes();
-    for (int64_t it = 0; it < iters; ++it) {
-      for (int net = 0; net < 2; ++net) {
-        for (int l = 0; l <= sh.L; ++l) {
-          const int K = sh.K_of(l), N = sh.N_of(l), halves = sh.halves(l);
-          const int ks = sh.stage_k(K, N);
-          const uint32_t idesc = make_idesc(N);
-          for (int g = 0; g < G; ++g) {
-            const long long c0 = clock64();
-            if (net == 0 && l == 0) {
-              mbar_wait(&ct.a1_ready[g], (a1_phase >> g) & 1);
-              a1_phase ^= 1u << g;
-            } else {
-              mbar_wait(&ct.e_done[g], (e_phase >> g) & 1);
-              e_phase ^= 1u << g;
-            }
+    const int JT = 2 * (sh.L + 1);
+    const int64_t n_jobs = iters * JT;
+    const int shift = (G > 1) ? sh.L + 1 : 0;   // see the producer: group 1 trails group 0 by half a tile
+    for (int64_t n = 0; n < n_jobs + shift; ++n) {
+      for (int g = 0; g < G; ++g) {
+        const int64_t j = n - (g ? shift : 0);
+        if (j < 0 || j >= n_jobs) continue;
+        const int jj = (int)(j % JT);
+        const int net = jj / (sh.L + 1), l = jj % (sh.L + 1);
+        const int K = sh.K_of(l), N = sh.N_of(l), halves = sh.halves(l);
+        const int ks = sh.stage_k(K, N);
+        const uint32_t idesc = make_idesc(N);
+        const long long c0 = diag ? clock64() : 0;
+        if (net == 0 && l == 0) {
+          mbar_wait(&ct.a1_ready[g], (a1_phase >> g) & 1);
+          a1_phase ^= 1u << g;
+        } else {
+          mbar_wait(&ct.e_done[g], (e_phase >> g) & 1);
+          e_phase ^= 1u << g;
+        }
+        tc_fence_after();
+        if (diag) t_dep += clock64() - c0;
+        const uint32_t a_addr = (l == 0) ? a1_addr + g * a1_sz : act_addr + g * act_sz;
+        const uint64_t a_base = make_desc(a_addr, kTileM);
+        const uint64_t b_base = make_desc(0u, N);                 // + (stage address >> 4)
+        const uint32_t a_step = (2u * kTileM * 16u) >> 4, b_step = (2u * (uint32_t)N * 16u) >> 4;
+        for (int hb = 0; hb < halves; ++hb) {
+          const uint32_t d_tmem = tmem + (uint32_t)g * 256u + (uint32_t)(hb * sh.Nh);
+          for (int k0 = 0; k0 < K; k0 += ks) {
+            const long long c1 = diag ? clock64() : 0;
+            mbar_wait(&ct.w_full[slot], phase);
             tc_fence_after();
-            t_dep += clock64() - c0;
-            const uint32_t a_addr = (l == 0) ? a1_addr + g * a1_sz : act_addr + g * act_sz;
-            for (int hb = 0; hb < halves; ++hb) {
-              const uint32_t d_tmem = tmem + (uint32_t)g * 256u + (uint32_t)(hb * sh.Nh);
-              for (int k0 = 0; k0 < K; k0 += ks) {
-                const long long c1 = clock64();
-                mbar_wait(&ct.w_full[slot], phase);
-                tc_fence_after();
-                t_w += clock64() - c1;
-                const uint32_t b_addr = ring_addr + slot * stage_bytes;
-                if (leader) {
-                  for (int kk = 0; kk < ks; kk += 16) {
-                    const uint64_t adesc = make_desc(a_addr + (uint32_t)((k0 + kk) >> 3) * (kTileM * 16u), kTileM);
-                    const uint64_t bdesc = make_desc(b_addr + (uint32_t)(kk >> 3) * (uint32_t)N * 16u, N);
-                    umma_ss(d_tmem, adesc, bdesc, idesc, (k0 + kk) > 0 ? 1u : 0u);
-                  }
-                  tc_commit(&ct.w_empty[slot]);
-                }
-                __syncwarp();
-                if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+            if (diag) t_w += clock64() - c1;
+            // descriptors advance by constants: one K=16 step = two 8-column K groups = 2*rows*16 bytes
+            const uint64_t ad = a_base + (uint64_t)(((uint32_t)k0 >> 4) * a_step);
+            const uint64_t bd = b_base + (uint64_t)((ring_addr + slot * stage_bytes) >> 4);
+            if (leader) {
+              const uint32_t acc0 = k0 > 0 ? 1u : 0u;
+              if (ks == 32) {
+                umma_ss(d_tmem, ad, bd, idesc, acc0);
+                umma_ss(d_tmem, ad + a_step, bd + b_step, idesc, 1u);
+              } else {
+#pragma unroll 4
+                for (int kq = 0; kq < ks / 16; ++kq)
+                  umma_ss(d_tmem, ad + (uint64_t)kq * a_step, bd + (uint64_t)kq * b_step, idesc, (kq > 0) ? 1u : acc0);
               }
-              if (leader) tc_commit(&ct.h_ready[g][hb]);
-              __syncwarp();
+              tc_commit(&ct.w_empty[slot]);
             }
+            __syncwarp();
+            if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
           }
+          if (leader) tc_commit(&ct.h_ready[g][hb]);
+          __syncwarp();
         }
       }
     }
