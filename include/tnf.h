@@ -95,8 +95,11 @@ int tnf_maf_bwd(const void* z_in, const void* params, int64_t param_row_stride, 
  * pre_scale/pre_shift (D floats each, or NULL): per-column affine
  * z <- z*pre_scale + pre_shift applied on load, which is how BatchNorm /
  * Affine neighbours (bijectors.py:292,399,423-424) are folded in.
- * col_stats (or NULL): [2*D] doubles, accumulates sum and sum of squares of
- * the OUTPUT columns (the next BatchNorm's batch statistics, :401-410). */
+ * col_stats (or NULL): receives [sum(D) | sumsq(D) | rows] (float64, the layout of
+ * tnf_colstats) of the OUTPUT columns = the next BatchNorm's batch statistics
+ * (:401-410), accumulated inside the kernel (fp32 per warp, float64 across warps);
+ * needs stats_workspace of tnf_colstats_workspace_bytes(D) bytes; D = 64 only.
+ * z_out must not alias z_in. */
 int tnf_tc_supported(int D, int U, int L);
 /* diagnostic: out[128 x N] = bf16(A[128 x K]) . bf16(W[K x N]) through the same
  * operand images, UMMA descriptors and TMEM accumulator layout as the fused
@@ -114,7 +117,7 @@ int tnf_tc_pack(const float* params, void* packed, int D, int U, int L, int tran
 int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void* packed,
                     int64_t rows, int D, int U, int L, int transform_upper, int direction,
                     int accum, const float* pre_scale, const float* pre_shift,
-                    double* col_stats, tnf_stream_t stream);
+                    double* col_stats, void* stats_workspace, tnf_stream_t stream);
 
 /* ---- Affine: replaces Affine.forward_and_log_det / inverse_and_log_det
  * (bijectors.py:277-315).  params row = [alpha(D), shift(D)].

@@ -107,3 +107,20 @@ def test_normflow_bf16_mode_c3(golden):
     dlp = np.abs(lp.cpu().numpy() - g["log_prob"]) / np.maximum(1.0, np.abs(g["log_prob"]))
     assert dz <= 1e-1, dz                 # 8 coupling layers + BatchNorm amplification
     assert dlq.max() <= 4e-3 and dlp.max() <= 4e-3, (dlq.max(), dlp.max())
+
+
+def test_coupling_tc_fused_column_stats():
+    """The kernel's own [sum | sumsq | rows] of its output equals tnf_colstats on that output."""
+    D, U, L = 64, 256, 2
+    for N, upper in ((1000, True), (128 * 148 * 2 + 77, False), (90, True)):
+        params = T(synthetic_params([("RealNVP", L, U, upper)], D, 1, seed=21))
+        z_in = torch.randn(1, N, D, device="cuda") * 1.5 + 0.3
+        packed = ops.tc_pack(params.cuda()[0], D, U, L, upper)
+        ps = (torch.rand(D) + 0.5).cuda(); pb = torch.randn(D).cuda()
+        z, ld, sums = ops.coupling_tc(z_in, packed, D, U, L, upper, ops.TNF_FORWARD, pre_scale=ps, pre_shift=pb,
+                                      want_stats=True)
+        ref = ops.colstats(z, D)
+        assert float(sums[2 * D]) == N == float(ref[2 * D])
+        np.testing.assert_allclose(sums[:2 * D].cpu().numpy(), ref[:2 * D].cpu().numpy(), rtol=2e-5, atol=2e-3 * N ** 0.5)
+        z2, _ = ops.coupling_tc(z_in, packed, D, U, L, upper, ops.TNF_FORWARD, pre_scale=ps, pre_shift=pb)
+        assert torch.equal(z, z2)

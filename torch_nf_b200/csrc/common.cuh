@@ -11,6 +11,8 @@ namespace tnf {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int num_sms();
+// sums[2D+1] = column-wise sum of partial[nblocks][2][D] (fixed order) and the row count
+int colstats_reduce_launch(const double* partial, int nblocks, int D, double* sums, double rows, cudaStream_t st);
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -283,6 +283,7 @@ struct Args {
   const float* pre_scale; const float* pre_shift;
   int64_t rows;
   int D, U, L, upper, inverse, accum, n_stages, n_groups;
+  double* stat_partials;   // [grid*8 warps][2][D] per-warp column sums of the OUTPUT (NULL = off)
   long long* dbg;   // diagnostics: per-phase clock64 stamps of CTA 0 (NULL = off)
 };
 
@@ -301,6 +302,21 @@ struct __align__(16) Ctrl {
 __host__ __device__ inline size_t smem_bytes(const Shape& sh, int n_stages) {
   return (size_t)n_stages * sh.stage_elems() * 2 + 2 * sh.a1_bytes() + 2 * sh.act_bytes() + sizeof(Ctrl) +
          (size_t)(2 * sh.net_bias_elems() + 2 * sh.D) * sizeof(float);
+}
+
+// Sum over the 32 lanes of v[j] for every j, by recursive halving: 31 shuffles; lane l returns column l's sum.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? v[i] : v[i + off];
+      const float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
 }
 
 __device__ __forceinline__ float exp2_fast(float x) {
@@ -537,6 +553,8 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
       if (lane == 0) mbar_arrive(&ct.a1_ready[g]);
     };
 
+    float st_y = 0.f, st_y2 = 0.f, st_v = 0.f, st_v2 = 0.f;   // per-lane column sums (lane = column of the half)
+    const bool want_stats = kRegs && a.stat_partials != nullptr;
     // ---- first tile of this group: load and publish A1, store the pass-through half
     {
       const int64_t tile = (int64_t)g * gridDim.x + blockIdx.x;
@@ -556,6 +574,15 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
 #pragma unroll
         for (int j = 0; j < DH; j += 4)
           *reinterpret_cast<float4*>(a.z_out + row * sh.D + sh.c_off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      if (want_stats) {
+        if (DH == 32) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1[j] = valid ? v[DH == 32 ? j : 0] : 0.f; s2[j] = s1[j] * s1[j]; }
+          st_v += warp_transpose_sum(s1, lane);
+          st_v2 += warp_transpose_sum(s2, lane);
+        }
       }
     }
     for (int64_t it = 0; it < iters; ++it) {
@@ -702,6 +729,19 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
             for (int j = 0; j < DH; j += 4)
               *reinterpret_cast<float4*>(a.z_out + nrow * sh.D + sh.c_off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
+          if (want_stats) {
+            if (DH == 32) {
+              float s1[32], s2[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { s1[j] = valid ? y[DH == 32 ? j : 0] : 0.f; s2[j] = s1[j] * s1[j]; }
+              st_y += warp_transpose_sum(s1, lane);
+              st_y2 += warp_transpose_sum(s2, lane);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { s1[j] = nvalid ? v[DH == 32 ? j : 0] : 0.f; s2[j] = s1[j] * s1[j]; }
+              st_v += warp_transpose_sum(s1, lane);
+              st_v2 += warp_transpose_sum(s2, lane);
+            }
+          }
         } else {
           // large D: stream the transformed half in 16-column pieces (t was parked in z_out)
 #pragma unroll 1
@@ -747,6 +787,16 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
       TNF_STAMP(600);
     }
 #undef TNF_STAMP
+    if (want_stats) {   // one [2][D] block of doubles per epilogue warp
+      double* out = a.stat_partials + ((size_t)blockIdx.x * kEpiWarps + warp) * 2 * sh.D;
+      out[sh.t_off + lane] = (double)st_y;
+      out[sh.D + sh.t_off + lane] = (double)st_y2;
+      out[sh.c_off + lane] = (double)st_v;
+      out[sh.D + sh.c_off + lane] = (double)st_v2;
+    }
+  } else if (warp < kEpiWarps && a.stat_partials != nullptr) {   // idle epilogue group (solo mode): zero block
+    double* out = a.stat_partials + ((size_t)blockIdx.x * kEpiWarps + warp) * 2 * sh.D;
+    for (int i = lane; i < 2 * sh.D; i += 32) out[i] = 0.0;
   }
   // ---- teardown
   tc_fence_before();
@@ -856,7 +906,7 @@ int tnf_tc_pack(const float* params, void* packed, int D, int U, int L, int tran
 
 int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void* packed, int64_t rows, int D, int U,
                     int L, int transform_upper, int direction, int accum, const float* pre_scale,
-                    const float* pre_shift, double* col_stats, tnf_stream_t stream) {
+                    const float* pre_shift, double* col_stats, void* stats_workspace, tnf_stream_t stream) {
   TNF_REQUIRE(tc::shape_supported(D, U, L), TNF_ERR_UNSUPPORTED,
               "tnf_coupling_tc: shape D=%d U=%d L=%d not supported", D, U, L);
   TNF_REQUIRE(rows >= 0, TNF_ERR_ARG, "tnf_coupling_tc: rows < 0");
@@ -864,7 +914,8 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   TNF_REQUIRE(z_in && z_out && log_det && packed, TNF_ERR_ARG, "tnf_coupling_tc: null pointer");
   TNF_REQUIRE((((uintptr_t)z_in | (uintptr_t)z_out | (uintptr_t)packed) & 15) == 0, TNF_ERR_ALIGN,
               "tnf_coupling_tc: z and packed weights must be 16-byte aligned");
-  TNF_REQUIRE(col_stats == nullptr, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: fused column statistics not built yet");
+  TNF_REQUIRE(col_stats == nullptr || (D == 64 && stats_workspace != nullptr), TNF_ERR_UNSUPPORTED,
+              "tnf_coupling_tc: fused column statistics need D = 64 and a workspace");
   tc::Shape sh(D, U, L, transform_upper != 0);
   // as many 16 KB weight stages as fit next to the activation images (227 KB per CTA)
   int n_stages = tc::kMaxStages;
@@ -872,7 +923,8 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   const size_t smem = tc::smem_bytes(sh, n_stages);
   TNF_REQUIRE(smem <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem);
   tc::Args a{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
-             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_groups, g_tc_debug};
+             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_groups,
+             col_stats ? (double*)stats_workspace : nullptr, g_tc_debug};
   const int64_t n_tiles = (rows + tc::kTileM - 1) / tc::kTileM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;
@@ -892,7 +944,9 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
     set_error("tnf_coupling_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e));
     return (int)e;
   }
-  return check_launch("tnf_coupling_tc");
+  int rc = check_launch("tnf_coupling_tc");
+  if (rc || col_stats == nullptr) return rc;
+  return colstats_reduce_launch((const double*)stats_workspace, grid * tc::kEpiWarps, D, col_stats, (double)rows, st);
 }
 
 int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N, int a_in_tmem,

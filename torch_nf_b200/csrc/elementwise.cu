@@ -646,6 +646,11 @@ __global__ void colaffine_kernel(const float* __restrict__ z_in, float* __restri
 
 static inline int rowgroup_grid(int64_t rows, int G) { return grid_for(rows * G, 256, 16); }
 
+int colstats_reduce_launch(const double* partial, int nblocks, int D, double* sums, double rows, cudaStream_t st) {
+  colstats_reduce_kernel<<<(2 * D + 1 + 7) / 8, 256, 0, st>>>(partial, nblocks, D, sums, rows);
+  return check_launch("colstats_reduce");
+}
+
 }  // namespace tnf
 
 using namespace tnf;
@@ -722,8 +727,7 @@ static int colstats_launch(const void* a, const void* b, int64_t rows, int D, do
   });
   int rc = check_launch(what);
   if (rc) return rc;
-  colstats_reduce_kernel<<<(2 * D + 1 + 7) / 8, 256, 0, st>>>((const double*)workspace, grid, D, sums, (double)rows);
-  return check_launch(what);
+  return colstats_reduce_launch((const double*)workspace, grid, D, sums, (double)rows, st);
 }
 
 int tnf_colstats(const void* z, int64_t rows, int D, double* sums, void* workspace, int dtype, tnf_stream_t stream) {

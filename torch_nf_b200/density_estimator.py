@@ -253,27 +253,35 @@ class NormFlow(DensityEstimator):
         scal = torch.zeros(Mp, dtype=torch.float32, device=z.device)
         fold = self._can_fold(pd, z)
         pend = None     # per-column map (scale, shift) owed to z; consumed by the next coupling kernel
-        for (b, idx, n) in self._slices():
+        stats = None    # column statistics of z produced by the previous coupling kernel itself
+        slices = self._slices()
+        for i, (b, idx, n) in enumerate(slices):
             if b.name == "RealNVP":
                 if self._use_tc(b, pd, z):
-                    z, _ = ops.coupling_tc(z, self._packed(b, idx, n, pd), b.D, b.num_units, b.num_layers,
-                                           b.transform_upper, TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD,
-                                           pre_scale=pend[0] if pend else None, pre_shift=pend[1] if pend else None)
+                    nxt = slices[i + 1][0].name if i + 1 < len(slices) else None
+                    fuse_stats = (nxt == "BatchNorm" and not freeze_bn and D == 64)
+                    res = ops.coupling_tc(z, self._packed(b, idx, n, pd), b.D, b.num_units, b.num_layers,
+                                          b.transform_upper, TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD,
+                                          pre_scale=pend[0] if pend else None, pre_shift=pend[1] if pend else None,
+                                          want_stats=fuse_stats)
+                    z, stats = res[0], (res[2] if fuse_stats else None)
                     pend = None
                 else:
                     z, _ = ops.coupling(z, pd[:, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper,
                                         TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD)
+                    stats = None
             elif b.name == "BatchNorm":
                 if pend is not None:       # statistics are taken on the materialised tensor
-                    z, pend = ops.colaffine(z, pend, D), None
+                    z, pend, stats = ops.colaffine(z, pend, D), None, None
                 if freeze_bn:
                     mean, alpha = b._state_on(z.device, z.dtype)
                     ld = b._last_ld.to(device=z.device, dtype=z.dtype)
                 else:
                     from .bijectors import _reduce_stats
-                    sums = _reduce_stats(ops.colstats(z, D))
+                    sums = _reduce_stats(stats if stats is not None else ops.colstats(z, D))
                     mean, alpha, ld = ops.bn_finalize(sums, D, b.eps, z.dtype)
                     b._set_state(mean, alpha, ld, home)
+                stats = None
                 if fold:
                     pend = ops.fold_colaffine(pend, ops.FOLD_BN_FWD, mean, alpha, D)
                 else:

@@ -188,7 +188,9 @@ def tc_pack(params_row, D, U, L, upper):
 
 
 def coupling_tc(z, packed, D, U, L, upper, direction, ld=None, accum=TNF_LD_WRITE, pre_scale=None, pre_shift=None,
-                col_stats=None, out=None):
+                want_stats=False, out=None):
+    """Returns (z_out, log_det) or, with ``want_stats`` (D = 64), (z_out, log_det, sums) where ``sums`` is the
+    float64 [sum | sumsq | rows] buffer of the OUTPUT columns (the next BatchNorm's statistics)."""
     z2 = z.reshape(-1, D)
     if z2.dtype != torch.float32 or not z2.is_contiguous():
         raise TypeError("tensor-core coupling takes contiguous float32 z")
@@ -197,17 +199,23 @@ def coupling_tc(z, packed, D, U, L, upper, direction, ld=None, accum=TNF_LD_WRIT
     if ld is None:
         ld = torch.empty(rows, dtype=torch.float32, device=z.device)
         accum = TNF_LD_WRITE
+    sums = ws = None
+    if want_stats:
+        sums = torch.empty(2 * D + 1, dtype=torch.float64, device=z.device)
+        ws = _workspace(D, z.device)
     timer = kernel_timer
     if timer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     rc = _lib.lib().tnf_coupling_tc(z2.data_ptr(), z_out.data_ptr(), ld.data_ptr(), packed.data_ptr(), rows, D, U, L,
-                                    int(upper), direction, accum, _ptr(pre_scale), _ptr(pre_shift), _ptr(col_stats),
-                                    _stream())
+                                    int(upper), direction, accum, _ptr(pre_scale), _ptr(pre_shift), _ptr(sums),
+                                    _ptr(ws), _stream())
     if timer is not None:
         e1.record()
         timer.append((e0, e1))
     _lib.check(rc, "tnf_coupling_tc")
+    if want_stats:
+        return z_out.view(z.shape), ld, sums
     return z_out.view(z.shape), ld
 
 
