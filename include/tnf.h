@@ -109,6 +109,9 @@ int tnf_tc_supported(int D, int U, int L);
 void tnf_tc_set_debug(void* dev_buffer);
 /* diagnostic: 1 = only one epilogue group works (no tile ping-pong), 2 = default. */
 void tnf_tc_set_groups(int n_groups);
+/* diagnostic: kernel choice of tnf_coupling_tc: 0 = automatic (K-chunk pipelined kernel for D <= 128,
+ * tile ping-pong kernel otherwise), 1 = always the tile ping-pong kernel, 2 = same as 0. */
+void tnf_tc_set_variant(int variant);
 int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N, int a_in_tmem,
                          tnf_stream_t stream);
 size_t tnf_tc_packed_bytes(int D, int U, int L);

@@ -12,7 +12,12 @@ params = torch.tensor(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=0))
 packed = ops.tc_pack(params[0], D, U, L, True)
 z = torch.randn(1, N, D, device="cuda")
 if len(sys.argv) > 1 and sys.argv[1] == "solo":
+    _lib.lib().tnf_tc_set_variant(1)
     _lib.lib().tnf_tc_set_groups(1)
+elif len(sys.argv) > 1 and sys.argv[1] == "pingpong":
+    _lib.lib().tnf_tc_set_variant(1)
+elif len(sys.argv) > 1 and sys.argv[1].startswith("x"):
+    _lib.lib().tnf_tc_set_groups(int(sys.argv[1][1:]))
 for _ in range(3):
     ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -21,15 +26,16 @@ for _ in range(5):
     ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)
 e1.record(); torch.cuda.synchronize()
 print("ms per launch: %.4f" % (e0.elapsed_time(e1) / 5))
-dbg = torch.zeros(2048, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(2048 * 4, dtype=torch.int64, device="cuda")
 _lib.lib().tnf_tc_set_debug(dbg.data_ptr())
 ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)
 torch.cuda.synchronize()
 _lib.lib().tnf_tc_set_debug(None)
 raw = dbg.cpu().numpy()
 print("MMA warp (CTA 0): cycles waiting on epilogue %d, on weights %d, total %d" % (raw[2040], raw[2041], raw[2042]))
-d = raw.reshape(2, 512, 2)  # group g at int64 offset 1024*g
-names = {100: "tile start", 101: "A1 published", 600: "tile end", 601: "y computed", 602: "next A1 published"}
+d = raw[:2048].reshape(2, 512, 2)  # group g at int64 offset 1024*g
+names = {100: "tile start", 101: "A1 published", 600: "tile end", 601: "y computed", 602: "next A1 published", 610: "A1 image written", 611: "A1 proxy fence done",
+         700: "step: chunk landed", 701: "step: tanh+stores issued", 702: "step: chunk published", 703: "step: begin"}
 for g in range(2):
     ev = [(int(t), int(c)) for t, c in d[g] if t != 0]
     if not ev:
@@ -37,7 +43,24 @@ for g in range(2):
     t0 = ev[0][1]
     print("group", g, "events", len(ev))
     prev = t0
-    for i, (t, c) in enumerate(ev[40:72]):
+    def label(t):
+        return names.get(t) or ("wait H net%d l%d" % ((t - 200) // 10, (t - 200) % 10) if 200 <= t < 300 else
+                                "got  H net%d l%d" % ((t - 300) // 10, (t - 300) % 10) if 300 <= t < 400 else
+                                "wait F net%d" % (t - 400) if 400 <= t < 500 else "got  F net%d" % (t - 500))
+    # mean duration of every phase over the steady tiles
+    from collections import OrderedDict
+    acc = OrderedDict()
+    first = [i for i, (t, c) in enumerate(ev) if t == 100]
+    if len(first) > 4:
+        for i in range(first[2], first[-1]):
+            key = (ev[i][0], ev[i + 1][0])
+            acc.setdefault(key, []).append(ev[i + 1][1] - ev[i][1])
+        print("  mean cycles per phase (steady tiles):")
+        for (a_, b_), v in acc.items():
+            print("    %-22s -> %-22s %7.0f  (n=%d)" % (label(a_), label(b_), np.mean(v), len(v)))
+    if "-v" not in sys.argv:
+        ev = []
+    for i, (t, c) in enumerate(ev[60:100]):
         nm = names.get(t) or ("wait H net%d l%d" % ((t - 200) // 10, (t - 200) % 10) if 200 <= t < 300 else
                               "got  H net%d l%d" % ((t - 300) // 10, (t - 300) % 10) if 300 <= t < 400 else
                               "wait F net%d" % (t - 400) if 400 <= t < 500 else "got  F net%d" % (t - 500))

@@ -30,6 +30,7 @@ PROTOTYPES = {
     "tnf_tc_supported": (I, [I, I, I]),
     "tnf_tc_set_debug": (None, [P]),
     "tnf_tc_set_groups": (None, [I]),
+    "tnf_tc_set_variant": (None, [I]),
     "tnf_tc_selftest_gemm": (I, [P, P, P, I, I, I, P]),
     "tnf_tc_packed_bytes": (Z, [I, I, I]),
     "tnf_tc_pack": (I, [P, P, I, I, I, I, P]),

@@ -154,6 +154,29 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, descriptors passed as (low, high) 32-bit words: only the low word (start address, LBO) changes per step
+__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}" ::"r"(bar_addr), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_addr(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
 // D[tmem] (+)= A[tmem] . B[smem desc]  (kept for the TMEM-A diagnostic)
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
@@ -346,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
-  const int G = a.n_groups;   // epilogue groups in use (2; 1 = diagnostic solo mode)
+  const int G = (a.n_groups & 3) == 1 ? 1 : 2;   // epilogue groups in use (2; 1 = diagnostic solo mode)
   const int64_t iters = (n_tiles + G * (int64_t)gridDim.x - 1) / (G * (int64_t)gridDim.x);
   const int64_t weight_bytes = 2 * sh.net_weight_elems() * 2;
 
@@ -499,31 +522,38 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
   } while (0)
 
     // Software-pipelined epilogue step.  `cur` holds chunk c's pre-activations (accumulator + bias), `acc` the raw
-    // accumulator of the NEXT chunk.  In source order, per group of 8 columns: 8 MUFU.TANH of chunk c, 8 bias adds
-    // preparing the next chunk, pack + st.shared of the previous group - so the MUFU pipe (8 cycles per warp
-    // instruction) never waits for the FMA-pipe / LSU work of a single in-order warp.
-    auto epi_step = [&](float (&cur)[32], float (&nxt)[32], const uint32_t (&acc)[32], const float* bias_next, int c) {
+    // accumulator of chunk c+1 (landed).  First half of the step: 16 MUFU.TANH of chunk c interleaved with all 32
+    // bias adds that turn `acc` into `nxt`; then the tcgen05.ld of chunk c+2 is issued into the now-free `acc`
+    // (the __syncwarp pins it there: it may not sink below the later st.shared) so that its latency hides under
+    // the second half's 16 MUFU.TANH; pack + st.shared of each group trail its tanh by one group.
+    auto epi_step = [&](float (&cur)[32], float (&nxt)[32], uint32_t (&acc)[32], const float* bias_next, int c,
+                        uint32_t next_ld_col) {
       const float4* b4 = reinterpret_cast<const float4*>(bias_next);
       unsigned char* dst = myAct + img_off(r_tile, c * kChunk, kTileM);
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) cur[j + e] = tanh_fast(cur[j + e]);
-        const float4 b0 = b4[j / 4], b1 = b4[j / 4 + 1];
-        nxt[j] = __uint_as_float(acc[j]) + b0.x;         nxt[j + 1] = __uint_as_float(acc[j + 1]) + b0.y;
-        nxt[j + 2] = __uint_as_float(acc[j + 2]) + b0.z; nxt[j + 3] = __uint_as_float(acc[j + 3]) + b0.w;
-        nxt[j + 4] = __uint_as_float(acc[j + 4]) + b1.x; nxt[j + 5] = __uint_as_float(acc[j + 5]) + b1.y;
-        nxt[j + 6] = __uint_as_float(acc[j + 6]) + b1.z; nxt[j + 7] = __uint_as_float(acc[j + 7]) + b1.w;
+        if (j < 16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = b4[j / 2 + q];
+            const int o = 2 * j + 4 * q;
+            nxt[o] = __uint_as_float(acc[o]) + b.x;         nxt[o + 1] = __uint_as_float(acc[o + 1]) + b.y;
+            nxt[o + 2] = __uint_as_float(acc[o + 2]) + b.z; nxt[o + 3] = __uint_as_float(acc[o + 3]) + b.w;
+          }
+        }
         if (j > 0) {
           const int k = j - 8;
           *reinterpret_cast<uint4*>(dst + (k >> 3) * (kTileM * 16)) =
               make_uint4(pack_bf16(cur[k], cur[k + 1]), pack_bf16(cur[k + 2], cur[k + 3]),
                          pack_bf16(cur[k + 4], cur[k + 5]), pack_bf16(cur[k + 6], cur[k + 7]));
         }
+        if (j == 8) {
+          tmem_ld32(next_ld_col, acc);
+          __syncwarp();
+        }
       }
-    };
-    auto epi_flush = [&](const float (&cur)[32], int c) {   // pack + store the last group of chunk c
-      unsigned char* dst = myAct + img_off(r_tile, c * kChunk, kTileM);
       *reinterpret_cast<uint4*>(dst + 3 * (kTileM * 16)) =
           make_uint4(pack_bf16(cur[24], cur[25]), pack_bf16(cur[26], cur[27]), pack_bf16(cur[28], cur[29]),
                      pack_bf16(cur[30], cur[31]));
@@ -633,19 +663,15 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
           tmem_ld32(hcol + (uint32_t)kChunk, acc);
 #pragma unroll 1
           for (int c = 0; c < n_chunks; c += 2) {
-            // chunk c (xa) while chunk c+1 is prepared into xb
-            tc_wait_ld();
-            epi_step(xa, xb, acc, bl + (c + 1) * kChunk, c);
-            // the last iteration re-reads its own last chunk (harmless) so that the loop stays branch-free
+            // chunk c (xa) while chunk c+1 is prepared into xb and chunk c+2 is fetched
+            // (the last iteration re-reads its own last chunk - harmless - so that the loop stays branch-free)
             const int c2 = (c + 2 < n_chunks) ? c + 2 : c + 1;
-            tmem_ld32(hcol + (uint32_t)(c2 * kChunk), acc);
-            epi_flush(xa, c);
-            // chunk c+1 (xb) while chunk c+2 is prepared into xa
-            tc_wait_ld();
-            epi_step(xb, xa, acc, bl + c2 * kChunk, c + 1);
             const int c3 = (c + 3 < n_chunks) ? c + 3 : c + 1;
-            tmem_ld32(hcol + (uint32_t)(c3 * kChunk), acc);
-            epi_flush(xb, c + 1);
+            tc_wait_ld();
+            epi_step(xa, xb, acc, bl + (c + 1) * kChunk, c, hcol + (uint32_t)(c2 * kChunk));
+            // chunk c+1 (xb) while chunk c+2 is prepared into xa and chunk c+3 is fetched
+            tc_wait_ld();
+            epi_step(xb, xa, acc, bl + c2 * kChunk, c + 1, hcol + (uint32_t)(c3 * kChunk));
           }
           tc_wait_ld();
           fence_async_smem();
@@ -804,6 +830,506 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
   if (warp == kEpiWarps) tmem_dealloc(tmem, 512);
 }
 
+// ================================================================ K-chunk pipelined kernel (D <= 128)
+// One tile in flight per CTA, all 8 epilogue warps on it (warp w: TMEM lane quadrant w%4, accumulator chunks
+// c = w/4 (mod 2)).  The 512 TMEM columns hold TWO 256-column accumulators, so the MMA warp can run layer l+1
+// into one while the epilogue still drains layer l from the other: it issues the two K=16 MMAs of K-chunk c as
+// soon as the 4 warps owning chunk c have published those 32 activation columns (act_ready[c]) - the tensor
+// pipe trails the MUFU-bound tanh epilogue by one chunk instead of waiting for the whole layer.  Global I/O is
+// done by two dedicated warps with coalesced 16-byte accesses: they load the next tile, apply the folded
+// per-column affine, write the conditioning half as the bf16 A1 image (double buffered) and straight through to
+// z_out, and stage the transformed half in shared memory (ZT, padded rows); the epilogue warps transform it in
+// place and the same two warps store it (and accumulate the fused column statistics).
+constexpr int kThreads2 = (kEpiWarps + 4) * 32;
+constexpr int kMaxJobs = 6;   // L + 1 <= 6
+
+struct __align__(16) Ctrl2 {
+  uint64_t w_full[kMaxStages];
+  uint64_t w_empty[kMaxStages];
+  uint64_t a1_ready[2];     // 2 I/O warps: A1 image + ZT staging of a tile written
+  uint64_t a1_free[2];      // tcgen05.commit: both layer-0 jobs of the tile have read the A1 image
+  uint64_t y_ready[2];      // 8 epilogue warps: transformed half written back into the ZT staging
+  uint64_t act_ready[8];    // 4 epilogue warps: activation chunk c (32 K-columns, all 128 rows) written
+  uint64_t h_ready[2][kMaxJobs];   // tcgen05.commit per (net, layer): accumulator complete
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+// dynamic shared memory:
+//   [ring: n_stages x 16 KB][A1 x2][Act][ZT x2][Ctrl2][bias 2 x nb][pre_scale D][pre_shift D][ld partial 128]
+__host__ __device__ inline size_t zt_bytes(const Shape& sh) { return (size_t)kTileM * (sh.d_out + 4) * sizeof(float); }
+__host__ __device__ inline size_t smem_bytes2(const Shape& sh, int n_stages) {
+  return (size_t)n_stages * sh.stage_elems() * 2 + 2 * sh.a1_bytes() + sh.act_bytes() + 2 * zt_bytes(sh) + sizeof(Ctrl2) +
+         (size_t)(2 * sh.net_bias_elems() + 2 * sh.D + kTileM) * sizeof(float);
+}
+__host__ __device__ inline bool shape_supported2(int D, int U, int L) {
+  return shape_supported(D, U, L) && D <= 128;
+}
+
+// One GEMM job of the MMA warp, fully unrolled over its 32-wide K chunks: per chunk at most two mbarrier waits
+// (activation chunk published / weight stage landed), two K=16 MMAs whose descriptor low words differ from the
+// job's base by compile-time constants, and a commit when the weight stage is used up.  The loop is run by the
+// whole warp (uniform control flow), the elected lane issues.
+template <int K, int N, bool kWaitAct>
+__device__ __forceinline__ void mma_job(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo_ring, uint32_t b_hi,
+                                        uint32_t act_bar0, uint32_t e_par, uint32_t wfull0, uint32_t wempty0,
+                                        uint32_t S, uint32_t& slot, uint32_t& phase, bool leader) {
+  constexpr int KS = (kStageElems / N) < K ? (kStageElems / N) : K;   // K rows per weight stage
+  constexpr int CPS = KS / kChunk;                                     // chunks per stage
+  constexpr uint32_t kStage16 = kStageBytes >> 4;
+  const uint32_t idesc = make_idesc(N);
+#pragma unroll
+  for (int c = 0; c < K / kChunk; ++c) {
+    if (kWaitAct) mbar_wait_addr(act_bar0 + 8u * c, e_par);
+    if (c % CPS == 0) mbar_wait_addr(wfull0 + slot * 8u, phase);
+    tc_fence_after();
+    if (leader) {
+      const uint32_t b_lo = b_lo_ring + slot * kStage16 + (uint32_t)((c % CPS) * 4 * N);
+      umma_ss2(d_tmem, a_lo + 512u * c, a_hi, b_lo, b_hi, idesc, c > 0 ? 1u : 0u);
+      umma_ss2(d_tmem, a_lo + 512u * c + 256u, a_hi, b_lo + 2u * N, b_hi, idesc, 1u);
+      if (c % CPS == CPS - 1) tc_commit_addr(wempty0 + slot * 8u);
+    }
+    if (c % CPS == CPS - 1) {
+      if (++slot == S) { slot = 0; phase ^= 1; }
+    }
+  }
+}
+
+template <bool kInverse, int DH, int U_>   // DH = D/2 = d_in = d_out in {32, 64}; U_ = hidden units
+__global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const Shape sh(a.D, a.U, a.L, a.upper);
+  const int S = a.n_stages;
+  unsigned char* ring = smem_raw;
+  const uint32_t stage_bytes = (uint32_t)sh.stage_elems() * 2;
+  unsigned char* sA1 = ring + (size_t)S * stage_bytes;             // 2 images (tile parity)
+  unsigned char* sAct = sA1 + 2 * sh.a1_bytes();                    // 1 image
+  float* sZT = reinterpret_cast<float*>(sAct + sh.act_bytes());     // 2 x [128][DH+4] fp32 (tile parity)
+  constexpr int kZS = DH + 4;                                       // padded row stride (floats)
+  Ctrl2& ct = *reinterpret_cast<Ctrl2*>(reinterpret_cast<unsigned char*>(sZT) + 2 * zt_bytes(sh));
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl2));
+  const int nb = sh.net_bias_elems();
+  float* s_pscale = s_bias + 2 * nb;
+  float* s_pshift = s_pscale + sh.D;
+  float* s_ldp = s_pshift + sh.D;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
+  const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles blockIdx.x + i*grid
+  const int64_t weight_bytes = 2 * sh.net_weight_elems() * 2;
+  constexpr int n_chunks = U_ / kChunk;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&ct.w_full[i], 1); mbar_init(&ct.w_empty[i], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ct.a1_ready[b], 2);
+      mbar_init(&ct.a1_free[b], 1);
+      mbar_init(&ct.y_ready[b], kEpiWarps);
+    }
+    for (int c = 0; c < 8; ++c) mbar_init(&ct.act_ready[c], 4);
+    for (int n = 0; n < 2; ++n)
+      for (int l = 0; l < kMaxJobs; ++l) mbar_init(&ct.h_ready[n][l], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kEpiWarps) tmem_alloc(&ct.tmem_base, 512);
+  {
+    const float* gb = reinterpret_cast<const float*>(a.packed + weight_bytes);
+    for (int i = threadIdx.x; i < 2 * nb; i += blockDim.x) s_bias[i] = gb[i];
+    for (int i = threadIdx.x; i < sh.D; i += blockDim.x) {
+      s_pscale[i] = a.pre_scale ? a.pre_scale[i] : 1.0f;
+      s_pshift[i] = a.pre_shift ? a.pre_shift[i] : 0.0f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ct.tmem_base;
+
+  if (warp == kEpiWarps + 1) {
+    // =============================== weight producer (one elected lane) ===============================
+    if (elect_one()) {
+      uint32_t slot = 0, phase = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        for (int net = 0; net < 2; ++net) {
+          size_t off = 0;
+          for (int l = 0; l <= sh.L; ++l) {
+            const int K = sh.K_of(l), J = sh.J_of(l), N = sh.N_of(l);
+            const int ks = sh.stage_k(K, N);
+            const uint32_t bytes = (uint32_t)(ks * N * 2);
+            const unsigned char* nsrc = a.packed + off + (size_t)net * K * J * 2;
+            for (int st = 0; st < K / ks; ++st) {
+              mbar_wait(&ct.w_empty[slot], phase ^ 1);
+              mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
+              bulk_g2s(ring + (size_t)slot * stage_bytes, nsrc + (size_t)st * bytes, bytes, &ct.w_full[slot]);
+              if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+            }
+            off += (size_t)2 * K * J * 2;
+          }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps) {
+    // =============================== MMA issuer (warp-uniform, elected lane issues) ===============================
+    const bool leader = elect_one();
+    uint32_t slot = 0, phase = 0, e_par = 0;
+    int cur = 0;   // accumulator buffer of the most recent hidden-layer job
+    const long long t_all = a.dbg != nullptr ? clock64() : 0;
+    const uint32_t a1_sz16 = (uint32_t)sh.a1_bytes() >> 4;
+    const uint32_t act_bar0 = smem_u32(&ct.act_ready[0]);
+    const uint32_t wfull0 = smem_u32(&ct.w_full[0]), wempty0 = smem_u32(&ct.w_empty[0]);
+    const uint32_t ring16 = smem_u32(ring) >> 4;
+    const uint64_t a1_desc = make_desc(smem_u32(sA1), kTileM), act_desc = make_desc(smem_u32(sAct), kTileM);
+    const uint32_t a_hi = (uint32_t)(a1_desc >> 32);
+    const uint64_t bU_desc = make_desc(0u, U_), bF_desc = make_desc(0u, DH);
+    const uint32_t bU_lo = (uint32_t)bU_desc + ring16, bU_hi = (uint32_t)(bU_desc >> 32);
+    const uint32_t bF_lo = (uint32_t)bF_desc + ring16, bF_hi = (uint32_t)(bF_desc >> 32);
+    const uint32_t act_lo = (uint32_t)act_desc;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint32_t ab = (uint32_t)(it & 1);
+      const uint32_t a1_lo = (uint32_t)a1_desc + ab * a1_sz16;
+      mbar_wait(&ct.a1_ready[ab], (uint32_t)((it >> 1) & 1));
+#pragma unroll 1
+      for (int net = 0; net < 2; ++net) {
+        // layer 0: A1 image, accumulator = the buffer the previous epilogue phase has just drained
+        mma_job<DH, U_, false>(tmem + (uint32_t)cur * 256u, a1_lo, a_hi, bU_lo, bU_hi, act_bar0, e_par, wfull0, wempty0,
+                               (uint32_t)S, slot, phase, leader);
+        if (leader) {
+          tc_commit(&ct.h_ready[net][0]);
+          if (net == 1) tc_commit(&ct.a1_free[ab]);
+        }
+        // hidden layers 1..L-1, each trailing the epilogue of the layer before it chunk by chunk
+#pragma unroll 1
+        for (int l = 1; l < sh.L; ++l) {
+          cur ^= 1;
+          mma_job<U_, U_, true>(tmem + (uint32_t)cur * 256u, act_lo, a_hi, bU_lo, bU_hi, act_bar0, e_par, wfull0, wempty0,
+                                (uint32_t)S, slot, phase, leader);
+          e_par ^= 1;
+          if (leader) tc_commit(&ct.h_ready[net][l]);
+        }
+        // final layer -> the other buffer's first DH columns
+        mma_job<U_, DH, true>(tmem + (uint32_t)(cur ^ 1) * 256u, act_lo, a_hi, bF_lo, bF_hi, act_bar0, e_par, wfull0, wempty0,
+                              (uint32_t)S, slot, phase, leader);
+        e_par ^= 1;
+        if (leader) tc_commit(&ct.h_ready[net][sh.L]);
+        __syncwarp();
+      }
+    }
+    if (a.dbg != nullptr && blockIdx.x == 0 && leader) {
+      a.dbg[2040] = 0; a.dbg[2041] = 0; a.dbg[2042] = clock64() - t_all;
+    }
+  } else if (warp < kEpiWarps) {
+    // =============================== epilogue warps ===============================
+    const int q = warp & 3, par = warp >> 2;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int r_tile = q * 32 + lane;
+    constexpr int W = DH / 2;                 // final-layer columns per thread
+    constexpr int n_own = n_chunks / 2;       // chunks par, par+2, ...
+    const int c_last = par + 2 * (n_own - 1);
+    const float kLog2e = 1.4426950408889634f;
+    int cur = 0;
+
+    int dbg_n = 0;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
+    long long* dbg = a.dbg;
+#define TNF_STAMP(tag)                                                                     \
+  do {                                                                                     \
+    if (dbg_on && dbg_n < 500) { dbg[2 * dbg_n] = (tag); dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; } \
+  } while (0)
+
+    // see the tile ping-pong kernel: chunk c from `cur` through MUFU.TANH -> bf16 -> A image, while the bias adds
+    // turn `acc` (raw chunk, landed) into `nxt` and the tcgen05.ld of a further chunk is issued mid-step
+    // publish activation chunk c: generic-proxy writes -> async proxy, then one arrival per warp
+    auto publish = [&](int c) {
+      if (!(a.n_groups & 32)) fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ct.act_ready[c]);
+    };
+    // The arrival (release) waits for the chunk's st.shared to be performed, so chunk c is published in the middle
+    // of the NEXT step (prev_c), when its stores have long completed, instead of right behind them.
+    auto epi_step = [&](float (&cur_x)[32], float (&nxt)[32], uint32_t (&acc)[32], const float* bias_next, int c,
+                        uint32_t next_ld_col, int prev_c) {
+      const float4* b4 = reinterpret_cast<const float4*>(bias_next);
+      unsigned char* dst = sAct + img_off(r_tile, c * kChunk, kTileM);
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cur_x[j + e] = tanh_fast(cur_x[j + e]);
+        if (j < 16) {
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const float4 b = b4[j / 2 + qq];
+            const int o = 2 * j + 4 * qq;
+            nxt[o] = __uint_as_float(acc[o]) + b.x;         nxt[o + 1] = __uint_as_float(acc[o + 1]) + b.y;
+            nxt[o + 2] = __uint_as_float(acc[o + 2]) + b.z; nxt[o + 3] = __uint_as_float(acc[o + 3]) + b.w;
+          }
+        }
+        if (j > 0 && !(a.n_groups & 8)) {
+          const int k = j - 8;
+          *reinterpret_cast<uint4*>(dst + (k >> 3) * (kTileM * 16)) =
+              make_uint4(pack_bf16(cur_x[k], cur_x[k + 1]), pack_bf16(cur_x[k + 2], cur_x[k + 3]),
+                         pack_bf16(cur_x[k + 4], cur_x[k + 5]), pack_bf16(cur_x[k + 6], cur_x[k + 7]));
+        }
+        if (j == 8) {
+          if (!(a.n_groups & 4)) tmem_ld32(next_ld_col, acc);
+          __syncwarp();
+        }
+      }
+      *reinterpret_cast<uint4*>(dst + 3 * (kTileM * 16)) =
+          make_uint4(pack_bf16(cur_x[24], cur_x[25]), pack_bf16(cur_x[26], cur_x[27]), pack_bf16(cur_x[28], cur_x[29]),
+                     pack_bf16(cur_x[30], cur_x[31]));
+      TNF_STAMP(701);
+      publish(c);
+      TNF_STAMP(702);
+    };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
+
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = it * (int64_t)gridDim.x + blockIdx.x;
+      const int64_t row = tile * kTileM + r_tile;
+      const bool valid = row < a.rows;
+      const uint32_t h_par = (uint32_t)(it & 1);
+      const int zb = (int)(it & 1);
+      TNF_STAMP(100);
+      float tv[W];
+      float ld_old = 0.f;
+#pragma unroll
+      for (int net = 0; net < 2; ++net) {
+        const float* bias = s_bias + net * nb;
+#pragma unroll 1
+        for (int l = 0; l < sh.L; ++l) {
+          const float* bl = bias + l * sh.U;
+          if (l > 0) cur ^= 1;
+          const uint32_t hcol = tmem + lane_addr + (uint32_t)cur * 256u;
+          TNF_STAMP(200 + net * 10 + l);
+          mbar_wait(&ct.h_ready[net][l], h_par);
+          tc_fence_after();
+          TNF_STAMP(300 + net * 10 + l);
+          uint32_t acc[32];
+          float xa[32], xb[32];
+          tmem_ld32(hcol + (uint32_t)(par * kChunk), acc);
+          tc_wait_ld();
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(bl + par * kChunk);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = b4[j / 4];
+              xa[j] = __uint_as_float(acc[j]) + b.x;         xa[j + 1] = __uint_as_float(acc[j + 1]) + b.y;
+              xa[j + 2] = __uint_as_float(acc[j + 2]) + b.z; xa[j + 3] = __uint_as_float(acc[j + 3]) + b.w;
+            }
+          }
+          {
+            const int c1 = par + 2 <= c_last ? par + 2 : c_last;
+            tmem_ld32(hcol + (uint32_t)(c1 * kChunk), acc);
+          }
+#pragma unroll 1
+          for (int i = 0; i < n_own; i += 2) {
+            // own chunks ca, cb = ca + 2, ... (clamped re-reads of the last own chunk keep the loop branch-free)
+            const int ca = par + 2 * i;
+            const int cb = ca + 2 <= c_last ? ca + 2 : c_last;
+            const int cc = ca + 4 <= c_last ? ca + 4 : c_last;
+            const int cd = ca + 6 <= c_last ? ca + 6 : c_last;
+            TNF_STAMP(703);
+            tc_wait_ld();
+            TNF_STAMP(700);
+            epi_step(xa, xb, acc, bl + cb * kChunk, ca, hcol + (uint32_t)(cc * kChunk), -1);
+            if (i + 1 < n_own) {
+              TNF_STAMP(703);
+              tc_wait_ld();
+              TNF_STAMP(700);
+              epi_step(xb, xa, acc, bl + cc * kChunk, cb, hcol + (uint32_t)(cd * kChunk), -1);
+            }
+          }
+          tc_wait_ld();
+        }
+        // ---- final layer of this net: W columns per thread
+        const float* bL = bias + sh.L * sh.U + par * W;
+        const uint32_t fcol = tmem + lane_addr + (uint32_t)(cur ^ 1) * 256u + (uint32_t)(par * W);
+        if (net == 0 && par == 0 && valid && a.accum != TNF_LD_WRITE) ld_old = a.log_det[row];
+        TNF_STAMP(400 + net);
+        mbar_wait(&ct.h_ready[net][sh.L], h_par);
+        tc_fence_after();
+        TNF_STAMP(500 + net);
+        if (net == 0) {
+#pragma unroll
+          for (int j0 = 0; j0 < W; j0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(fcol + (uint32_t)j0, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) tv[j0 + j] = __uint_as_float(o[j]) + bL[j0 + j];
+          }
+          tc_fence_before();
+          pair_sync();   // both column halves of t are read out before chunk 0 of the s-net lets MMAs overwrite them
+        } else {
+          mbar_wait(&ct.a1_ready[zb], (uint32_t)((it >> 1) & 1));   // ZT staging of this tile (long since written)
+          float* zrow = sZT + (size_t)zb * kTileM * kZS + (size_t)r_tile * kZS + par * W;
+          float ld_sum = 0.f;
+#pragma unroll
+          for (int j0 = 0; j0 < W; j0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(fcol + (uint32_t)j0, o);
+            float zin[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(zrow + j0 + j);
+              zin[j] = t4.x; zin[j + 1] = t4.y; zin[j + 2] = t4.z; zin[j + 3] = t4.w;
+            }
+            tc_wait_ld();
+            float y[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float sv = __uint_as_float(o[j]) + bL[j0 + j];
+              ld_sum += sv;
+              y[j] = kInverse ? (zin[j] - tv[j0 + j]) * exp2_fast(-sv * kLog2e)
+                              : fmaf(zin[j], exp2_fast(sv * kLog2e), tv[j0 + j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(zrow + j0 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ct.y_ready[zb]);
+          TNF_STAMP(601);
+          if (par == 1) s_ldp[r_tile] = ld_sum;
+          pair_sync();   // also: both halves of s are read out before the next tile's MMAs may overwrite them
+          if (par == 0 && valid) {
+            const float tot = ld_sum + s_ldp[r_tile];
+            float* o = a.log_det + row;
+            if (a.accum == TNF_LD_WRITE) *o = tot;
+            else if (a.accum == TNF_LD_ADD) *o = ld_old + tot;
+            else *o = ld_old - tot;
+          }
+        }
+      }
+      TNF_STAMP(600);
+    }
+#undef TNF_STAMP
+  } else {
+    // =============================== I/O warps: coalesced loads / stores, A1 image, column statistics ===============================
+    const int w2 = warp - (kEpiWarps + 2);
+    const int row0 = w2 * (kTileM / 2);
+    constexpr int LPR = DH / 2;          // lanes per input row (16 B each)
+    constexpr int RPI = 32 / LPR;        // input rows per warp instruction
+    constexpr int NI = (kTileM / 2) / RPI;
+    constexpr int LPT = DH / 4;          // lanes per transformed-half row
+    constexpr int RPT = 32 / LPT;
+    constexpr int NT = (kTileM / 2) / RPT;
+    const int col = 4 * (lane % LPR);
+    const bool is_c = (col >= DH) == (sh.c_off != 0);
+    const int hc = col - (is_c ? sh.c_off : sh.t_off);   // column inside its half
+    const int rsub = lane / LPR;
+    const int tcol = 4 * (lane % LPT), trsub = lane / LPT;
+    const float4 ps = *reinterpret_cast<const float4*>(s_pscale + col);
+    const float4 pb = *reinterpret_cast<const float4*>(s_pshift + col);
+    const bool want_stats = a.stat_partials != nullptr;
+    float sv1[4] = {0.f, 0.f, 0.f, 0.f}, sv2[4] = {0.f, 0.f, 0.f, 0.f};   // pass-through columns col..col+3
+    float sy1[4] = {0.f, 0.f, 0.f, 0.f}, sy2[4] = {0.f, 0.f, 0.f, 0.f};   // transformed columns t_off+tcol..+3
+
+    auto load_tile = [&](int64_t it) {
+      const int b = (int)(it & 1);
+      const int64_t tile = it * (int64_t)gridDim.x + blockIdx.x;
+      unsigned char* a1 = sA1 + (size_t)b * sh.a1_bytes();
+      float* zt = sZT + (size_t)b * kTileM * kZS;
+#pragma unroll 1
+      for (int n0 = 0; n0 < NI; n0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = row0 + (n0 + u) * RPI + rsub;
+          const int64_t grow = tile * kTileM + r;
+          v[u] = grow < a.rows ? __ldg(reinterpret_cast<const float4*>(a.z_in + grow * sh.D + col))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = row0 + (n0 + u) * RPI + rsub;
+          const int64_t grow = tile * kTileM + r;
+          float4 x;
+          x.x = fmaf(v[u].x, ps.x, pb.x); x.y = fmaf(v[u].y, ps.y, pb.y);
+          x.z = fmaf(v[u].z, ps.z, pb.z); x.w = fmaf(v[u].w, ps.w, pb.w);
+          if (is_c) {
+            *reinterpret_cast<uint2*>(a1 + img_off(r, hc, kTileM)) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+            if (grow < a.rows) {
+              *reinterpret_cast<float4*>(a.z_out + grow * sh.D + col) = x;
+              if (want_stats) {
+                sv1[0] += x.x; sv1[1] += x.y; sv1[2] += x.z; sv1[3] += x.w;
+                sv2[0] = fmaf(x.x, x.x, sv2[0]); sv2[1] = fmaf(x.y, x.y, sv2[1]);
+                sv2[2] = fmaf(x.z, x.z, sv2[2]); sv2[3] = fmaf(x.w, x.w, sv2[3]);
+              }
+            }
+          } else {
+            *reinterpret_cast<float4*>(zt + (size_t)r * kZS + hc) = x;
+          }
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ct.a1_ready[b]);
+    };
+    auto store_tile = [&](int64_t it) {
+      const int b = (int)(it & 1);
+      const int64_t tile = it * (int64_t)gridDim.x + blockIdx.x;
+      const float* zt = sZT + (size_t)b * kTileM * kZS;
+      mbar_wait(&ct.y_ready[b], (uint32_t)((it >> 1) & 1));
+#pragma unroll 4
+      for (int n = 0; n < NT; ++n) {
+        const int r = row0 + n * RPT + trsub;
+        const int64_t grow = tile * kTileM + r;
+        const float4 y = *reinterpret_cast<const float4*>(zt + (size_t)r * kZS + tcol);
+        if (grow < a.rows) {
+          *reinterpret_cast<float4*>(a.z_out + grow * sh.D + sh.t_off + tcol) = y;
+          if (want_stats) {
+            sy1[0] += y.x; sy1[1] += y.y; sy1[2] += y.z; sy1[3] += y.w;
+            sy2[0] = fmaf(y.x, y.x, sy2[0]); sy2[1] = fmaf(y.y, y.y, sy2[1]);
+            sy2[2] = fmaf(y.z, y.z, sy2[2]); sy2[3] = fmaf(y.w, y.w, sy2[3]);
+          }
+        }
+      }
+    };
+    if (my_tiles > 0) load_tile(0);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      if (it + 1 < my_tiles) {
+        const int64_t t1 = it + 1;
+        if (t1 >= 2) mbar_wait(&ct.a1_free[t1 & 1], (uint32_t)(((t1 >> 1) - 1) & 1));   // layer-0 jobs of tile t1-2 done
+        load_tile(t1);
+      }
+      store_tile(it);
+    }
+    if (want_stats) {   // one [2][D] block of doubles per I/O warp
+      double* out = a.stat_partials + ((size_t)blockIdx.x * 2 + w2) * 2 * sh.D;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+          sv1[e] += __shfl_xor_sync(0xffffffffu, sv1[e], o);
+          sv2[e] += __shfl_xor_sync(0xffffffffu, sv2[e], o);
+        }
+#pragma unroll
+        for (int o = LPT; o < 32; o <<= 1) {
+          sy1[e] += __shfl_xor_sync(0xffffffffu, sy1[e], o);
+          sy2[e] += __shfl_xor_sync(0xffffffffu, sy2[e], o);
+        }
+      }
+      if (lane < LPR && is_c) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { out[col + e] = (double)sv1[e]; out[sh.D + col + e] = (double)sv2[e]; }
+      }
+      if (lane < LPT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          out[sh.t_off + tcol + e] = (double)sy1[e];
+          out[sh.D + sh.t_off + tcol + e] = (double)sy2[e];
+        }
+      }
+    }
+  }
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) tmem_dealloc(tmem, 512);
+}
+
 // ---------------------------------------------------------------- diagnostic: one UMMA GEMM
 // out[128 x N] = bf16(A[128 x K]) . bf16(W[K x N]) through the same operand images, descriptors and
 // TMEM accumulator layout as the fused kernel.  a_in_tmem selects the A source (TMEM or SMEM image).
@@ -881,11 +1407,13 @@ using namespace tnf;
 
 static long long* g_tc_debug = nullptr;
 static int g_tc_groups = 2;
+static int g_tc_variant = 0;   // 0 automatic, 1 tile ping-pong kernel, 2 K-chunk pipelined kernel
 
 extern "C" {
 
 void tnf_tc_set_debug(void* dev_buffer) { g_tc_debug = (long long*)dev_buffer; }
-void tnf_tc_set_groups(int n_groups) { g_tc_groups = n_groups == 1 ? 1 : 2; }
+void tnf_tc_set_groups(int n_groups) { g_tc_groups = n_groups; }
+void tnf_tc_set_variant(int variant) { g_tc_variant = (variant == 1 || variant == 2) ? variant : 0; }
 
 int tnf_tc_supported(int D, int U, int L) { return tc::shape_supported(D, U, L) ? 1 : 0; }
 
@@ -914,31 +1442,58 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   TNF_REQUIRE(z_in && z_out && log_det && packed, TNF_ERR_ARG, "tnf_coupling_tc: null pointer");
   TNF_REQUIRE((((uintptr_t)z_in | (uintptr_t)z_out | (uintptr_t)packed) & 15) == 0, TNF_ERR_ALIGN,
               "tnf_coupling_tc: z and packed weights must be 16-byte aligned");
-  TNF_REQUIRE(col_stats == nullptr || (D == 64 && stats_workspace != nullptr), TNF_ERR_UNSUPPORTED,
-              "tnf_coupling_tc: fused column statistics need D = 64 and a workspace");
+  TNF_REQUIRE(col_stats == nullptr || (D <= 128 && stats_workspace != nullptr), TNF_ERR_UNSUPPORTED,
+              "tnf_coupling_tc: fused column statistics need D <= 128 and a workspace");
+  TNF_REQUIRE(col_stats == nullptr || D == 64 || g_tc_variant != 1, TNF_ERR_UNSUPPORTED,
+              "tnf_coupling_tc: the tile ping-pong kernel accumulates column statistics only at D = 64");
   tc::Shape sh(D, U, L, transform_upper != 0);
-  // as many 16 KB weight stages as fit next to the activation images (227 KB per CTA)
-  int n_stages = tc::kMaxStages;
-  while (n_stages > 2 && tc::smem_bytes(sh, n_stages) > 227 * 1024) --n_stages;
-  const size_t smem = tc::smem_bytes(sh, n_stages);
-  TNF_REQUIRE(smem <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem);
-  tc::Args a{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
-             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_groups,
-             col_stats ? (double*)stats_workspace : nullptr, g_tc_debug};
   const int64_t n_tiles = (rows + tc::kTileM - 1) / tc::kTileM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-#define TNF_TC_LAUNCH(INV, DHV)                                                                               \
-  do {                                                                                                        \
-    e = cudaFuncSetAttribute(tc::coupling_tc_kernel<INV, DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                             (int)smem);                                                                      \
-    if (e == cudaSuccess) tc::coupling_tc_kernel<INV, DHV><<<grid, tc::kThreads, smem, st>>>(a);              \
-  } while (0)
   const bool inv = direction == TNF_INVERSE;
-  if (D == 64) { if (inv) TNF_TC_LAUNCH(true, 32); else TNF_TC_LAUNCH(false, 32); }
-  else if (D == 128) { if (inv) TNF_TC_LAUNCH(true, 64); else TNF_TC_LAUNCH(false, 64); }
-  else { if (inv) TNF_TC_LAUNCH(true, 128); else TNF_TC_LAUNCH(false, 128); }
+  const bool pipelined = tc::shape_supported2(D, U, L) && g_tc_variant != 1;
+  // as many 16 KB weight stages as fit next to the activation images (227 KB per CTA)
+  int n_stages = tc::kMaxStages;
+  size_t smem;
+  if (pipelined) {
+    while (n_stages > 2 && tc::smem_bytes2(sh, n_stages) > 227 * 1024) --n_stages;
+    smem = tc::smem_bytes2(sh, n_stages);
+  } else {
+    while (n_stages > 2 && tc::smem_bytes(sh, n_stages) > 227 * 1024) --n_stages;
+    smem = tc::smem_bytes(sh, n_stages);
+  }
+  TNF_REQUIRE(smem <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem);
+  tc::Args a{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
+             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_groups,
+             col_stats ? (double*)stats_workspace : nullptr, g_tc_debug};
+#define TNF_TC_LAUNCH(KERNEL, THREADS, INV, DHV)                                                              \
+  do {                                                                                                        \
+    e = cudaFuncSetAttribute(tc::KERNEL<INV, DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e == cudaSuccess) tc::KERNEL<INV, DHV><<<grid, THREADS, smem, st>>>(a);                               \
+  } while (0)
+  int stat_blocks = grid * tc::kEpiWarps;
+  if (pipelined) {
+    stat_blocks = grid * 2;
+#define TNF_TC2_LAUNCH(INV, DHV, UV)                                                                          \
+  do {                                                                                                        \
+    e = cudaFuncSetAttribute(tc::coupling_tc2_kernel<INV, DHV, UV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)smem);                                                                      \
+    if (e == cudaSuccess) tc::coupling_tc2_kernel<INV, DHV, UV><<<grid, tc::kThreads2, smem, st>>>(a);        \
+  } while (0)
+#define TNF_TC2_U(INV, DHV)                                                                                   \
+  do {                                                                                                        \
+    if (U == 256) TNF_TC2_LAUNCH(INV, DHV, 256);                                                              \
+    else if (U == 128) TNF_TC2_LAUNCH(INV, DHV, 128);                                                         \
+    else TNF_TC2_LAUNCH(INV, DHV, 64);                                                                        \
+  } while (0)
+    if (D == 64) { if (inv) TNF_TC2_U(true, 32); else TNF_TC2_U(false, 32); }
+    else { if (inv) TNF_TC2_U(true, 64); else TNF_TC2_U(false, 64); }
+#undef TNF_TC2_U
+#undef TNF_TC2_LAUNCH
+  } else if (D == 64) { if (inv) TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, true, 32); else TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, false, 32); }
+  else if (D == 128) { if (inv) TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, true, 64); else TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, false, 64); }
+  else { if (inv) TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, true, 128); else TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, false, 128); }
 #undef TNF_TC_LAUNCH
   if (e != cudaSuccess) {
     set_error("tnf_coupling_tc: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e));
@@ -946,7 +1501,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   }
   int rc = check_launch("tnf_coupling_tc");
   if (rc || col_stats == nullptr) return rc;
-  return colstats_reduce_launch((const double*)stats_workspace, grid * tc::kEpiWarps, D, col_stats, (double)rows, st);
+  return colstats_reduce_launch((const double*)stats_workspace, stat_blocks, D, col_stats, (double)rows, st);
 }
 
 int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N, int a_in_tmem,
