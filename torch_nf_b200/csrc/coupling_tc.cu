@@ -71,7 +71,17 @@ struct Shape {
     return (int64_t)d_in * U + (int64_t)(L - 1) * U * U + (int64_t)U * d_out;
   }
   __host__ __device__ int net_bias_elems() const { return L * U + d_out; }
-  __host__ __device__ int64_t packed_bytes() const { return 2 * net_weight_elems() * 2 + 2 * (int64_t)net_bias_elems() * 4; }
+  // bias operand images (pipelined kernel): per (layer, net) one K=16 group of J columns, K-row 0 = bf16(b),
+  // K-row 1 = bf16(b - bf16(b)), rest 0; multiplied by a constant [1, 1, 0, ...] A image the MMA adds the bias
+  __host__ __device__ int64_t bias_img_bytes() const { return 2 * (int64_t)net_bias_elems() * 32; }
+  __host__ __device__ int64_t bias_img_off(int l, int net) const {
+    int64_t off = 2 * net_weight_elems() * 2 + 2 * (int64_t)net_bias_elems() * 4;
+    for (int i = 0; i < l; ++i) off += 2 * (int64_t)J_of(i) * 32;
+    return off + (int64_t)net * J_of(l) * 32;
+  }
+  __host__ __device__ int64_t packed_bytes() const {
+    return 2 * net_weight_elems() * 2 + 2 * (int64_t)net_bias_elems() * 4 + bias_img_bytes();
+  }
   __host__ __device__ size_t a1_bytes() const { return (size_t)kTileM * d_in * 2; }
   __host__ __device__ size_t act_bytes() const { return (size_t)kTileM * U * 2; }
 };
@@ -230,6 +240,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -252,7 +268,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // Packed buffer = the weight stream in consumption order:
 //   for layer l in 0..L: for net in {t, s}: for column half hb: for stage s:
 //     image of stage_k(K,N) x N bf16 (N = N_of(l); see img_off, rows = N)
-// followed by the fp32 biases [net][layer][unit].
+// followed by the fp32 biases [net][layer][unit] and the bias operand images (Shape::bias_img_off).
 __global__ void pack_kernel(const float* __restrict__ params, unsigned char* __restrict__ packed, Shape sh) {
   const int64_t per_net = sh.net_weight_elems();
   const int64_t total = 2 * per_net;
@@ -296,7 +312,13 @@ __global__ void pack_kernel(const float* __restrict__ params, unsigned char* __r
       src_off += 2 * (int64_t)sh.K_of(l) * sh.J_of(l) + 2 * sh.J_of(l);
     }
     const int K = sh.K_of(l), J = sh.J_of(l);
-    bias_dst[idx] = params[src_off + 2 * (int64_t)K * J + (net ? J : 0) + rem];
+    const float b = params[src_off + 2 * (int64_t)K * J + (net ? J : 0) + rem];
+    bias_dst[idx] = b;
+    unsigned char* img = packed + sh.bias_img_off(l, net);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+    for (int kk = 0; kk < 16; ++kk)
+      *reinterpret_cast<__nv_bfloat16*>(img + img_off(rem, kk, J)) = kk == 0 ? hi : (kk == 1 ? lo : __float2bfloat16_rn(0.f));
   }
 }
 
@@ -831,8 +853,9 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
 }
 
 // ================================================================ K-chunk pipelined kernel (D <= 128)
-// One tile in flight per CTA, all 8 epilogue warps on it (warp w: TMEM lane quadrant w%4, accumulator chunks
-// c = w/4 (mod 2)).  The 512 TMEM columns hold TWO 256-column accumulators, so the MMA warp can run layer l+1
+// One tile in flight per CTA, 16 epilogue warps on it (warp w: TMEM lane quadrant w%4, accumulator chunks
+// c = w/4 (mod 4); four warps per SM sub-partition, so the MUFU pipe stays fed while a warp packs, stores and
+// publishes).  The 512 TMEM columns hold TWO 256-column accumulators, so the MMA warp can run layer l+1
 // into one while the epilogue still drains layer l from the other: it issues the two K=16 MMAs of K-chunk c as
 // soon as the 4 warps owning chunk c have published those 32 activation columns (act_ready[c]) - the tensor
 // pipe trails the MUFU-bound tanh epilogue by one chunk instead of waiting for the whole layer.  Global I/O is
@@ -840,26 +863,28 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
 // per-column affine, write the conditioning half as the bf16 A1 image (double buffered) and straight through to
 // z_out, and stage the transformed half in shared memory (ZT, padded rows); the epilogue warps transform it in
 // place and the same two warps store it (and accumulate the fused column statistics).
-constexpr int kThreads2 = (kEpiWarps + 4) * 32;
+constexpr int kEpiWarps2 = 16;   // 4 per SM sub-partition: the other three hide one warp's non-MUFU work
+constexpr int kThreads2 = (kEpiWarps2 + 4) * 32;
 constexpr int kMaxJobs = 6;   // L + 1 <= 6
+constexpr int kOnesBytes = 2 * kTileM * 16;   // A image of one K=16 step: [1, 1, 0, ..., 0] in every row
 
 struct __align__(16) Ctrl2 {
   uint64_t w_full[kMaxStages];
   uint64_t w_empty[kMaxStages];
   uint64_t a1_ready[2];     // 2 I/O warps: A1 image + ZT staging of a tile written
   uint64_t a1_free[2];      // tcgen05.commit: both layer-0 jobs of the tile have read the A1 image
-  uint64_t y_ready[2];      // 8 epilogue warps: transformed half written back into the ZT staging
+  uint64_t y_ready[2];      // 16 epilogue warps: transformed half written back into the ZT staging
   uint64_t act_ready[8];    // 4 epilogue warps: activation chunk c (32 K-columns, all 128 rows) written
   uint64_t h_ready[2][kMaxJobs];   // tcgen05.commit per (net, layer): accumulator complete
   uint32_t tmem_base;
   uint32_t pad;
 };
 // dynamic shared memory:
-//   [ring: n_stages x 16 KB][A1 x2][Act][ZT x2][Ctrl2][bias 2 x nb][pre_scale D][pre_shift D][ld partial 128]
+//   [ring: n_stages x 16 KB][A1 x2][Act][ones 4 KB][ZT x2][Ctrl2][pre_scale D][pre_shift D][ld partial 3 x 128]
 __host__ __device__ inline size_t zt_bytes(const Shape& sh) { return (size_t)kTileM * (sh.d_out + 4) * sizeof(float); }
 __host__ __device__ inline size_t smem_bytes2(const Shape& sh, int n_stages) {
-  return (size_t)n_stages * sh.stage_elems() * 2 + 2 * sh.a1_bytes() + sh.act_bytes() + 2 * zt_bytes(sh) + sizeof(Ctrl2) +
-         (size_t)(2 * sh.net_bias_elems() + 2 * sh.D + kTileM) * sizeof(float);
+  return (size_t)n_stages * sh.stage_elems() * 2 + 2 * sh.a1_bytes() + sh.act_bytes() + kOnesBytes + 2 * zt_bytes(sh) +
+         sizeof(Ctrl2) + (size_t)(2 * sh.D + 3 * kTileM) * sizeof(float);
 }
 __host__ __device__ inline bool shape_supported2(int D, int U, int L) {
   return shape_supported(D, U, L) && D <= 128;
@@ -871,8 +896,8 @@ __host__ __device__ inline bool shape_supported2(int D, int U, int L) {
 // whole warp (uniform control flow), the elected lane issues.
 template <int K, int N, bool kWaitAct>
 __device__ __forceinline__ void mma_job(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo_ring, uint32_t b_hi,
-                                        uint32_t act_bar0, uint32_t e_par, uint32_t wfull0, uint32_t wempty0,
-                                        uint32_t S, uint32_t& slot, uint32_t& phase, bool leader) {
+                                        uint32_t ones_lo, uint32_t act_bar0, uint32_t e_par, uint32_t wfull0,
+                                        uint32_t wempty0, uint32_t S, uint32_t& slot, uint32_t& phase, bool leader) {
   constexpr int KS = (kStageElems / N) < K ? (kStageElems / N) : K;   // K rows per weight stage
   constexpr int CPS = KS / kChunk;                                     // chunks per stage
   constexpr uint32_t kStage16 = kStageBytes >> 4;
@@ -880,11 +905,22 @@ __device__ __forceinline__ void mma_job(uint32_t d_tmem, uint32_t a_lo, uint32_t
 #pragma unroll
   for (int c = 0; c < K / kChunk; ++c) {
     if (kWaitAct) mbar_wait_addr(act_bar0 + 8u * c, e_par);
+    if (c == 0) {
+      // accumulator := bias (ones image . bias image, a stage of its own).  Issued only after the first activation
+      // chunk is published: that also tells that the epilogue warps have drained whatever the accumulator held.
+      mbar_wait_addr(wfull0 + slot * 8u, phase);
+      tc_fence_after();
+      if (leader) {
+        umma_ss2(d_tmem, ones_lo, a_hi, b_lo_ring + slot * kStage16, b_hi, idesc, 0u);
+        tc_commit_addr(wempty0 + slot * 8u);
+      }
+      if (++slot == S) { slot = 0; phase ^= 1; }
+    }
     if (c % CPS == 0) mbar_wait_addr(wfull0 + slot * 8u, phase);
     tc_fence_after();
     if (leader) {
       const uint32_t b_lo = b_lo_ring + slot * kStage16 + (uint32_t)((c % CPS) * 4 * N);
-      umma_ss2(d_tmem, a_lo + 512u * c, a_hi, b_lo, b_hi, idesc, c > 0 ? 1u : 0u);
+      umma_ss2(d_tmem, a_lo + 512u * c, a_hi, b_lo, b_hi, idesc, 1u);
       umma_ss2(d_tmem, a_lo + 512u * c + 256u, a_hi, b_lo + 2u * N, b_hi, idesc, 1u);
       if (c % CPS == CPS - 1) tc_commit_addr(wempty0 + slot * 8u);
     }
@@ -903,19 +939,17 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
   const uint32_t stage_bytes = (uint32_t)sh.stage_elems() * 2;
   unsigned char* sA1 = ring + (size_t)S * stage_bytes;             // 2 images (tile parity)
   unsigned char* sAct = sA1 + 2 * sh.a1_bytes();                    // 1 image
-  float* sZT = reinterpret_cast<float*>(sAct + sh.act_bytes());     // 2 x [128][DH+4] fp32 (tile parity)
+  unsigned char* sOnes = sAct + sh.act_bytes();                     // constant A image for the bias MMA
+  float* sZT = reinterpret_cast<float*>(sOnes + kOnesBytes);        // 2 x [128][DH+4] fp32 (tile parity)
   constexpr int kZS = DH + 4;                                       // padded row stride (floats)
   Ctrl2& ct = *reinterpret_cast<Ctrl2*>(reinterpret_cast<unsigned char*>(sZT) + 2 * zt_bytes(sh));
-  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl2));
-  const int nb = sh.net_bias_elems();
-  float* s_pscale = s_bias + 2 * nb;
+  float* s_pscale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl2));
   float* s_pshift = s_pscale + sh.D;
   float* s_ldp = s_pshift + sh.D;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
   const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles blockIdx.x + i*grid
-  const int64_t weight_bytes = 2 * sh.net_weight_elems() * 2;
   constexpr int n_chunks = U_ / kChunk;
 
   if (threadIdx.x == 0) {
@@ -923,17 +957,18 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&ct.a1_ready[b], 2);
       mbar_init(&ct.a1_free[b], 1);
-      mbar_init(&ct.y_ready[b], kEpiWarps);
+      mbar_init(&ct.y_ready[b], kEpiWarps2);
     }
     for (int c = 0; c < 8; ++c) mbar_init(&ct.act_ready[c], 4);
     for (int n = 0; n < 2; ++n)
       for (int l = 0; l < kMaxJobs; ++l) mbar_init(&ct.h_ready[n][l], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kEpiWarps) tmem_alloc(&ct.tmem_base, 512);
+  if (warp == kEpiWarps2) tmem_alloc(&ct.tmem_base, 512);
   {
-    const float* gb = reinterpret_cast<const float*>(a.packed + weight_bytes);
-    for (int i = threadIdx.x; i < 2 * nb; i += blockDim.x) s_bias[i] = gb[i];
+    for (int i = threadIdx.x; i < kOnesBytes / 4; i += blockDim.x)   // row r: K columns 0 and 1 are 1.0 (bf16 0x3f80)
+      reinterpret_cast<uint32_t*>(sOnes)[i] = (i < kTileM * 4 && (i & 3) == 0) ? 0x3f803f80u : 0u;
+    fence_async_smem();
     for (int i = threadIdx.x; i < sh.D; i += blockDim.x) {
       s_pscale[i] = a.pre_scale ? a.pre_scale[i] : 1.0f;
       s_pshift[i] = a.pre_shift ? a.pre_shift[i] : 0.0f;
@@ -944,7 +979,7 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
   tc_fence_after();
   const uint32_t tmem = ct.tmem_base;
 
-  if (warp == kEpiWarps + 1) {
+  if (warp == kEpiWarps2 + 1) {
     // =============================== weight producer (one elected lane) ===============================
     if (elect_one()) {
       uint32_t slot = 0, phase = 0;
@@ -956,6 +991,12 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
             const int ks = sh.stage_k(K, N);
             const uint32_t bytes = (uint32_t)(ks * N * 2);
             const unsigned char* nsrc = a.packed + off + (size_t)net * K * J * 2;
+            {   // the job's bias operand image travels as a stage of its own, ahead of the weights
+              mbar_wait(&ct.w_empty[slot], phase ^ 1);
+              mbar_arrive_expect_tx(&ct.w_full[slot], (uint32_t)J * 32u);
+              bulk_g2s(ring + (size_t)slot * stage_bytes, a.packed + sh.bias_img_off(l, net), (uint32_t)J * 32u, &ct.w_full[slot]);
+              if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+            }
             for (int st = 0; st < K / ks; ++st) {
               mbar_wait(&ct.w_empty[slot], phase ^ 1);
               mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
@@ -967,7 +1008,7 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
         }
       }
     }
-  } else if (warp == kEpiWarps) {
+  } else if (warp == kEpiWarps2) {
     // =============================== MMA issuer (warp-uniform, elected lane issues) ===============================
     const bool leader = elect_one();
     uint32_t slot = 0, phase = 0, e_par = 0;
@@ -983,6 +1024,7 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
     const uint32_t bU_lo = (uint32_t)bU_desc + ring16, bU_hi = (uint32_t)(bU_desc >> 32);
     const uint32_t bF_lo = (uint32_t)bF_desc + ring16, bF_hi = (uint32_t)(bF_desc >> 32);
     const uint32_t act_lo = (uint32_t)act_desc;
+    const uint32_t ones_lo = (uint32_t)make_desc(smem_u32(sOnes), kTileM);
     for (int64_t it = 0; it < my_tiles; ++it) {
       const uint32_t ab = (uint32_t)(it & 1);
       const uint32_t a1_lo = (uint32_t)a1_desc + ab * a1_sz16;
@@ -990,7 +1032,7 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
 #pragma unroll 1
       for (int net = 0; net < 2; ++net) {
         // layer 0: A1 image, accumulator = the buffer the previous epilogue phase has just drained
-        mma_job<DH, U_, false>(tmem + (uint32_t)cur * 256u, a1_lo, a_hi, bU_lo, bU_hi, act_bar0, e_par, wfull0, wempty0,
+        mma_job<DH, U_, false>(tmem + (uint32_t)cur * 256u, a1_lo, a_hi, bU_lo, bU_hi, ones_lo, act_bar0, e_par, wfull0, wempty0,
                                (uint32_t)S, slot, phase, leader);
         if (leader) {
           tc_commit(&ct.h_ready[net][0]);
@@ -1000,13 +1042,13 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
 #pragma unroll 1
         for (int l = 1; l < sh.L; ++l) {
           cur ^= 1;
-          mma_job<U_, U_, true>(tmem + (uint32_t)cur * 256u, act_lo, a_hi, bU_lo, bU_hi, act_bar0, e_par, wfull0, wempty0,
+          mma_job<U_, U_, true>(tmem + (uint32_t)cur * 256u, act_lo, a_hi, bU_lo, bU_hi, ones_lo, act_bar0, e_par, wfull0, wempty0,
                                 (uint32_t)S, slot, phase, leader);
           e_par ^= 1;
           if (leader) tc_commit(&ct.h_ready[net][l]);
         }
         // final layer -> the other buffer's first DH columns
-        mma_job<U_, DH, true>(tmem + (uint32_t)(cur ^ 1) * 256u, act_lo, a_hi, bF_lo, bF_hi, act_bar0, e_par, wfull0, wempty0,
+        mma_job<U_, DH, true>(tmem + (uint32_t)(cur ^ 1) * 256u, act_lo, a_hi, bF_lo, bF_hi, ones_lo, act_bar0, e_par, wfull0, wempty0,
                               (uint32_t)S, slot, phase, leader);
         e_par ^= 1;
         if (leader) tc_commit(&ct.h_ready[net][sh.L]);
@@ -1016,14 +1058,12 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
     if (a.dbg != nullptr && blockIdx.x == 0 && leader) {
       a.dbg[2040] = 0; a.dbg[2041] = 0; a.dbg[2042] = clock64() - t_all;
     }
-  } else if (warp < kEpiWarps) {
+  } else if (warp < kEpiWarps2) {
     // =============================== epilogue warps ===============================
-    const int q = warp & 3, par = warp >> 2;
+    const int q = warp & 3, par = warp >> 2;  // par in 0..3
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int r_tile = q * 32 + lane;
-    constexpr int W = DH / 2;                 // final-layer columns per thread
-    constexpr int n_own = n_chunks / 2;       // chunks par, par+2, ...
-    const int c_last = par + 2 * (n_own - 1);
+    constexpr int W = DH / 4;                 // final-layer columns per thread (8 or 16)
     const float kLog2e = 1.4426950408889634f;
     int cur = 0;
 
@@ -1035,8 +1075,6 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
     if (dbg_on && dbg_n < 500) { dbg[2 * dbg_n] = (tag); dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; } \
   } while (0)
 
-    // see the tile ping-pong kernel: chunk c from `cur` through MUFU.TANH -> bf16 -> A image, while the bias adds
-    // turn `acc` (raw chunk, landed) into `nxt` and the tcgen05.ld of a further chunk is issued mid-step
     // publish activation chunk c: generic-proxy writes -> async proxy, then one arrival per warp
     auto publish = [&](int c) {
       if (!(a.n_groups & 32)) fence_async_smem();
@@ -1044,44 +1082,27 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&ct.act_ready[c]);
     };
-    // The arrival (release) waits for the chunk's st.shared to be performed, so chunk c is published in the middle
-    // of the NEXT step (prev_c), when its stores have long completed, instead of right behind them.
-    auto epi_step = [&](float (&cur_x)[32], float (&nxt)[32], uint32_t (&acc)[32], const float* bias_next, int c,
-                        uint32_t next_ld_col, int prev_c) {
-      const float4* b4 = reinterpret_cast<const float4*>(bias_next);
+    // One epilogue step: accumulator chunk c (bias already added by the bias MMA) -> MUFU.TANH -> bf16 -> A image.
+    // No software pipelining inside the warp: the other three warps of the sub-partition cover its latencies.
+    auto epi_step = [&](uint32_t hcol, int c) {
+      uint32_t x[32];
+      if (!(a.n_groups & 4)) tmem_ld32(hcol + (uint32_t)(c * kChunk), x);
+      tc_wait_ld();
       unsigned char* dst = sAct + img_off(r_tile, c * kChunk, kTileM);
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) cur_x[j + e] = tanh_fast(cur_x[j + e]);
-        if (j < 16) {
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            const float4 b = b4[j / 2 + qq];
-            const int o = 2 * j + 4 * qq;
-            nxt[o] = __uint_as_float(acc[o]) + b.x;         nxt[o + 1] = __uint_as_float(acc[o + 1]) + b.y;
-            nxt[o + 2] = __uint_as_float(acc[o + 2]) + b.z; nxt[o + 3] = __uint_as_float(acc[o + 3]) + b.w;
-          }
-        }
-        if (j > 0 && !(a.n_groups & 8)) {
-          const int k = j - 8;
-          *reinterpret_cast<uint4*>(dst + (k >> 3) * (kTileM * 16)) =
-              make_uint4(pack_bf16(cur_x[k], cur_x[k + 1]), pack_bf16(cur_x[k + 2], cur_x[k + 3]),
-                         pack_bf16(cur_x[k + 4], cur_x[k + 5]), pack_bf16(cur_x[k + 6], cur_x[k + 7]));
-        }
-        if (j == 8) {
-          if (!(a.n_groups & 4)) tmem_ld32(next_ld_col, acc);
-          __syncwarp();
-        }
+        for (int e = 0; e < 8; ++e) x[j + e] = __float_as_uint(tanh_fast(__uint_as_float(x[j + e])));
+        if (!(a.n_groups & 8))
+          *reinterpret_cast<uint4*>(dst + (j >> 3) * (kTileM * 16)) =
+              make_uint4(pack_bf16(__uint_as_float(x[j]), __uint_as_float(x[j + 1])),
+                         pack_bf16(__uint_as_float(x[j + 2]), __uint_as_float(x[j + 3])),
+                         pack_bf16(__uint_as_float(x[j + 4]), __uint_as_float(x[j + 5])),
+                         pack_bf16(__uint_as_float(x[j + 6]), __uint_as_float(x[j + 7])));
       }
-      *reinterpret_cast<uint4*>(dst + 3 * (kTileM * 16)) =
-          make_uint4(pack_bf16(cur_x[24], cur_x[25]), pack_bf16(cur_x[26], cur_x[27]), pack_bf16(cur_x[28], cur_x[29]),
-                     pack_bf16(cur_x[30], cur_x[31]));
-      TNF_STAMP(701);
       publish(c);
-      TNF_STAMP(702);
     };
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
+    auto quad_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory"); };
 
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = it * (int64_t)gridDim.x + blockIdx.x;
@@ -1094,111 +1115,66 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
       float ld_old = 0.f;
 #pragma unroll
       for (int net = 0; net < 2; ++net) {
-        const float* bias = s_bias + net * nb;
 #pragma unroll 1
         for (int l = 0; l < sh.L; ++l) {
-          const float* bl = bias + l * sh.U;
           if (l > 0) cur ^= 1;
           const uint32_t hcol = tmem + lane_addr + (uint32_t)cur * 256u;
           TNF_STAMP(200 + net * 10 + l);
           mbar_wait(&ct.h_ready[net][l], h_par);
           tc_fence_after();
           TNF_STAMP(300 + net * 10 + l);
-          uint32_t acc[32];
-          float xa[32], xb[32];
-          tmem_ld32(hcol + (uint32_t)(par * kChunk), acc);
-          tc_wait_ld();
-          {
-            const float4* b4 = reinterpret_cast<const float4*>(bl + par * kChunk);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = b4[j / 4];
-              xa[j] = __uint_as_float(acc[j]) + b.x;         xa[j + 1] = __uint_as_float(acc[j + 1]) + b.y;
-              xa[j + 2] = __uint_as_float(acc[j + 2]) + b.z; xa[j + 3] = __uint_as_float(acc[j + 3]) + b.w;
-            }
-          }
-          {
-            const int c1 = par + 2 <= c_last ? par + 2 : c_last;
-            tmem_ld32(hcol + (uint32_t)(c1 * kChunk), acc);
-          }
 #pragma unroll 1
-          for (int i = 0; i < n_own; i += 2) {
-            // own chunks ca, cb = ca + 2, ... (clamped re-reads of the last own chunk keep the loop branch-free)
-            const int ca = par + 2 * i;
-            const int cb = ca + 2 <= c_last ? ca + 2 : c_last;
-            const int cc = ca + 4 <= c_last ? ca + 4 : c_last;
-            const int cd = ca + 6 <= c_last ? ca + 6 : c_last;
-            TNF_STAMP(703);
-            tc_wait_ld();
-            TNF_STAMP(700);
-            epi_step(xa, xb, acc, bl + cb * kChunk, ca, hcol + (uint32_t)(cc * kChunk), -1);
-            if (i + 1 < n_own) {
-              TNF_STAMP(703);
-              tc_wait_ld();
-              TNF_STAMP(700);
-              epi_step(xb, xa, acc, bl + cc * kChunk, cb, hcol + (uint32_t)(cd * kChunk), -1);
-            }
-          }
-          tc_wait_ld();
+          for (int c = par; c < n_chunks; c += 4) epi_step(hcol, c);
         }
         // ---- final layer of this net: W columns per thread
-        const float* bL = bias + sh.L * sh.U + par * W;
         const uint32_t fcol = tmem + lane_addr + (uint32_t)(cur ^ 1) * 256u + (uint32_t)(par * W);
         if (net == 0 && par == 0 && valid && a.accum != TNF_LD_WRITE) ld_old = a.log_det[row];
         TNF_STAMP(400 + net);
         mbar_wait(&ct.h_ready[net][sh.L], h_par);
         tc_fence_after();
         TNF_STAMP(500 + net);
+        uint32_t o[W];
+        if (W == 8) tmem_ld8(fcol, reinterpret_cast<uint32_t(&)[8]>(o));
+        else tmem_ld16(fcol, reinterpret_cast<uint32_t(&)[16]>(o));
         if (net == 0) {
+          tc_wait_ld();
 #pragma unroll
-          for (int j0 = 0; j0 < W; j0 += 16) {
-            uint32_t o[16];
-            tmem_ld16(fcol + (uint32_t)j0, o);
-            tc_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) tv[j0 + j] = __uint_as_float(o[j]) + bL[j0 + j];
-          }
+          for (int j = 0; j < W; ++j) tv[j] = __uint_as_float(o[j]);
           tc_fence_before();
-          pair_sync();   // both column halves of t are read out before chunk 0 of the s-net lets MMAs overwrite them
+          quad_sync();   // every column of t is read out before chunk 0 of the s-net lets MMAs overwrite it
         } else {
           mbar_wait(&ct.a1_ready[zb], (uint32_t)((it >> 1) & 1));   // ZT staging of this tile (long since written)
           float* zrow = sZT + (size_t)zb * kTileM * kZS + (size_t)r_tile * kZS + par * W;
           float ld_sum = 0.f;
+          float zin[W];
 #pragma unroll
-          for (int j0 = 0; j0 < W; j0 += 16) {
-            uint32_t o[16];
-            tmem_ld16(fcol + (uint32_t)j0, o);
-            float zin[16];
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 t4 = *reinterpret_cast<const float4*>(zrow + j0 + j);
-              zin[j] = t4.x; zin[j + 1] = t4.y; zin[j + 2] = t4.z; zin[j + 3] = t4.w;
-            }
-            tc_wait_ld();
-            float y[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float sv = __uint_as_float(o[j]) + bL[j0 + j];
-              ld_sum += sv;
-              y[j] = kInverse ? (zin[j] - tv[j0 + j]) * exp2_fast(-sv * kLog2e)
-                              : fmaf(zin[j], exp2_fast(sv * kLog2e), tv[j0 + j]);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(zrow + j0 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          for (int j = 0; j < W; j += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(zrow + j);
+            zin[j] = t4.x; zin[j + 1] = t4.y; zin[j + 2] = t4.z; zin[j + 3] = t4.w;
           }
+          tc_wait_ld();
+          float y[W];
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            const float sv = __uint_as_float(o[j]);
+            ld_sum += sv;
+            y[j] = kInverse ? (zin[j] - tv[j]) * exp2_fast(-sv * kLog2e) : fmaf(zin[j], exp2_fast(sv * kLog2e), tv[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < W; j += 4)
+            *reinterpret_cast<float4*>(zrow + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&ct.y_ready[zb]);
           TNF_STAMP(601);
-          if (par == 1) s_ldp[r_tile] = ld_sum;
-          pair_sync();   // also: both halves of s are read out before the next tile's MMAs may overwrite them
+          if (par > 0) s_ldp[(par - 1) * kTileM + r_tile] = ld_sum;
+          quad_sync();   // also: every column of s is read out before the next tile's MMAs may overwrite it
           if (par == 0 && valid) {
-            const float tot = ld_sum + s_ldp[r_tile];
-            float* o = a.log_det + row;
-            if (a.accum == TNF_LD_WRITE) *o = tot;
-            else if (a.accum == TNF_LD_ADD) *o = ld_old + tot;
-            else *o = ld_old - tot;
+            const float tot = ld_sum + s_ldp[r_tile] + s_ldp[kTileM + r_tile] + s_ldp[2 * kTileM + r_tile];
+            float* op = a.log_det + row;
+            if (a.accum == TNF_LD_WRITE) *op = tot;
+            else if (a.accum == TNF_LD_ADD) *op = ld_old + tot;
+            else *op = ld_old - tot;
           }
         }
       }
@@ -1207,7 +1183,7 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
 #undef TNF_STAMP
   } else {
     // =============================== I/O warps: coalesced loads / stores, A1 image, column statistics ===============================
-    const int w2 = warp - (kEpiWarps + 2);
+    const int w2 = warp - (kEpiWarps2 + 2);
     const int row0 = w2 * (kTileM / 2);
     constexpr int LPR = DH / 2;          // lanes per input row (16 B each)
     constexpr int RPI = 32 / LPR;        // input rows per warp instruction
@@ -1327,7 +1303,7 @@ __global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
   // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == kEpiWarps) tmem_dealloc(tmem, 512);
+  if (warp == kEpiWarps2) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------- diagnostic: one UMMA GEMM
@@ -1472,7 +1448,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
     e = cudaFuncSetAttribute(tc::KERNEL<INV, DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     if (e == cudaSuccess) tc::KERNEL<INV, DHV><<<grid, THREADS, smem, st>>>(a);                               \
   } while (0)
-  int stat_blocks = grid * tc::kEpiWarps;
+  int stat_blocks = grid * tc::kEpiWarps2;
   if (pipelined) {
     stat_blocks = grid * 2;
 #define TNF_TC2_LAUNCH(INV, DHV, UV)                                                                          \
