@@ -8,6 +8,8 @@ from torch_nf_b200 import _lib, ops
 from torch_nf_b200.synthetic import synthetic_params
 
 D, U, L, N = 64, 256, 2, 1 << 20
+if len(sys.argv) > 2:
+    N = int(sys.argv[2])
 params = torch.tensor(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=0)).cuda()
 packed = ops.tc_pack(params[0], D, U, L, True)
 z = torch.randn(1, N, D, device="cuda")
