@@ -98,7 +98,7 @@ int tnf_maf_bwd(const void* z_in, const void* params, int64_t param_row_stride, 
  * col_stats (or NULL): receives [sum(D) | sumsq(D) | rows] (float64, the layout of
  * tnf_colstats) of the OUTPUT columns = the next BatchNorm's batch statistics
  * (:401-410), accumulated inside the kernel (fp32 per warp, float64 across warps);
- * needs stats_workspace of tnf_colstats_workspace_bytes(D) bytes; D = 64 only.
+ * needs stats_workspace of tnf_colstats_workspace_bytes(D) bytes; D <= 128 (variant 1: D = 64 only).
  * z_out must not alias z_in. */
 int tnf_tc_supported(int D, int U, int L);
 /* diagnostic: out[128 x N] = bf16(A[128 x K]) . bf16(W[K x N]) through the same
@@ -109,8 +109,8 @@ int tnf_tc_supported(int D, int U, int L);
 void tnf_tc_set_debug(void* dev_buffer);
 /* diagnostic: 1 = only one epilogue group works (no tile ping-pong), 2 = default. */
 void tnf_tc_set_groups(int n_groups);
-/* diagnostic: kernel choice of tnf_coupling_tc: 0 = automatic (K-chunk pipelined kernel for D <= 128,
- * tile ping-pong kernel otherwise), 1 = always the tile ping-pong kernel, 2 = same as 0. */
+/* diagnostic: kernel choice of tnf_coupling_tc: 0 = automatic (16-epilogue-warp two-tile kernel for
+ * D <= 128, the first 8-epilogue-warp kernel for D = 256), 1 = always the first kernel. */
 void tnf_tc_set_variant(int variant);
 int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N, int a_in_tmem,
                          tnf_stream_t stream);

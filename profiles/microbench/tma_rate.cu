@@ -16,8 +16,10 @@ __global__ void __launch_bounds__(128, 1) bench(const unsigned char* src, size_t
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < n_thr) {
-    const int tw = threadIdx.x >> 5;
+  const bool lanes_mode = n_thr < 0;
+  const int n_iss = lanes_mode ? -n_thr : n_thr;
+  if (lanes_mode ? (threadIdx.x < n_iss) : ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < n_iss)) {
+    const int tw = lanes_mode ? threadIdx.x : (threadIdx.x >> 5);
     uint64_t* bar = bar_all + tw * 8;
     unsigned char* smem = smem_all + (size_t)tw * depth * copy_bytes;
     size_t off = ((size_t)(blockIdx.x * 4 + tw) * 16384) % src_bytes;
@@ -47,10 +49,10 @@ int main() {
   long long* d; cudaMalloc(&d, 148 * 8);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int n_bytes_total = 8 << 20;   // per SM
-  for (int n_thr : {1, 2, 4})
-  for (int copy_kb : {8, 16})
+  for (int n_thr : {1, 2, -2, -4})
+  for (int copy_kb : {16})
     for (int depth : {2, 4}) {
-      if (copy_kb * depth * n_thr > 192) continue;
+      if (copy_kb * depth * (n_thr < 0 ? -n_thr : n_thr) > 192) continue;
       const int copy_bytes = copy_kb * 1024, n_copies = n_bytes_total / copy_bytes;
       for (int grid : {148}) {
         bench<<<grid, 128, 200 * 1024>>>(src, src_bytes, copy_bytes, depth, n_copies, d, n_thr);
@@ -58,7 +60,7 @@ int main() {
         long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
         double c = 0; for (int i = 0; i < grid; ++i) c += h[i]; c /= grid;
         printf("%d issuing threads, copy %2d KB x %d in flight each, %3d SMs: %.1f B/cycle/SM, %.0f cycles per copy per thread  [%s]\n", n_thr, copy_kb, depth, grid,
-               (double)n_bytes_total * n_thr / c, c / n_copies, cudaGetErrorString(e));
+               (double)n_bytes_total * (n_thr < 0 ? -n_thr : n_thr) / c, c / n_copies, cudaGetErrorString(e));
       }
     }
   return 0;

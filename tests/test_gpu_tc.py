@@ -66,6 +66,33 @@ def test_coupling_tc_vs_oracle(D, U, L, N, upper):
         assert (ld - ldr).abs().max().item() < 5e-2 * L
 
 
+@pytest.mark.parametrize("D,U,L,N", [(64, 256, 2, 1000), (64, 128, 2, 257), (128, 256, 2, 384), (64, 64, 3, 129)])
+def test_coupling_tc_first_kernel_variant(D, U, L, N):
+    """Diagnostic variant 1 routes D <= 128 through the first (8 epilogue warp) kernel: same results as the default
+    two-tile kernel up to bf16 rounding of the bias (the default adds biases through a bf16 hi/lo bias MMA)."""
+    params = T(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=3))
+    z_in = T(synthetic_noise(1, N, D, seed=8).astype(np.float32)).cuda()
+    packed = ops.tc_pack(params.cuda()[0], D, U, L, True)
+    out = {}
+    try:
+        for variant in (0, 1):
+            _lib.lib().tnf_tc_set_variant(variant)
+            for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
+                z, ld = ops.coupling_tc(z_in, packed, D, U, L, True, direction)
+                torch.cuda.synchronize()
+                out[(variant, direction)] = (z.cpu(), ld.cpu())
+    finally:
+        _lib.lib().tnf_tc_set_variant(0)
+    for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
+        z0, l0 = out[(0, direction)]
+        z1, l1 = out[(1, direction)]
+        assert (z0 - z1).abs().max().item() < 2e-2 * L
+        assert (l0 - l1).abs().max().item() < 2e-2 * L
+        ze, lde = O.coupling_bf16_emulated(z_in.cpu(), params, D, L, U, True, direction == ops.TNF_INVERSE)
+        assert (z1 - ze).abs().max().item() < 2e-2 * L
+        assert (l1.view(1, N) - lde).abs().max().item() < 2e-2 * L
+
+
 def test_coupling_tc_accum_and_preaffine():
     D, U, L, N = 64, 256, 2, 515
     params = T(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=9))
@@ -111,8 +138,8 @@ def test_normflow_bf16_mode_c3(golden):
 
 def test_coupling_tc_fused_column_stats():
     """The kernel's own [sum | sumsq | rows] of its output equals tnf_colstats on that output."""
-    D, U, L = 64, 256, 2
-    for N, upper in ((1000, True), (128 * 148 * 2 + 77, False), (90, True)):
+    U, L = 256, 2
+    for D, N, upper in ((64, 1000, True), (64, 128 * 148 * 2 + 77, False), (64, 90, True), (128, 128 * 148 + 5, True)):
         params = T(synthetic_params([("RealNVP", L, U, upper)], D, 1, seed=21))
         z_in = torch.randn(1, N, D, device="cuda") * 1.5 + 0.3
         packed = ops.tc_pack(params.cuda()[0], D, U, L, upper)

@@ -16,15 +16,23 @@
 // through a ring of 16 KB stages by one producer warp (cp.async.bulk + mbarrier
 // complete_tx).
 //
-// Tile ping-pong: the 8 epilogue warps form two groups of 4 (one warp per TMEM
-// lane quadrant); each group owns a tile, 256 TMEM columns for its accumulator
-// and its own A images.  The MMA warp serves the two groups alternately in a
-// static order, so while one group runs its MUFU-bound tanh epilogue (or waits
-// on HBM), the tensor pipe computes the other group's next layer.
+// Two kernels share this file:
 //
-// Warp roles (320 threads): warps 0-7 epilogue (group = w/4, rows 32*(w%4)..+31
-// of the group's tile, thread = one sample row); warp 8 MMA issuer (warp-uniform
-// control flow, one elected lane issues); warp 9 weight producer.
+// coupling_tc3_kernel (D <= 128, the default): two tiles in flight per CTA.  16 epilogue
+// warps in two groups of 8 (per group two warps per TMEM lane quadrant, each taking the
+// accumulator chunks of one parity); each group owns a tile, 256 TMEM columns and its own
+// A images.  The MMA warp serves the groups alternately in a static order, so while one
+// group runs its MUFU-bound tanh epilogue the tensor pipe computes the other group's next
+// layer.  Biases are added by one extra K=16 MMA per layer (constant [1,1,0..] A image x
+// bf16 hi/lo bias image), the MMA jobs are fully unrolled per hidden width, and two I/O
+// warps load the conditioning half with coalesced 16-byte accesses, build the bf16 A1
+// image and write the pass-through half.  Warp roles (640 threads): 0-15 epilogue,
+// 16 MMA issuer, 17 weight producer, 18-19 I/O.
+//
+// coupling_tc_kernel (D = 256, or diagnostic variant 1): the first design - 8 epilogue
+// warps in two groups of 4 (thread = one sample row, all I/O in the epilogue threads,
+// biases added in the epilogue), warp 8 MMA issuer, warp 9 weight producer (320 threads).
+// Kept because the two-tile kernel's images do not fit shared memory at D = 256.
 //
 // Reference semantics: torch_nf/bijectors.py:145-242 (RealNVP).
 #include <cuda_bf16.h>
@@ -71,7 +79,7 @@ struct Shape {
     return (int64_t)d_in * U + (int64_t)(L - 1) * U * U + (int64_t)U * d_out;
   }
   __host__ __device__ int net_bias_elems() const { return L * U + d_out; }
-  // bias operand images (pipelined kernel): per (layer, net) one K=16 group of J columns, K-row 0 = bf16(b),
+  // bias operand images (two-tile kernel): per (layer, net) one K=16 group of J columns, K-row 0 = bf16(b),
   // K-row 1 = bf16(b - bf16(b)), rest 0; multiplied by a constant [1, 1, 0, ...] A image the MMA adds the bias
   __host__ __device__ int64_t bias_img_bytes() const { return 2 * (int64_t)net_bias_elems() * 32; }
   __host__ __device__ int64_t bias_img_off(int l, int net) const {
@@ -240,12 +248,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
-  const int G = (a.n_groups & 3) == 1 ? 1 : 2;   // epilogue groups in use (2; 1 = diagnostic solo mode)
+  const int G = a.n_groups == 1 ? 1 : 2;   // epilogue groups in use (2; 1 = diagnostic solo mode)
   const int64_t iters = (n_tiles + G * (int64_t)gridDim.x - 1) / (G * (int64_t)gridDim.x);
   const int64_t weight_bytes = 2 * sh.net_weight_elems() * 2;
 
@@ -852,79 +854,47 @@ __global__ void __launch_bounds__(kThreads, 1) coupling_tc_kernel(Args a) {
   if (warp == kEpiWarps) tmem_dealloc(tmem, 512);
 }
 
-// ================================================================ K-chunk pipelined kernel (D <= 128)
-// One tile in flight per CTA, 16 epilogue warps on it (warp w: TMEM lane quadrant w%4, accumulator chunks
-// c = w/4 (mod 4); four warps per SM sub-partition, so the MUFU pipe stays fed while a warp packs, stores and
-// publishes).  The 512 TMEM columns hold TWO 256-column accumulators, so the MMA warp can run layer l+1
-// into one while the epilogue still drains layer l from the other: it issues the two K=16 MMAs of K-chunk c as
-// soon as the 4 warps owning chunk c have published those 32 activation columns (act_ready[c]) - the tensor
-// pipe trails the MUFU-bound tanh epilogue by one chunk instead of waiting for the whole layer.  Global I/O is
-// done by two dedicated warps with coalesced 16-byte accesses: they load the next tile, apply the folded
-// per-column affine, write the conditioning half as the bf16 A1 image (double buffered) and straight through to
-// z_out, and stage the transformed half in shared memory (ZT, padded rows); the epilogue warps transform it in
-// place and the same two warps store it (and accumulate the fused column statistics).
-constexpr int kEpiWarps2 = 16;   // 4 per SM sub-partition: the other three hide one warp's non-MUFU work
-constexpr int kThreads2 = (kEpiWarps2 + 4) * 32;
-constexpr int kMaxJobs = 6;   // L + 1 <= 6
+// ================================================================ building blocks of the two-tile kernel (D <= 128)
+constexpr int kEpiWarps2 = 16;   // 4 per SM sub-partition
 constexpr int kOnesBytes = 2 * kTileM * 16;   // A image of one K=16 step: [1, 1, 0, ..., 0] in every row
 
-struct __align__(16) Ctrl2 {
-  uint64_t w_full[kMaxStages];
-  uint64_t w_empty[kMaxStages];
-  uint64_t a1_ready[2];     // 2 I/O warps: A1 image + ZT staging of a tile written
-  uint64_t a1_free[2];      // tcgen05.commit: both layer-0 jobs of the tile have read the A1 image
-  uint64_t y_ready[2];      // 16 epilogue warps: transformed half written back into the ZT staging
-  uint64_t act_ready[8];    // 4 epilogue warps: activation chunk c (32 K-columns, all 128 rows) written
-  uint64_t h_ready[2][kMaxJobs];   // tcgen05.commit per (net, layer): accumulator complete
-  uint32_t tmem_base;
-  uint32_t pad;
-};
-// dynamic shared memory:
-//   [ring: n_stages x 16 KB][A1 x2][Act][ones 4 KB][ZT x2][Ctrl2][pre_scale D][pre_shift D][ld partial 3 x 128]
-__host__ __device__ inline size_t zt_bytes(const Shape& sh) { return (size_t)kTileM * (sh.d_out + 4) * sizeof(float); }
-__host__ __device__ inline size_t smem_bytes2(const Shape& sh, int n_stages) {
-  return (size_t)n_stages * sh.stage_elems() * 2 + 2 * sh.a1_bytes() + sh.act_bytes() + kOnesBytes + 2 * zt_bytes(sh) +
-         sizeof(Ctrl2) + (size_t)(2 * sh.D + 3 * kTileM) * sizeof(float);
-}
 __host__ __device__ inline bool shape_supported2(int D, int U, int L) {
   return shape_supported(D, U, L) && D <= 128;
 }
 
-// One GEMM job of the MMA warp, fully unrolled over its 32-wide K chunks: per chunk at most two mbarrier waits
-// (activation chunk published / weight stage landed), two K=16 MMAs whose descriptor low words differ from the
-// job's base by compile-time constants, and a commit when the weight stage is used up.  The loop is run by the
-// whole warp (uniform control flow), the elected lane issues.
-template <int K, int N, bool kWaitAct>
+// One GEMM job of the MMA warp, fully unrolled over its 32-wide K chunks: the job's bias MMA first (accumulator :=
+// ones image . bias image, a stage of its own), then per chunk two K=16 MMAs whose descriptor low words differ from the
+// job's base by compile-time constants, an mbarrier wait when a new weight stage begins and a commit when it is used
+// up.  Run by the whole warp (uniform control flow), the elected lane issues.  A single warp executes dependent
+// instructions only every ~5 cycles, so a generic loop with run-time strides (~80 instructions per chunk) was the
+// bottleneck of the first kernel; unrolled with constant offsets a chunk step is ~20 instructions.
+template <int K, int N>
 __device__ __forceinline__ void mma_job(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo_ring, uint32_t b_hi,
-                                        uint32_t ones_lo, uint32_t act_bar0, uint32_t e_par, uint32_t wfull0,
-                                        uint32_t wempty0, uint32_t S, uint32_t& slot, uint32_t& phase, bool leader,
-                                        long long* t_w = nullptr) {
+                                        uint32_t ones_lo, uint32_t wfull0, uint32_t wempty0, uint32_t S, uint32_t& slot,
+                                        uint32_t& phase, bool leader, long long* t_w = nullptr) {
   constexpr int KS = (kStageElems / N) < K ? (kStageElems / N) : K;   // K rows per weight stage
   constexpr int CPS = KS / kChunk;                                     // chunks per stage
   constexpr uint32_t kStage16 = kStageBytes >> 4;
   const uint32_t idesc = make_idesc(N);
+  {
+    const long long c0 = t_w ? clock64() : 0;
+    mbar_wait_addr(wfull0 + slot * 8u, phase);
+    if (t_w) *t_w += clock64() - c0;
+    tc_fence_after();
+    if (leader) {
+      umma_ss2(d_tmem, ones_lo, a_hi, b_lo_ring + slot * kStage16, b_hi, idesc, 0u);
+      tc_commit_addr(wempty0 + slot * 8u);
+    }
+    if (++slot == S) { slot = 0; phase ^= 1; }
+  }
 #pragma unroll
   for (int c = 0; c < K / kChunk; ++c) {
-    if (kWaitAct) mbar_wait_addr(act_bar0 + 8u * c, e_par);
-    if (c == 0) {
-      // accumulator := bias (ones image . bias image, a stage of its own).  Issued only after the first activation
-      // chunk is published: that also tells that the epilogue warps have drained whatever the accumulator held.
-      const long long c0 = t_w ? clock64() : 0;
-      mbar_wait_addr(wfull0 + slot * 8u, phase);
-      if (t_w) *t_w += clock64() - c0;
-      tc_fence_after();
-      if (leader) {
-        umma_ss2(d_tmem, ones_lo, a_hi, b_lo_ring + slot * kStage16, b_hi, idesc, 0u);
-        tc_commit_addr(wempty0 + slot * 8u);
-      }
-      if (++slot == S) { slot = 0; phase ^= 1; }
-    }
     if (c % CPS == 0) {
       const long long c0 = t_w ? clock64() : 0;
       mbar_wait_addr(wfull0 + slot * 8u, phase);
       if (t_w) *t_w += clock64() - c0;
+      tc_fence_after();
     }
-    tc_fence_after();
     if (leader) {
       const uint32_t b_lo = b_lo_ring + slot * kStage16 + (uint32_t)((c % CPS) * 4 * N);
       umma_ss2(d_tmem, a_lo + 512u * c, a_hi, b_lo, b_hi, idesc, 1u);
@@ -935,382 +905,6 @@ __device__ __forceinline__ void mma_job(uint32_t d_tmem, uint32_t a_lo, uint32_t
       if (++slot == S) { slot = 0; phase ^= 1; }
     }
   }
-}
-
-template <bool kInverse, int DH, int U_>   // DH = D/2 = d_in = d_out in {32, 64}; U_ = hidden units
-__global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const Shape sh(a.D, a.U, a.L, a.upper);
-  const int S = a.n_stages;
-  unsigned char* ring = smem_raw;
-  const uint32_t stage_bytes = (uint32_t)sh.stage_elems() * 2;
-  unsigned char* sA1 = ring + (size_t)S * stage_bytes;             // 2 images (tile parity)
-  unsigned char* sAct = sA1 + 2 * sh.a1_bytes();                    // 1 image
-  unsigned char* sOnes = sAct + sh.act_bytes();                     // constant A image for the bias MMA
-  float* sZT = reinterpret_cast<float*>(sOnes + kOnesBytes);        // 2 x [128][DH+4] fp32 (tile parity)
-  constexpr int kZS = DH + 4;                                       // padded row stride (floats)
-  Ctrl2& ct = *reinterpret_cast<Ctrl2*>(reinterpret_cast<unsigned char*>(sZT) + 2 * zt_bytes(sh));
-  float* s_pscale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl2));
-  float* s_pshift = s_pscale + sh.D;
-  float* s_ldp = s_pshift + sh.D;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
-  const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles blockIdx.x + i*grid
-  constexpr int n_chunks = U_ / kChunk;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < S; ++i) { mbar_init(&ct.w_full[i], 1); mbar_init(&ct.w_empty[i], 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&ct.a1_ready[b], 2);
-      mbar_init(&ct.a1_free[b], 1);
-      mbar_init(&ct.y_ready[b], kEpiWarps2);
-    }
-    for (int c = 0; c < 8; ++c) mbar_init(&ct.act_ready[c], 4);
-    for (int n = 0; n < 2; ++n)
-      for (int l = 0; l < kMaxJobs; ++l) mbar_init(&ct.h_ready[n][l], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == kEpiWarps2) tmem_alloc(&ct.tmem_base, 512);
-  {
-    for (int i = threadIdx.x; i < kOnesBytes / 4; i += blockDim.x)   // row r: K columns 0 and 1 are 1.0 (bf16 0x3f80)
-      reinterpret_cast<uint32_t*>(sOnes)[i] = (i < kTileM * 4 && (i & 3) == 0) ? 0x3f803f80u : 0u;
-    fence_async_smem();
-    for (int i = threadIdx.x; i < sh.D; i += blockDim.x) {
-      s_pscale[i] = a.pre_scale ? a.pre_scale[i] : 1.0f;
-      s_pshift[i] = a.pre_shift ? a.pre_shift[i] : 0.0f;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = ct.tmem_base;
-
-  if (warp == kEpiWarps2 + 1) {
-    // =============================== weight producer (one elected lane) ===============================
-    if (elect_one()) {
-      uint32_t slot = 0, phase = 0;
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        for (int net = 0; net < 2; ++net) {
-          size_t off = 0;
-          for (int l = 0; l <= sh.L; ++l) {
-            const int K = sh.K_of(l), J = sh.J_of(l), N = sh.N_of(l);
-            const int ks = sh.stage_k(K, N);
-            const uint32_t bytes = (uint32_t)(ks * N * 2);
-            const unsigned char* nsrc = a.packed + off + (size_t)net * K * J * 2;
-            {   // the job's bias operand image travels as a stage of its own, ahead of the weights
-              mbar_wait(&ct.w_empty[slot], phase ^ 1);
-              mbar_arrive_expect_tx(&ct.w_full[slot], (uint32_t)J * 32u);
-              bulk_g2s(ring + (size_t)slot * stage_bytes, a.packed + sh.bias_img_off(l, net), (uint32_t)J * 32u, &ct.w_full[slot]);
-              if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
-            }
-            for (int st = 0; st < K / ks; ++st) {
-              mbar_wait(&ct.w_empty[slot], phase ^ 1);
-              mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
-              bulk_g2s(ring + (size_t)slot * stage_bytes, nsrc + (size_t)st * bytes, bytes, &ct.w_full[slot]);
-              if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
-            }
-            off += (size_t)2 * K * J * 2;
-          }
-        }
-      }
-    }
-  } else if (warp == kEpiWarps2) {
-    // =============================== MMA issuer (warp-uniform, elected lane issues) ===============================
-    const bool leader = elect_one();
-    uint32_t slot = 0, phase = 0, e_par = 0;
-    int cur = 0;   // accumulator buffer of the most recent hidden-layer job
-    const long long t_all = a.dbg != nullptr ? clock64() : 0;
-    const uint32_t a1_sz16 = (uint32_t)sh.a1_bytes() >> 4;
-    const uint32_t act_bar0 = smem_u32(&ct.act_ready[0]);
-    const uint32_t wfull0 = smem_u32(&ct.w_full[0]), wempty0 = smem_u32(&ct.w_empty[0]);
-    const uint32_t ring16 = smem_u32(ring) >> 4;
-    const uint64_t a1_desc = make_desc(smem_u32(sA1), kTileM), act_desc = make_desc(smem_u32(sAct), kTileM);
-    const uint32_t a_hi = (uint32_t)(a1_desc >> 32);
-    const uint64_t bU_desc = make_desc(0u, U_), bF_desc = make_desc(0u, DH);
-    const uint32_t bU_lo = (uint32_t)bU_desc + ring16, bU_hi = (uint32_t)(bU_desc >> 32);
-    const uint32_t bF_lo = (uint32_t)bF_desc + ring16, bF_hi = (uint32_t)(bF_desc >> 32);
-    const uint32_t act_lo = (uint32_t)act_desc;
-    const uint32_t ones_lo = (uint32_t)make_desc(smem_u32(sOnes), kTileM);
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      const uint32_t ab = (uint32_t)(it & 1);
-      const uint32_t a1_lo = (uint32_t)a1_desc + ab * a1_sz16;
-      mbar_wait(&ct.a1_ready[ab], (uint32_t)((it >> 1) & 1));
-#pragma unroll 1
-      for (int net = 0; net < 2; ++net) {
-        // layer 0: A1 image, accumulator = the buffer the previous epilogue phase has just drained
-        mma_job<DH, U_, false>(tmem + (uint32_t)cur * 256u, a1_lo, a_hi, bU_lo, bU_hi, ones_lo, act_bar0, e_par, wfull0, wempty0,
-                               (uint32_t)S, slot, phase, leader);
-        if (leader) {
-          tc_commit(&ct.h_ready[net][0]);
-          if (net == 1) tc_commit(&ct.a1_free[ab]);
-        }
-        // hidden layers 1..L-1, each trailing the epilogue of the layer before it chunk by chunk
-#pragma unroll 1
-        for (int l = 1; l < sh.L; ++l) {
-          cur ^= 1;
-          mma_job<U_, U_, true>(tmem + (uint32_t)cur * 256u, act_lo, a_hi, bU_lo, bU_hi, ones_lo, act_bar0, e_par, wfull0, wempty0,
-                                (uint32_t)S, slot, phase, leader);
-          e_par ^= 1;
-          if (leader) tc_commit(&ct.h_ready[net][l]);
-        }
-        // final layer -> the other buffer's first DH columns
-        mma_job<U_, DH, true>(tmem + (uint32_t)(cur ^ 1) * 256u, act_lo, a_hi, bF_lo, bF_hi, ones_lo, act_bar0, e_par, wfull0, wempty0,
-                              (uint32_t)S, slot, phase, leader);
-        e_par ^= 1;
-        if (leader) tc_commit(&ct.h_ready[net][sh.L]);
-        __syncwarp();
-      }
-    }
-    if (a.dbg != nullptr && blockIdx.x == 0 && leader) {
-      a.dbg[2040] = 0; a.dbg[2041] = 0; a.dbg[2042] = clock64() - t_all;
-    }
-  } else if (warp < kEpiWarps2) {
-    // =============================== epilogue warps ===============================
-    const int q = warp & 3, par = warp >> 2;  // par in 0..3
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int r_tile = q * 32 + lane;
-    constexpr int W = DH / 4;                 // final-layer columns per thread (8 or 16)
-    const float kLog2e = 1.4426950408889634f;
-    int cur = 0;
-
-    int dbg_n = 0;
-    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
-    long long* dbg = a.dbg;
-#define TNF_STAMP(tag)                                                                     \
-  do {                                                                                     \
-    if (dbg_on && dbg_n < 500) { dbg[2 * dbg_n] = (tag); dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; } \
-  } while (0)
-
-    // publish activation chunk c: generic-proxy writes -> async proxy, then one arrival per warp
-    auto publish = [&](int c) {
-      if (!(a.n_groups & 32)) fence_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ct.act_ready[c]);
-    };
-    // One epilogue step: accumulator chunk c (bias already added by the bias MMA) -> MUFU.TANH -> bf16 -> A image.
-    // No software pipelining inside the warp: the other three warps of the sub-partition cover its latencies.
-    auto epi_step = [&](uint32_t hcol, int c) {
-      uint32_t x[32];
-      if (!(a.n_groups & 4)) tmem_ld32(hcol + (uint32_t)(c * kChunk), x);
-      tc_wait_ld();
-      unsigned char* dst = sAct + img_off(r_tile, c * kChunk, kTileM);
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[j + e] = __float_as_uint(tanh_fast(__uint_as_float(x[j + e])));
-        if (!(a.n_groups & 8))
-          *reinterpret_cast<uint4*>(dst + (j >> 3) * (kTileM * 16)) =
-              make_uint4(pack_bf16(__uint_as_float(x[j]), __uint_as_float(x[j + 1])),
-                         pack_bf16(__uint_as_float(x[j + 2]), __uint_as_float(x[j + 3])),
-                         pack_bf16(__uint_as_float(x[j + 4]), __uint_as_float(x[j + 5])),
-                         pack_bf16(__uint_as_float(x[j + 6]), __uint_as_float(x[j + 7])));
-      }
-      publish(c);
-    };
-    auto quad_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory"); };
-
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      const int64_t tile = it * (int64_t)gridDim.x + blockIdx.x;
-      const int64_t row = tile * kTileM + r_tile;
-      const bool valid = row < a.rows;
-      const uint32_t h_par = (uint32_t)(it & 1);
-      const int zb = (int)(it & 1);
-      TNF_STAMP(100);
-      float tv[W];
-      float ld_old = 0.f;
-#pragma unroll
-      for (int net = 0; net < 2; ++net) {
-#pragma unroll 1
-        for (int l = 0; l < sh.L; ++l) {
-          if (l > 0) cur ^= 1;
-          const uint32_t hcol = tmem + lane_addr + (uint32_t)cur * 256u;
-          TNF_STAMP(200 + net * 10 + l);
-          mbar_wait(&ct.h_ready[net][l], h_par);
-          tc_fence_after();
-          TNF_STAMP(300 + net * 10 + l);
-#pragma unroll 1
-          for (int c = par; c < n_chunks; c += 4) epi_step(hcol, c);
-        }
-        // ---- final layer of this net: W columns per thread
-        const uint32_t fcol = tmem + lane_addr + (uint32_t)(cur ^ 1) * 256u + (uint32_t)(par * W);
-        if (net == 0 && par == 0 && valid && a.accum != TNF_LD_WRITE) ld_old = a.log_det[row];
-        TNF_STAMP(400 + net);
-        mbar_wait(&ct.h_ready[net][sh.L], h_par);
-        tc_fence_after();
-        TNF_STAMP(500 + net);
-        uint32_t o[W];
-        if (W == 8) tmem_ld8(fcol, reinterpret_cast<uint32_t(&)[8]>(o));
-        else tmem_ld16(fcol, reinterpret_cast<uint32_t(&)[16]>(o));
-        if (net == 0) {
-          tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < W; ++j) tv[j] = __uint_as_float(o[j]);
-          tc_fence_before();
-          quad_sync();   // every column of t is read out before chunk 0 of the s-net lets MMAs overwrite it
-        } else {
-          mbar_wait(&ct.a1_ready[zb], (uint32_t)((it >> 1) & 1));   // ZT staging of this tile (long since written)
-          float* zrow = sZT + (size_t)zb * kTileM * kZS + (size_t)r_tile * kZS + par * W;
-          float ld_sum = 0.f;
-          float zin[W];
-#pragma unroll
-          for (int j = 0; j < W; j += 4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(zrow + j);
-            zin[j] = t4.x; zin[j + 1] = t4.y; zin[j + 2] = t4.z; zin[j + 3] = t4.w;
-          }
-          tc_wait_ld();
-          float y[W];
-#pragma unroll
-          for (int j = 0; j < W; ++j) {
-            const float sv = __uint_as_float(o[j]);
-            ld_sum += sv;
-            y[j] = kInverse ? (zin[j] - tv[j]) * exp2_fast(-sv * kLog2e) : fmaf(zin[j], exp2_fast(sv * kLog2e), tv[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < W; j += 4)
-            *reinterpret_cast<float4*>(zrow + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&ct.y_ready[zb]);
-          TNF_STAMP(601);
-          if (par > 0) s_ldp[(par - 1) * kTileM + r_tile] = ld_sum;
-          quad_sync();   // also: every column of s is read out before the next tile's MMAs may overwrite it
-          if (par == 0 && valid) {
-            const float tot = ld_sum + s_ldp[r_tile] + s_ldp[kTileM + r_tile] + s_ldp[2 * kTileM + r_tile];
-            float* op = a.log_det + row;
-            if (a.accum == TNF_LD_WRITE) *op = tot;
-            else if (a.accum == TNF_LD_ADD) *op = ld_old + tot;
-            else *op = ld_old - tot;
-          }
-        }
-      }
-      TNF_STAMP(600);
-    }
-#undef TNF_STAMP
-  } else {
-    // =============================== I/O warps: coalesced loads / stores, A1 image, column statistics ===============================
-    const int w2 = warp - (kEpiWarps2 + 2);
-    const int row0 = w2 * (kTileM / 2);
-    constexpr int LPR = DH / 2;          // lanes per input row (16 B each)
-    constexpr int RPI = 32 / LPR;        // input rows per warp instruction
-    constexpr int NI = (kTileM / 2) / RPI;
-    constexpr int LPT = DH / 4;          // lanes per transformed-half row
-    constexpr int RPT = 32 / LPT;
-    constexpr int NT = (kTileM / 2) / RPT;
-    const int col = 4 * (lane % LPR);
-    const bool is_c = (col >= DH) == (sh.c_off != 0);
-    const int hc = col - (is_c ? sh.c_off : sh.t_off);   // column inside its half
-    const int rsub = lane / LPR;
-    const int tcol = 4 * (lane % LPT), trsub = lane / LPT;
-    const float4 ps = *reinterpret_cast<const float4*>(s_pscale + col);
-    const float4 pb = *reinterpret_cast<const float4*>(s_pshift + col);
-    const bool want_stats = a.stat_partials != nullptr;
-    float sv1[4] = {0.f, 0.f, 0.f, 0.f}, sv2[4] = {0.f, 0.f, 0.f, 0.f};   // pass-through columns col..col+3
-    float sy1[4] = {0.f, 0.f, 0.f, 0.f}, sy2[4] = {0.f, 0.f, 0.f, 0.f};   // transformed columns t_off+tcol..+3
-
-    auto load_tile = [&](int64_t it) {
-      const int b = (int)(it & 1);
-      const int64_t tile = it * (int64_t)gridDim.x + blockIdx.x;
-      unsigned char* a1 = sA1 + (size_t)b * sh.a1_bytes();
-      float* zt = sZT + (size_t)b * kTileM * kZS;
-#pragma unroll 1
-      for (int n0 = 0; n0 < NI; n0 += 8) {
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int r = row0 + (n0 + u) * RPI + rsub;
-          const int64_t grow = tile * kTileM + r;
-          v[u] = grow < a.rows ? __ldg(reinterpret_cast<const float4*>(a.z_in + grow * sh.D + col))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int r = row0 + (n0 + u) * RPI + rsub;
-          const int64_t grow = tile * kTileM + r;
-          float4 x;
-          x.x = fmaf(v[u].x, ps.x, pb.x); x.y = fmaf(v[u].y, ps.y, pb.y);
-          x.z = fmaf(v[u].z, ps.z, pb.z); x.w = fmaf(v[u].w, ps.w, pb.w);
-          if (is_c) {
-            *reinterpret_cast<uint2*>(a1 + img_off(r, hc, kTileM)) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
-            if (grow < a.rows) {
-              *reinterpret_cast<float4*>(a.z_out + grow * sh.D + col) = x;
-              if (want_stats) {
-                sv1[0] += x.x; sv1[1] += x.y; sv1[2] += x.z; sv1[3] += x.w;
-                sv2[0] = fmaf(x.x, x.x, sv2[0]); sv2[1] = fmaf(x.y, x.y, sv2[1]);
-                sv2[2] = fmaf(x.z, x.z, sv2[2]); sv2[3] = fmaf(x.w, x.w, sv2[3]);
-              }
-            }
-          } else {
-            *reinterpret_cast<float4*>(zt + (size_t)r * kZS + hc) = x;
-          }
-        }
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ct.a1_ready[b]);
-    };
-    auto store_tile = [&](int64_t it) {
-      const int b = (int)(it & 1);
-      const int64_t tile = it * (int64_t)gridDim.x + blockIdx.x;
-      const float* zt = sZT + (size_t)b * kTileM * kZS;
-      mbar_wait(&ct.y_ready[b], (uint32_t)((it >> 1) & 1));
-#pragma unroll 4
-      for (int n = 0; n < NT; ++n) {
-        const int r = row0 + n * RPT + trsub;
-        const int64_t grow = tile * kTileM + r;
-        const float4 y = *reinterpret_cast<const float4*>(zt + (size_t)r * kZS + tcol);
-        if (grow < a.rows) {
-          *reinterpret_cast<float4*>(a.z_out + grow * sh.D + sh.t_off + tcol) = y;
-          if (want_stats) {
-            sy1[0] += y.x; sy1[1] += y.y; sy1[2] += y.z; sy1[3] += y.w;
-            sy2[0] = fmaf(y.x, y.x, sy2[0]); sy2[1] = fmaf(y.y, y.y, sy2[1]);
-            sy2[2] = fmaf(y.z, y.z, sy2[2]); sy2[3] = fmaf(y.w, y.w, sy2[3]);
-          }
-        }
-      }
-    };
-    if (my_tiles > 0) load_tile(0);
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      if (it + 1 < my_tiles) {
-        const int64_t t1 = it + 1;
-        if (t1 >= 2) mbar_wait(&ct.a1_free[t1 & 1], (uint32_t)(((t1 >> 1) - 1) & 1));   // layer-0 jobs of tile t1-2 done
-        load_tile(t1);
-      }
-      store_tile(it);
-    }
-    if (want_stats) {   // one [2][D] block of doubles per I/O warp
-      double* out = a.stat_partials + ((size_t)blockIdx.x * 2 + w2) * 2 * sh.D;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-#pragma unroll
-        for (int o = LPR; o < 32; o <<= 1) {
-          sv1[e] += __shfl_xor_sync(0xffffffffu, sv1[e], o);
-          sv2[e] += __shfl_xor_sync(0xffffffffu, sv2[e], o);
-        }
-#pragma unroll
-        for (int o = LPT; o < 32; o <<= 1) {
-          sy1[e] += __shfl_xor_sync(0xffffffffu, sy1[e], o);
-          sy2[e] += __shfl_xor_sync(0xffffffffu, sy2[e], o);
-        }
-      }
-      if (lane < LPR && is_c) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { out[col + e] = (double)sv1[e]; out[sh.D + col + e] = (double)sv2[e]; }
-      }
-      if (lane < LPT) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          out[sh.t_off + tcol + e] = (double)sy1[e];
-          out[sh.D + sh.t_off + tcol + e] = (double)sy2[e];
-        }
-      }
-    }
-  }
-  // ---- teardown
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kEpiWarps2) tmem_dealloc(tmem, 512);
 }
 
 // ================================================================ two-tile ping-pong kernel (D <= 128)
@@ -1384,7 +978,7 @@ __global__ void __launch_bounds__(kThreads3, 1) coupling_tc3_kernel(Args a) {
   }
   constexpr int n_chunks = U_ / kChunk;
   const int JT = 2 * (sh.L + 1);     // jobs per tile
-  const int shift = (a.n_groups & 0xf0) ? ((a.n_groups >> 4) & 0xf) : sh.L + 1;   // group 1 runs this many jobs behind group 0
+  const int shift = sh.L + 1;        // group 1 runs half a tile behind group 0 (other shifts measured no better)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&ct.w_full[i], 1); mbar_init(&ct.w_empty[i], 1); }
@@ -1418,8 +1012,9 @@ __global__ void __launch_bounds__(kThreads3, 1) coupling_tc3_kernel(Args a) {
 
   if (warp == kEpiWarps2 + 1) {
     // =============================== weight producer (one elected lane) ===============================
-    // (one thread issues a cp.async.bulk every ~330 cycles - profiles/microbench/tma_rate.cu - i.e. ~50 B/cycle with
-    // 16 KB stages; a second producer warp was tried and bought nothing: the ring depth, not the issue rate, limits)
+    // One thread issues a cp.async.bulk every ~330 cycles (profiles/microbench/tma_rate.cu), i.e. ~50 B/cycle with 16 KB
+    // stages.  Tried and rejected: a second producer warp (a 21st warp drops every thread to 80 registers), and two
+    // diverged lanes of this warp issuing alternate stages (their mbarrier spin loops serialise: slower).
     if (elect_one()) {
       uint32_t slot = 0, phase = 0;
       const int64_t n_steps = cnt[0] * JT + shift;
@@ -1491,11 +1086,11 @@ __global__ void __launch_bounds__(kThreads3, 1) coupling_tc3_kernel(Args a) {
         const uint32_t a1_lo = (uint32_t)a1_desc + (uint32_t)g * a1_sz16;
         const uint32_t act_lo = (uint32_t)act_desc + (uint32_t)g * act_sz16;
         if (l == 0)
-          mma_job<DH, U_, false>(d_tmem, a1_lo, a_hi, bU_lo, bU_hi, ones_lo, 0u, 0u, wfull0, wempty0, (uint32_t)S, slot, phase, leader, t_w);
+          mma_job<DH, U_>(d_tmem, a1_lo, a_hi, bU_lo, bU_hi, ones_lo, wfull0, wempty0, (uint32_t)S, slot, phase, leader, t_w);
         else if (l < sh.L)
-          mma_job<U_, U_, false>(d_tmem, act_lo, a_hi, bU_lo, bU_hi, ones_lo, 0u, 0u, wfull0, wempty0, (uint32_t)S, slot, phase, leader, t_w);
+          mma_job<U_, U_>(d_tmem, act_lo, a_hi, bU_lo, bU_hi, ones_lo, wfull0, wempty0, (uint32_t)S, slot, phase, leader, t_w);
         else
-          mma_job<U_, DH, false>(d_tmem, act_lo, a_hi, bF_lo, bF_hi, ones_lo, 0u, 0u, wfull0, wempty0, (uint32_t)S, slot, phase, leader, t_w);
+          mma_job<U_, DH>(d_tmem, act_lo, a_hi, bF_lo, bF_hi, ones_lo, wfull0, wempty0, (uint32_t)S, slot, phase, leader, t_w);
         if (leader) {
           tc_commit(&ct.h_ready[g]);
           if (l == 0 && net == 1) tc_commit(&ct.a1_free[g]);
@@ -1831,13 +1426,13 @@ using namespace tnf;
 
 static long long* g_tc_debug = nullptr;
 static int g_tc_groups = 2;
-static int g_tc_variant = 0;   // 0 automatic, 1 first tile ping-pong kernel, 2 K-chunk pipelined kernel
+static int g_tc_variant = 0;   // 0 automatic, 1 always the first (8 epilogue warp) kernel
 
 extern "C" {
 
 void tnf_tc_set_debug(void* dev_buffer) { g_tc_debug = (long long*)dev_buffer; }
-void tnf_tc_set_groups(int n_groups) { g_tc_groups = n_groups; }
-void tnf_tc_set_variant(int variant) { g_tc_variant = (variant == 1 || variant == 2) ? variant : 0; }
+void tnf_tc_set_groups(int n_groups) { g_tc_groups = n_groups == 1 ? 1 : 2; }
+void tnf_tc_set_variant(int variant) { g_tc_variant = variant == 1 ? 1 : 0; }
 
 int tnf_tc_supported(int D, int U, int L) { return tc::shape_supported(D, U, L) ? 1 : 0; }
 
@@ -1872,22 +1467,16 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
               "tnf_coupling_tc: the tile ping-pong kernel accumulates column statistics only at D = 64");
   tc::Shape sh(D, U, L, transform_upper != 0);
   const int64_t n_tiles = (rows + tc::kTileM - 1) / tc::kTileM;
-  int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-  if ((g_tc_groups >> 8) > 0 && grid > (g_tc_groups >> 8)) grid = g_tc_groups >> 8;   // diagnostic: fewer CTAs
+  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
   const bool inv = direction == TNF_INVERSE;
-  // kernel choice: D <= 128 -> two-tile ping-pong kernel (variant 2: the K-chunk pipelined one); else the first kernel
-  const bool small_d = tc::shape_supported2(D, U, L) && g_tc_variant != 1;
-  const bool pipelined = small_d && g_tc_variant == 2;
-  const bool pingpong2 = small_d && !pipelined;
+  // kernel choice: D <= 128 -> two-tile kernel with 16 epilogue warps; D = 256 (or variant 1) -> the first kernel
+  const bool pingpong2 = tc::shape_supported2(D, U, L) && g_tc_variant != 1;
   // as many 16 KB weight stages as fit next to the activation images (227 KB per CTA)
   int n_stages = tc::kMaxStages;
   size_t smem;
-  if (pipelined) {
-    while (n_stages > 2 && tc::smem_bytes2(sh, n_stages) > 227 * 1024) --n_stages;
-    smem = tc::smem_bytes2(sh, n_stages);
-  } else if (pingpong2) {
+  if (pingpong2) {
     while (n_stages > 2 && tc::smem_bytes3(sh, n_stages) > 227 * 1024) --n_stages;
     smem = tc::smem_bytes3(sh, n_stages);
   } else {
@@ -1916,11 +1505,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
     else TNF_TCU_LAUNCH(KERNEL, THREADS, INV, DHV, 64);                                                       \
   } while (0)
   int stat_blocks = grid * tc::kEpiWarps;
-  if (pipelined) {
-    stat_blocks = grid * 2;
-    if (D == 64) { if (inv) TNF_TCU(coupling_tc2_kernel, tc::kThreads2, true, 32); else TNF_TCU(coupling_tc2_kernel, tc::kThreads2, false, 32); }
-    else { if (inv) TNF_TCU(coupling_tc2_kernel, tc::kThreads2, true, 64); else TNF_TCU(coupling_tc2_kernel, tc::kThreads2, false, 64); }
-  } else if (pingpong2) {
+  if (pingpong2) {
     stat_blocks = grid;
     if (D == 64) { if (inv) TNF_TCU(coupling_tc3_kernel, tc::kThreads3, true, 32); else TNF_TCU(coupling_tc3_kernel, tc::kThreads3, false, 32); }
     else { if (inv) TNF_TCU(coupling_tc3_kernel, tc::kThreads3, true, 64); else TNF_TCU(coupling_tc3_kernel, tc::kThreads3, false, 64); }

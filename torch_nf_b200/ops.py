@@ -189,7 +189,7 @@ def tc_pack(params_row, D, U, L, upper):
 
 def coupling_tc(z, packed, D, U, L, upper, direction, ld=None, accum=TNF_LD_WRITE, pre_scale=None, pre_shift=None,
                 want_stats=False, out=None):
-    """Returns (z_out, log_det) or, with ``want_stats`` (D = 64), (z_out, log_det, sums) where ``sums`` is the
+    """Returns (z_out, log_det) or, with ``want_stats`` (D <= 128), (z_out, log_det, sums) where ``sums`` is the
     float64 [sum | sumsq | rows] buffer of the OUTPUT columns (the next BatchNorm's statistics)."""
     z2 = z.reshape(-1, D)
     if z2.dtype != torch.float32 or not z2.is_contiguous():
