@@ -158,3 +158,34 @@ def test_round_trip_full_size_property():
     # z0 must be standard normal again
     m = z0.double().mean().item(); s = z0.double().std().item()
     assert abs(m) < 5e-3 and abs(s - 1.0) < 5e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_log_prob_host_pipeline_is_exact(precision):
+    """log_prob of HOST samples runs as overlapped row chunks (copy stream / compute stream); the inverse chain has
+    no cross-sample coupling, so the result must equal the one-shot device path bit for bit."""
+    import torch_nf_b200 as tnf
+    from torch_nf_b200 import config
+    D, N = 64, 128 * 37 + 19
+    nf = de.NormFlow(D, False, "coupling", 2, 2, 64)
+    params = torch.tensor(synthetic_params(chain_spec(nf.bijectors), D, 1, seed=4)).cuda()
+    old_rows, old_chunks = config.host_pipeline_min_rows(), config.host_pipeline_chunks()
+    tnf.set_conditioner_precision(precision)
+    try:
+        with torch.no_grad():
+            z, _ = nf.forward(params, N)                      # sets the BatchNorm statistics
+            lp_dev = nf.log_prob(z, params)
+            z_host = z.cpu()
+            config.set_host_pipeline(min_rows=1 << 30)
+            lp_one = nf.log_prob(z_host, params)              # one-shot host path
+            config.set_host_pipeline(min_rows=256, chunks=5)
+            lp_pipe = nf.log_prob(z_host, params)             # 5 ragged chunks
+            lp_pin = nf.log_prob(z_host.pin_memory(), params)
+    finally:
+        tnf.set_conditioner_precision("fp32")
+        config.set_host_pipeline(min_rows=old_rows, chunks=old_chunks)
+    assert not lp_pipe.is_cuda and lp_pipe.shape == (1, N)
+    assert torch.equal(lp_one, lp_dev.cpu())
+    assert torch.equal(lp_pipe, lp_one)
+    assert torch.equal(lp_pin, lp_one)
+    assert torch.isfinite(lp_pipe).all()

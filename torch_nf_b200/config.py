@@ -7,6 +7,13 @@
     ``"bf16"``: shared-weight coupling layers run on tcgen05 tensor cores with
     bf16 operands, fp32 accumulation, fp32 affine transform and log-det.
     Stated tolerance: max|dz| <= 5e-2, |d log_prob| <= 2e-3 relative.
+
+``host pipeline``
+    ``log_prob`` of HOST-resident samples (no autograd, one shared parameter row)
+    with at least ``host_pipeline_min_rows()`` rows is cut into row chunks whose
+    host->device copies overlap the inverse chain of the previous chunk.  The
+    inverse chain has no cross-sample coupling (BatchNorm uses its stored
+    statistics), so the result is identical to the one-shot path.
 """
 import os
 
@@ -32,3 +39,23 @@ def set_tc_min_rows(n):
 
 def tc_min_rows():
     return _tc_min_rows
+
+
+_host_pipeline_min_rows = int(os.environ.get("TNF_HOST_PIPELINE_MIN_ROWS", str(1 << 17)))
+_host_pipeline_chunks = int(os.environ.get("TNF_HOST_PIPELINE_CHUNKS", "8"))
+
+
+def set_host_pipeline(min_rows=None, chunks=None):
+    global _host_pipeline_min_rows, _host_pipeline_chunks
+    if min_rows is not None:
+        _host_pipeline_min_rows = int(min_rows)
+    if chunks is not None:
+        _host_pipeline_chunks = max(1, int(chunks))
+
+
+def host_pipeline_min_rows():
+    return _host_pipeline_min_rows
+
+
+def host_pipeline_chunks():
+    return _host_pipeline_chunks

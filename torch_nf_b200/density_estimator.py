@@ -402,12 +402,52 @@ class NormFlow(DensityEstimator):
             sum_log_det = sum_log_det + log_det
         return z, sum_log_det
 
+    def _log_prob_host_pipelined(self, z, pd):
+        """``log_prob`` of host samples ``z (1, N, D)`` in row chunks: the host->device copy of chunk i+1 (copy stream)
+        overlaps the inverse chain of chunk i (current stream).  Exact: no bijector couples samples in this direction
+        (BatchNorm.inverse_and_log_det uses its stored statistics, bijectors.py:420-426)."""
+        M, N, D = z.shape
+        n_chunks = config.host_pipeline_chunks()
+        step = -(-N // n_chunks)
+        step = (step + 127) // 128 * 128                      # whole 128-row tiles per chunk
+        dev = torch.device("cuda", torch.cuda.current_device())
+        compute, copy = torch.cuda.current_stream(), _copy_stream()
+        zd = torch.empty((M, N, D), dtype=z.dtype, device=dev)
+        lp = torch.empty((M, N), dtype=z.dtype, device=dev)
+        ready = torch.cuda.Event()
+        ready.record(compute)                                  # zd's block may still be in use by earlier kernels
+        copy.wait_event(ready)
+        bounds = [(lo, min(N, lo + step)) for lo in range(0, N, step)]
+
+        def issue_copy(lo, hi):
+            with torch.cuda.stream(copy):
+                zd[:, lo:hi].copy_(z[:, lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return ev
+
+        ev = issue_copy(*bounds[0])
+        for i, (lo, hi) in enumerate(bounds):
+            compute.wait_event(ev)
+            z0, ld_acc, scal, div = self._inverse_plan(zd[:, lo:hi], pd)
+            lp[:, lo:hi] = ops.base_logprob(z0, ld_acc, scal, div)
+            if i + 1 < len(bounds):                            # queued after chunk i's kernels: a pageable source blocks
+                ev = issue_copy(*bounds[i + 1])                # the host here while the GPU works on chunk i
+        return lp
+
     def log_prob(self, z, params=None):
         """log q(z) = log N(z0; 0, I) - sum_log_det (density_estimator.py:408-416)."""
         if not self.conditioner:
             params = self.params
         home = z.device
-        zd = ops.to_device(z if z.dtype in (torch.float32, torch.float64) else z.float())
+        if z.dtype not in (torch.float32, torch.float64):
+            z = z.float()
+        needs_grad = torch.is_grad_enabled() and (params.requires_grad or z.requires_grad)
+        if (not z.is_cuda and not needs_grad and z.dim() == 3 and z.shape[0] == 1 and params.shape[0] == 1
+                and z.shape[1] >= config.host_pipeline_min_rows() and config.host_pipeline_chunks() > 1):
+            ops.require_cuda()
+            return _to(self._log_prob_host_pipelined(z.detach().contiguous(), ops.to_device(params.detach(), z.dtype)), home)
+        zd = ops.to_device(z)
         pd = ops.to_device(params, zd.dtype)
         if torch.is_grad_enabled() and (pd.requires_grad or zd.requires_grad):
             z0, sld = self._inverse_autograd(zd, pd)
@@ -416,6 +456,16 @@ class NormFlow(DensityEstimator):
             z0, ld_acc, scal, div = self._inverse_plan(zd.detach().contiguous(), pd.detach())
             lp = ops.base_logprob(z0, ld_acc, scal, div)
         return _to(lp, home)
+
+
+_copy_streams = {}
+
+
+def _copy_stream():
+    dev = torch.cuda.current_device()
+    if dev not in _copy_streams:
+        _copy_streams[dev] = torch.cuda.Stream(device=dev)
+    return _copy_streams[dev]
 
 
 class _BaseLogProbFn(torch.autograd.Function):
