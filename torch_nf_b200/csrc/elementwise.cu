@@ -570,6 +570,29 @@ __global__ void base_sample_kernel(float* __restrict__ z, int64_t n_el, uint64_t
   }
 }
 
+// D = 4*G with G a power of two <= 32: the G threads that draw one row also reduce its -1/2 sum z^2, so the base
+// log-density costs no second pass over z.  Same Philox counters as base_sample_kernel -> identical samples.
+template <int G>
+__global__ void base_sample_logq_kernel(float* __restrict__ z, double* __restrict__ log_q, int64_t rows, uint64_t seed,
+                                        uint64_t offset) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;    // multiple of 32, so row groups never straddle iterations
+  const int64_t nq = rows * G;
+  const int64_t nq_pad = (nq + stride - 1) / stride * stride;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq_pad; q += stride) {
+    double s = 0.0;
+    if (q < nq) {
+      uint64_t cidx = (uint64_t)q + offset;
+      uint4 ctr = make_uint4((uint32_t)cidx, (uint32_t)(cidx >> 32), 0u, 0u);
+      uint4 rnd = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      float2 p0 = box_muller(rnd.x, rnd.y), p1 = box_muller(rnd.z, rnd.w);
+      reinterpret_cast<float4*>(z)[q] = make_float4(p0.x, p0.y, p1.x, p1.y);
+      s = -((double)p0.x * p0.x + (double)p0.y * p0.y + (double)p1.x * p1.x + (double)p1.y * p1.y);
+    }
+    s = group_sum<double, G>(s);
+    if (q < nq && (threadIdx.x % G) == 0) log_q[q / G] = 0.5 * s - (double)(4 * G) * 0.91893853320467274178;
+  }
+}
+
 template <int G>
 __global__ void base_logq_kernel(const float* __restrict__ omega, double* __restrict__ log_q, int64_t rows, int D) {
   int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -876,6 +899,16 @@ int tnf_base_sample(float* z, double* log_q, int64_t rows, int D, uint64_t seed,
   if (rows == 0) return 0;
   TNF_REQUIRE(z && log_q, TNF_ERR_ARG, "tnf_base_sample: null pointer");
   int64_t n_el = rows * D;
+#define TNF_SAMPLE_FUSED(GV)                                                                                         \
+  case 4 * GV:                                                                                                       \
+    base_sample_logq_kernel<GV><<<grid_for(rows * GV, 256 * 2), 256, 0, (cudaStream_t)stream>>>(z, log_q, rows, seed, \
+                                                                                                offset);             \
+    return check_launch("tnf_base_sample");
+  switch (D) {   // row width a power of two <= 128: samples and their log-density in one pass
+    TNF_SAMPLE_FUSED(1) TNF_SAMPLE_FUSED(2) TNF_SAMPLE_FUSED(4) TNF_SAMPLE_FUSED(8) TNF_SAMPLE_FUSED(16) TNF_SAMPLE_FUSED(32)
+    default: break;
+  }
+#undef TNF_SAMPLE_FUSED
   base_sample_kernel<<<grid_for((n_el + 3) / 4, 256 * 2), 256, 0, (cudaStream_t)stream>>>(z, n_el, seed, offset);
   int rc = check_launch("tnf_base_sample");
   if (rc) return rc;
