@@ -109,8 +109,8 @@ int tnf_tc_supported(int D, int U, int L);
 void tnf_tc_set_debug(void* dev_buffer);
 /* diagnostic: 1 = only one epilogue group works (no tile ping-pong), 2 = default. */
 void tnf_tc_set_groups(int n_groups);
-/* diagnostic: kernel choice of tnf_coupling_tc: 0 = automatic (16-epilogue-warp two-tile kernel for
- * D <= 128, the first 8-epilogue-warp kernel for D = 256), 1 = always the first kernel. */
+/* diagnostic: kernel choice of tnf_coupling_tc: 0 = automatic (two-tile kernel for D <= 128, single-tile
+ * pipelined kernel for D = 256), 1 = always the first (8 epilogue warp) kernel. */
 void tnf_tc_set_variant(int variant);
 int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N, int a_in_tmem,
                          tnf_stream_t stream);

@@ -34,7 +34,7 @@ ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)
 torch.cuda.synchronize()
 _lib.lib().tnf_tc_set_debug(None)
 raw = dbg.cpu().numpy()
-print("MMA warp (CTA 0): cycles waiting on epilogue %d, on weights %d, total %d" % (raw[2040], raw[2041], raw[2042]))
+print("MMA warp (CTA 0): cycles waiting on epilogue %d, on weights %d, total %d (first layers %d, hidden layers %d, final layers %d)" % (raw[2040], raw[2041], raw[2042], raw[2043], raw[2044], raw[2045]))
 d = raw[:2048].reshape(2, 512, 2)  # group g at int64 offset 1024*g
 names = {100: "tile start", 101: "A1 published", 600: "tile end", 601: "y computed", 602: "next A1 published", 610: "A1 image written", 611: "A1 proxy fence done",
          700: "step: chunk landed", 701: "step: tanh+stores issued", 702: "step: chunk published", 703: "step: begin"}

@@ -16,9 +16,9 @@
 // through a ring of 16 KB stages by one producer warp (cp.async.bulk + mbarrier
 // complete_tx).
 //
-// Two kernels share this file:
+// Three kernels share this file (tnf_coupling_tc picks by shape):
 //
-// coupling_tc3_kernel (D <= 128, the default): two tiles in flight per CTA.  16 epilogue
+// coupling_tc3_kernel (D <= 128, the C3 path): two tiles in flight per CTA.  16 epilogue
 // warps in two groups of 8 (per group two warps per TMEM lane quadrant, each taking the
 // accumulator chunks of one parity); each group owns a tile, 256 TMEM columns and its own
 // A images.  The MMA warp serves the groups alternately in a static order, so while one
@@ -29,10 +29,13 @@
 // image and write the pass-through half.  Warp roles (640 threads): 0-15 epilogue,
 // 16 MMA issuer, 17 weight producer, 18-19 I/O.
 //
-// coupling_tc_kernel (D = 256, or diagnostic variant 1): the first design - 8 epilogue
-// warps in two groups of 4 (thread = one sample row, all I/O in the epilogue threads,
-// biases added in the epilogue), warp 8 MMA issuer, warp 9 weight producer (320 threads).
-// Kept because the two-tile kernel's images do not fit shared memory at D = 256.
+// coupling_tc2_kernel (D = 256): the images of two tiles do not fit shared memory, so one
+// tile is in flight, with two 256-column accumulators: layer l+1's MMAs trail the tanh
+// epilogue of layer l chunk by chunk (per-chunk mbarriers).  Same building blocks.
+//
+// coupling_tc_kernel (diagnostic variant 1): the first design - 8 epilogue warps in two
+// groups of 4 (thread = one sample row, all I/O and the bias adds in the epilogue
+// threads), generic MMA issue loop, 320 threads.  Kept as an independent cross-check.
 //
 // Reference semantics: torch_nf/bijectors.py:145-242 (RealNVP).
 #include <cuda_bf16.h>
@@ -907,6 +910,375 @@ __device__ __forceinline__ void mma_job(uint32_t d_tmem, uint32_t a_lo, uint32_t
   }
 }
 
+// ================================================================ single-tile pipelined kernel (D = 256)
+// At D = 256 two A1 images (32 KB each) and two activation images do not fit next to a weight ring, so the two-tile
+// kernel is out.  Here ONE tile is in flight per CTA and all 16 epilogue warps work on it (warp w: TMEM lane quadrant
+// w%4, accumulator chunks c = w/4 mod 4, final-layer columns [32*(w/4), +32)).  The 512 TMEM columns hold TWO
+// 256-column accumulators, so the MMA warp runs layer l+1 into one while the epilogue still drains layer l from the
+// other: it issues the two K=16 MMAs of K-chunk c as soon as the four warps owning chunk c have published those 32
+// activation columns (act_ready[c]) - the tensor pipe trails the MUFU-bound tanh epilogue by one chunk.  The A1 image
+// is double buffered (tile parity) and written, with the pass-through half, by two I/O warps using coalesced
+// 16-byte accesses; the t-net output is parked in z_out (L2) until the s-net is done, as in the first kernel.
+constexpr int kThreads2 = (kEpiWarps2 + 4) * 32;
+constexpr int kMaxJobs = 6;   // L + 1 <= 6
+
+struct __align__(16) Ctrl2 {
+  uint64_t w_full[kMaxStages];
+  uint64_t w_empty[kMaxStages];
+  uint64_t a1_ready[2];     // 2 I/O warps: A1 image of a tile written
+  uint64_t a1_free[2];      // tcgen05.commit: both layer-0 jobs of the tile have read the A1 image
+  uint64_t act_ready[8];    // 4 epilogue warps: activation chunk c (32 K-columns, all 128 rows) written
+  uint64_t h_ready[2][kMaxJobs];   // tcgen05.commit per (net, layer): accumulator complete
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+// dynamic shared memory:
+//   [ring: n_stages x 16 KB][A1 x2][Act][ones 4 KB][Ctrl2][pre_scale D][pre_shift D][ld partial 3 x 128]
+__host__ __device__ inline size_t smem_bytes2(const Shape& sh, int n_stages) {
+  return (size_t)n_stages * kStageBytes + 2 * sh.a1_bytes() + sh.act_bytes() + kOnesBytes + sizeof(Ctrl2) +
+         (size_t)(2 * sh.D + 3 * kTileM) * sizeof(float);
+}
+
+// mma_job whose K chunks wait for the epilogue of the previous layer chunk by chunk (act_ready[c], parity e_par).
+// The bias MMA is issued after the first activation chunk is published: that also tells that the epilogue warps have
+// drained whatever the destination accumulator held.
+template <int K, int N>
+__device__ __forceinline__ void mma_job_trailing(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo_ring,
+                                                 uint32_t b_hi, uint32_t ones_lo, uint32_t act_bar0, uint32_t e_par,
+                                                 uint32_t wfull0, uint32_t wempty0, uint32_t S, uint32_t& slot,
+                                                 uint32_t& phase, bool leader) {
+  constexpr int KS = (kStageElems / N) < K ? (kStageElems / N) : K;   // K rows per weight stage
+  constexpr int CPS = KS / kChunk;                                     // chunks per stage
+  constexpr uint32_t kStage16 = kStageBytes >> 4;
+  const uint32_t idesc = make_idesc(N);
+#pragma unroll
+  for (int c = 0; c < K / kChunk; ++c) {
+    mbar_wait_addr(act_bar0 + 8u * c, e_par);
+    if (c == 0) {
+      mbar_wait_addr(wfull0 + slot * 8u, phase);
+      tc_fence_after();
+      if (leader) {
+        umma_ss2(d_tmem, ones_lo, a_hi, b_lo_ring + slot * kStage16, b_hi, idesc, 0u);
+        tc_commit_addr(wempty0 + slot * 8u);
+      }
+      if (++slot == S) { slot = 0; phase ^= 1; }
+    }
+    if (c % CPS == 0) mbar_wait_addr(wfull0 + slot * 8u, phase);
+    tc_fence_after();
+    if (leader) {
+      const uint32_t b_lo = b_lo_ring + slot * kStage16 + (uint32_t)((c % CPS) * 4 * N);
+      umma_ss2(d_tmem, a_lo + 512u * c, a_hi, b_lo, b_hi, idesc, 1u);
+      umma_ss2(d_tmem, a_lo + 512u * c + 256u, a_hi, b_lo + 2u * N, b_hi, idesc, 1u);
+      if (c % CPS == CPS - 1) tc_commit_addr(wempty0 + slot * 8u);
+    }
+    if (c % CPS == CPS - 1) {
+      if (++slot == S) { slot = 0; phase ^= 1; }
+    }
+  }
+}
+
+template <bool kInverse, int DH, int U_>   // DH = D/2 = 128; U_ = hidden units
+__global__ void __launch_bounds__(kThreads2, 1) coupling_tc2_kernel(Args a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const Shape sh(a.D, a.U, a.L, a.upper);
+  const int S = a.n_stages;
+  unsigned char* ring = smem_raw;
+  unsigned char* sA1 = ring + (size_t)S * kStageBytes;              // 2 images (tile parity)
+  unsigned char* sAct = sA1 + 2 * sh.a1_bytes();                    // 1 image
+  unsigned char* sOnes = sAct + sh.act_bytes();                     // constant A image for the bias MMA
+  Ctrl2& ct = *reinterpret_cast<Ctrl2*>(sOnes + kOnesBytes);
+  float* s_pscale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl2));
+  float* s_pshift = s_pscale + sh.D;
+  float* s_ldp = s_pshift + sh.D;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
+  const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles blockIdx.x + i*grid
+  constexpr int n_chunks = U_ / kChunk;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&ct.w_full[i], 1); mbar_init(&ct.w_empty[i], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ct.a1_ready[b], 2);
+      mbar_init(&ct.a1_free[b], 1);
+    }
+    for (int c = 0; c < 8; ++c) mbar_init(&ct.act_ready[c], 4);
+    for (int n = 0; n < 2; ++n)
+      for (int l = 0; l < kMaxJobs; ++l) mbar_init(&ct.h_ready[n][l], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kEpiWarps2) tmem_alloc(&ct.tmem_base, 512);
+  {
+    for (int i = threadIdx.x; i < kOnesBytes / 4; i += blockDim.x)   // row r: K columns 0 and 1 are 1.0 (bf16 0x3f80)
+      reinterpret_cast<uint32_t*>(sOnes)[i] = (i < kTileM * 4 && (i & 3) == 0) ? 0x3f803f80u : 0u;
+    fence_async_smem();
+    for (int i = threadIdx.x; i < sh.D; i += blockDim.x) {
+      s_pscale[i] = a.pre_scale ? a.pre_scale[i] : 1.0f;
+      s_pshift[i] = a.pre_shift ? a.pre_shift[i] : 0.0f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ct.tmem_base;
+
+  if (warp == kEpiWarps2 + 1) {
+    // =============================== weight producer (one elected lane) ===============================
+    // 16 KB stages whatever grouping tnf_tc_pack used: a packed layer is a sequence of 8-row K groups, so any
+    // multiple of 8 K rows is a valid stage
+    if (elect_one()) {
+      uint32_t slot = 0, phase = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        for (int net = 0; net < 2; ++net) {
+          size_t off = 0;
+          for (int l = 0; l <= sh.L; ++l) {
+            const int K = sh.K_of(l), J = sh.J_of(l);
+            const int ks = (kStageElems / J) < K ? (kStageElems / J) : K;
+            const uint32_t bytes = (uint32_t)(ks * J * 2);
+            const unsigned char* nsrc = a.packed + off + (size_t)net * K * J * 2;
+            {   // the job's bias operand image travels as a stage of its own, ahead of the weights
+              mbar_wait(&ct.w_empty[slot], phase ^ 1);
+              mbar_arrive_expect_tx(&ct.w_full[slot], (uint32_t)J * 32u);
+              bulk_g2s(ring + (size_t)slot * kStageBytes, a.packed + sh.bias_img_off(l, net), (uint32_t)J * 32u, &ct.w_full[slot]);
+              if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+            }
+            for (int st = 0; st < K / ks; ++st) {
+              mbar_wait(&ct.w_empty[slot], phase ^ 1);
+              mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
+              bulk_g2s(ring + (size_t)slot * kStageBytes, nsrc + (size_t)st * bytes, bytes, &ct.w_full[slot]);
+              if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+            }
+            off += (size_t)2 * K * J * 2;
+          }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps2) {
+    // =============================== MMA issuer (warp-uniform, elected lane issues) ===============================
+    const bool leader = elect_one();
+    uint32_t slot = 0, phase = 0, e_par = 0;
+    int cur = 0;   // accumulator buffer of the most recent hidden-layer job
+    const uint32_t a1_sz16 = (uint32_t)sh.a1_bytes() >> 4;
+    const uint32_t act_bar0 = smem_u32(&ct.act_ready[0]);
+    const uint32_t wfull0 = smem_u32(&ct.w_full[0]), wempty0 = smem_u32(&ct.w_empty[0]);
+    const uint32_t ring16 = smem_u32(ring) >> 4;
+    const uint64_t a1_desc = make_desc(smem_u32(sA1), kTileM), act_desc = make_desc(smem_u32(sAct), kTileM);
+    const uint32_t a_hi = (uint32_t)(a1_desc >> 32);
+    const uint64_t bU_desc = make_desc(0u, U_), bF_desc = make_desc(0u, DH);
+    const uint32_t bU_lo = (uint32_t)bU_desc + ring16, bU_hi = (uint32_t)(bU_desc >> 32);
+    const uint32_t bF_lo = (uint32_t)bF_desc + ring16, bF_hi = (uint32_t)(bF_desc >> 32);
+    const uint32_t act_lo = (uint32_t)act_desc;
+    const uint32_t ones_lo = (uint32_t)make_desc(smem_u32(sOnes), kTileM);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const uint32_t ab = (uint32_t)(it & 1);
+      const uint32_t a1_lo = (uint32_t)a1_desc + ab * a1_sz16;
+      mbar_wait(&ct.a1_ready[ab], (uint32_t)((it >> 1) & 1));
+#pragma unroll 1
+      for (int net = 0; net < 2; ++net) {
+        // layer 0: A1 image, accumulator = the buffer the previous epilogue phase has just drained
+        mma_job<DH, U_>(tmem + (uint32_t)cur * 256u, a1_lo, a_hi, bU_lo, bU_hi, ones_lo, wfull0, wempty0, (uint32_t)S, slot,
+                        phase, leader);
+        if (leader) {
+          tc_commit(&ct.h_ready[net][0]);
+          if (net == 1) tc_commit(&ct.a1_free[ab]);
+        }
+        // hidden layers 1..L-1, each trailing the epilogue of the layer before it chunk by chunk
+#pragma unroll 1
+        for (int l = 1; l < sh.L; ++l) {
+          cur ^= 1;
+          mma_job_trailing<U_, U_>(tmem + (uint32_t)cur * 256u, act_lo, a_hi, bU_lo, bU_hi, ones_lo, act_bar0, e_par, wfull0,
+                                   wempty0, (uint32_t)S, slot, phase, leader);
+          e_par ^= 1;
+          if (leader) tc_commit(&ct.h_ready[net][l]);
+        }
+        // final layer -> the other buffer's first DH columns
+        mma_job_trailing<U_, DH>(tmem + (uint32_t)(cur ^ 1) * 256u, act_lo, a_hi, bF_lo, bF_hi, ones_lo, act_bar0, e_par,
+                                 wfull0, wempty0, (uint32_t)S, slot, phase, leader);
+        e_par ^= 1;
+        if (leader) tc_commit(&ct.h_ready[net][sh.L]);
+        __syncwarp();
+      }
+    }
+  } else if (warp < kEpiWarps2) {
+    // =============================== epilogue warps ===============================
+    const int q = warp & 3, par = warp >> 2;  // par in 0..3
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int r_tile = q * 32 + lane;
+    constexpr int W = DH / 4;                 // final-layer columns per thread (32)
+    const float kLog2e = 1.4426950408889634f;
+    int cur = 0;
+
+    // accumulator chunk c (bias already added by the bias MMA) -> MUFU.TANH -> bf16 -> A image, then publish the
+    // chunk: generic-proxy writes -> async proxy, one arrival per warp
+    auto epi_step = [&](uint32_t hcol, int c) {
+      uint32_t x[32];
+      tmem_ld32(hcol + (uint32_t)(c * kChunk), x);
+      tc_wait_ld();
+      unsigned char* dst = sAct + img_off(r_tile, c * kChunk, kTileM);
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[j + e] = __float_as_uint(tanh_fast(__uint_as_float(x[j + e])));
+        *reinterpret_cast<uint4*>(dst + (j >> 3) * (kTileM * 16)) =
+            make_uint4(pack_bf16(__uint_as_float(x[j]), __uint_as_float(x[j + 1])),
+                       pack_bf16(__uint_as_float(x[j + 2]), __uint_as_float(x[j + 3])),
+                       pack_bf16(__uint_as_float(x[j + 4]), __uint_as_float(x[j + 5])),
+                       pack_bf16(__uint_as_float(x[j + 6]), __uint_as_float(x[j + 7])));
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ct.act_ready[c]);
+    };
+    auto quad_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory"); };
+
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = it * (int64_t)gridDim.x + blockIdx.x;
+      const int64_t row = tile * kTileM + r_tile;
+      const bool valid = row < a.rows;
+      const uint32_t h_par = (uint32_t)(it & 1);
+      const float* zrow = a.z_in + row * sh.D + sh.t_off + par * W;
+      float* orow = a.z_out + row * sh.D + sh.t_off + par * W;
+      float ld_old = 0.f;
+      if (valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(zrow));   // 128 B = this thread's piece of the transformed half
+#pragma unroll
+      for (int net = 0; net < 2; ++net) {
+#pragma unroll 1
+        for (int l = 0; l < sh.L; ++l) {
+          if (l > 0) cur ^= 1;
+          const uint32_t hcol = tmem + lane_addr + (uint32_t)cur * 256u;
+          mbar_wait(&ct.h_ready[net][l], h_par);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = par; c < n_chunks; c += 4) epi_step(hcol, c);
+        }
+        // ---- final layer of this net: W columns per thread, in pieces of 16
+        const uint32_t fcol = tmem + lane_addr + (uint32_t)(cur ^ 1) * 256u + (uint32_t)(par * W);
+        if (net == 0 && par == 0 && valid && a.accum != TNF_LD_WRITE) ld_old = a.log_det[row];
+        float zin_s[16], tt_s[16];
+        auto load_piece = [&](int j0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 z4 = valid ? __ldg(reinterpret_cast<const float4*>(zrow + j0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 t4 = valid ? *reinterpret_cast<const float4*>(orow + j0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            zin_s[j] = z4.x; zin_s[j + 1] = z4.y; zin_s[j + 2] = z4.z; zin_s[j + 3] = z4.w;
+            tt_s[j] = t4.x; tt_s[j + 1] = t4.y; tt_s[j + 2] = t4.z; tt_s[j + 3] = t4.w;
+          }
+        };
+        if (net == 1) load_piece(0);   // in flight while the final-layer MMAs of the s-net run
+        mbar_wait(&ct.h_ready[net][sh.L], h_par);
+        tc_fence_after();
+        if (net == 0) {
+          // t (bias included) is parked in z_out until the s-net is done (it stays in L2; the same thread reads it back)
+#pragma unroll 1
+          for (int j0 = 0; j0 < W; j0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(fcol + (uint32_t)j0, o);
+            tc_wait_ld();
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(orow + j0 + j) = make_float4(__uint_as_float(o[j]), __uint_as_float(o[j + 1]),
+                                                                        __uint_as_float(o[j + 2]), __uint_as_float(o[j + 3]));
+            }
+          }
+          tc_fence_before();
+          quad_sync();   // every column of t is read out before chunk 0 of the s-net lets MMAs overwrite it
+        } else {
+          float ld_sum = 0.f;
+#pragma unroll 1
+          for (int j0 = 0; j0 < W; j0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(fcol + (uint32_t)j0, o);
+            tc_wait_ld();
+            float y[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = sh.t_off + par * W + j0 + j;
+              const float zz = fmaf(zin_s[j], s_pscale[col], s_pshift[col]);
+              const float sv = __uint_as_float(o[j]);
+              ld_sum += sv;
+              y[j] = kInverse ? (zz - tt_s[j]) * exp2_fast(-sv * kLog2e) : fmaf(zz, exp2_fast(sv * kLog2e), tt_s[j]);
+            }
+            if (j0 + 16 < W) load_piece(j0 + 16);
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(orow + j0 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            }
+          }
+          tc_fence_before();
+          if (par > 0) s_ldp[(par - 1) * kTileM + r_tile] = ld_sum;
+          quad_sync();   // also: every column of s is read out before the next tile's MMAs may overwrite it
+          if (par == 0 && valid) {
+            const float tot = ld_sum + s_ldp[r_tile] + s_ldp[kTileM + r_tile] + s_ldp[2 * kTileM + r_tile];
+            float* op = a.log_det + row;
+            if (a.accum == TNF_LD_WRITE) *op = tot;
+            else if (a.accum == TNF_LD_ADD) *op = ld_old + tot;
+            else *op = ld_old - tot;
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== I/O warps: conditioning half, coalesced ===============================
+    const int w2 = warp - (kEpiWarps2 + 2);
+    const int row0 = w2 * (kTileM / 2);
+    constexpr int LPR = DH / 4 > 32 ? 32 : DH / 4;   // lanes per row piece (16 B each)
+    constexpr int RPI = 32 / LPR;                    // rows per warp instruction
+    constexpr int PPR = (DH / 4) / LPR;              // 128-float pieces per row
+    constexpr int NI = (kTileM / 2) / RPI * PPR;
+    constexpr int kBatch = 16;                       // 16-byte loads in flight per lane (8 KB per warp)
+    const int rsub = lane / LPR;
+    auto load_tile = [&](int64_t it) {
+      const int b = (int)(it & 1);
+      const int64_t tile = it * (int64_t)gridDim.x + blockIdx.x;
+      unsigned char* a1 = sA1 + (size_t)b * sh.a1_bytes();
+#pragma unroll 1
+      for (int n0 = 0; n0 < NI; n0 += kBatch) {
+        float4 v[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int n = n0 + u;
+          const int r = row0 + (n / PPR) * RPI + rsub;
+          const int hc = 4 * (lane % LPR) + (n % PPR) * 4 * LPR;
+          const int64_t grow = tile * kTileM + r;
+          v[u] = grow < a.rows ? __ldg(reinterpret_cast<const float4*>(a.z_in + grow * sh.D + sh.c_off + hc))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int n = n0 + u;
+          const int r = row0 + (n / PPR) * RPI + rsub;
+          const int hc = 4 * (lane % LPR) + (n % PPR) * 4 * LPR;
+          const int col = sh.c_off + hc;
+          const int64_t grow = tile * kTileM + r;
+          const float4 ps = *reinterpret_cast<const float4*>(s_pscale + col);
+          const float4 pb = *reinterpret_cast<const float4*>(s_pshift + col);
+          float4 x;
+          x.x = fmaf(v[u].x, ps.x, pb.x); x.y = fmaf(v[u].y, ps.y, pb.y);
+          x.z = fmaf(v[u].z, ps.z, pb.z); x.w = fmaf(v[u].w, ps.w, pb.w);
+          *reinterpret_cast<uint2*>(a1 + img_off(r, hc, kTileM)) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+          if (grow < a.rows) *reinterpret_cast<float4*>(a.z_out + grow * sh.D + col) = x;
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ct.a1_ready[b]);
+    };
+    if (my_tiles > 0) load_tile(0);
+    for (int64_t it = 0; it + 1 < my_tiles; ++it) {
+      const int64_t t1 = it + 1;
+      if (t1 >= 2) mbar_wait(&ct.a1_free[t1 & 1], (uint32_t)(((t1 >> 1) - 1) & 1));   // layer-0 jobs of tile t1-2 done
+      load_tile(t1);
+    }
+  }
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps2) tmem_dealloc(tmem, 512);
+}
+
 // ================================================================ two-tile ping-pong kernel (D <= 128)
 // Two tiles in flight per CTA.  Epilogue group g (8 warps: TMEM lane quadrant w%4, accumulator chunks of parity
 // (w/4)%2) owns tile (2k+g)*grid + cta, the 256 TMEM columns [256g, 256g+256) and its own A1 / activation images.
@@ -1053,8 +1425,8 @@ __global__ void __launch_bounds__(kThreads3, 1) coupling_tc3_kernel(Args a) {
     const bool leader = elect_one();
     uint32_t slot = 0, phase = 0, e_par = 0, a1_par = 0;   // parities: bit g
     const long long t_all = a.dbg != nullptr ? clock64() : 0;
-    long long t_dep = 0, t_wsum = 0;
-    long long* t_w = a.dbg != nullptr ? &t_wsum : nullptr;
+    long long t_dep = 0, t_w3[3] = {0, 0, 0};
+    const bool diag = a.dbg != nullptr;
     const uint32_t wfull0 = smem_u32(&ct.w_full[0]), wempty0 = smem_u32(&ct.w_empty[0]);
     const uint32_t ring16 = smem_u32(ring) >> 4;
     const uint64_t a1_desc = make_desc(smem_u32(sA1), kTileM), act_desc = make_desc(smem_u32(sAct), kTileM);
@@ -1086,11 +1458,11 @@ __global__ void __launch_bounds__(kThreads3, 1) coupling_tc3_kernel(Args a) {
         const uint32_t a1_lo = (uint32_t)a1_desc + (uint32_t)g * a1_sz16;
         const uint32_t act_lo = (uint32_t)act_desc + (uint32_t)g * act_sz16;
         if (l == 0)
-          mma_job<DH, U_>(d_tmem, a1_lo, a_hi, bU_lo, bU_hi, ones_lo, wfull0, wempty0, (uint32_t)S, slot, phase, leader, t_w);
+          mma_job<DH, U_>(d_tmem, a1_lo, a_hi, bU_lo, bU_hi, ones_lo, wfull0, wempty0, (uint32_t)S, slot, phase, leader, diag ? &t_w3[0] : nullptr);
         else if (l < sh.L)
-          mma_job<U_, U_>(d_tmem, act_lo, a_hi, bU_lo, bU_hi, ones_lo, wfull0, wempty0, (uint32_t)S, slot, phase, leader, t_w);
+          mma_job<U_, U_>(d_tmem, act_lo, a_hi, bU_lo, bU_hi, ones_lo, wfull0, wempty0, (uint32_t)S, slot, phase, leader, diag ? &t_w3[1] : nullptr);
         else
-          mma_job<U_, DH>(d_tmem, act_lo, a_hi, bF_lo, bF_hi, ones_lo, wfull0, wempty0, (uint32_t)S, slot, phase, leader, t_w);
+          mma_job<U_, DH>(d_tmem, act_lo, a_hi, bF_lo, bF_hi, ones_lo, wfull0, wempty0, (uint32_t)S, slot, phase, leader, diag ? &t_w3[2] : nullptr);
         if (leader) {
           tc_commit(&ct.h_ready[g]);
           if (l == 0 && net == 1) tc_commit(&ct.a1_free[g]);
@@ -1099,7 +1471,8 @@ __global__ void __launch_bounds__(kThreads3, 1) coupling_tc3_kernel(Args a) {
       }
     }
     if (a.dbg != nullptr && blockIdx.x == 0 && leader) {
-      a.dbg[2040] = t_dep; a.dbg[2041] = t_wsum; a.dbg[2042] = clock64() - t_all;
+      a.dbg[2040] = t_dep; a.dbg[2041] = t_w3[0] + t_w3[1] + t_w3[2]; a.dbg[2042] = clock64() - t_all;
+      a.dbg[2043] = t_w3[0]; a.dbg[2044] = t_w3[1]; a.dbg[2045] = t_w3[2];
     }
   } else if (warp < kEpiWarps2) {
     // =============================== epilogue warps ===============================
@@ -1471,14 +1844,18 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
   const bool inv = direction == TNF_INVERSE;
-  // kernel choice: D <= 128 -> two-tile kernel with 16 epilogue warps; D = 256 (or variant 1) -> the first kernel
+  // kernel choice: D <= 128 -> two-tile kernel; D = 256 -> single-tile pipelined kernel; variant 1 -> the first kernel
   const bool pingpong2 = tc::shape_supported2(D, U, L) && g_tc_variant != 1;
+  const bool pipelined = D == 256 && g_tc_variant != 1;
   // as many 16 KB weight stages as fit next to the activation images (227 KB per CTA)
   int n_stages = tc::kMaxStages;
   size_t smem;
   if (pingpong2) {
     while (n_stages > 2 && tc::smem_bytes3(sh, n_stages) > 227 * 1024) --n_stages;
     smem = tc::smem_bytes3(sh, n_stages);
+  } else if (pipelined) {
+    while (n_stages > 2 && tc::smem_bytes2(sh, n_stages) > 227 * 1024) --n_stages;
+    smem = tc::smem_bytes2(sh, n_stages);
   } else {
     while (n_stages > 2 && tc::smem_bytes(sh, n_stages) > 227 * 1024) --n_stages;
     smem = tc::smem_bytes(sh, n_stages);
@@ -1509,6 +1886,8 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
     stat_blocks = grid;
     if (D == 64) { if (inv) TNF_TCU(coupling_tc3_kernel, tc::kThreads3, true, 32); else TNF_TCU(coupling_tc3_kernel, tc::kThreads3, false, 32); }
     else { if (inv) TNF_TCU(coupling_tc3_kernel, tc::kThreads3, true, 64); else TNF_TCU(coupling_tc3_kernel, tc::kThreads3, false, 64); }
+  } else if (pipelined) {
+    if (inv) TNF_TCU(coupling_tc2_kernel, tc::kThreads2, true, 128); else TNF_TCU(coupling_tc2_kernel, tc::kThreads2, false, 128);
   } else if (D == 64) { if (inv) TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, true, 32); else TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, false, 32); }
   else if (D == 128) { if (inv) TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, true, 64); else TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, false, 64); }
   else { if (inv) TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, true, 128); else TNF_TC_LAUNCH(coupling_tc_kernel, tc::kThreads, false, 128); }
