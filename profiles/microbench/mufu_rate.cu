@@ -9,9 +9,17 @@ __device__ __forceinline__ float op(float x) {
   if (OP == 0) asm volatile("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   else if (OP == 1) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   else if (OP == 2) asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  else {  // packed bf16x2 tanh
+  else if (OP == 3) {  // packed bf16x2 tanh
     unsigned u = __float_as_uint(x), r;
     asm volatile("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(u));
+    y = __uint_as_float(r);
+  } else if (OP == 4) {  // packed f16x2 tanh
+    unsigned u = __float_as_uint(x), r;
+    asm volatile("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(u));
+    y = __uint_as_float(r);
+  } else {  // packed f16x2 ex2
+    unsigned u = __float_as_uint(x), r;
+    asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(u));
     y = __uint_as_float(r);
   }
   return y;
@@ -58,5 +66,7 @@ int main() {
   run<1>("ex2.approx.ftz.f32");
   run<2>("rcp.approx.ftz.f32");
   run<3>("tanh.approx.bf16x2");
+  run<4>("tanh.approx.f16x2");
+  run<5>("ex2.approx.f16x2");
   return 0;
 }
