@@ -67,15 +67,16 @@ def test_coupling_tc_vs_oracle(D, U, L, N, upper):
 
 
 @pytest.mark.parametrize("D,U,L,N", [(64, 256, 2, 1000), (64, 128, 2, 257), (128, 256, 2, 384), (64, 64, 3, 129)])
-def test_coupling_tc_first_kernel_variant(D, U, L, N):
-    """Diagnostic variant 1 routes D <= 128 through the first (8 epilogue warp) kernel: same results as the default
-    two-tile kernel up to bf16 rounding of the bias (the default adds biases through a bf16 hi/lo bias MMA)."""
+def test_coupling_tc_kernel_variants(D, U, L, N):
+    """Diagnostic variants: 1 routes D <= 128 through the first (8 epilogue warp) kernel, 2 through the two-tile kernel
+    without CTA pairs; the default is the two-tile kernel on CTA pairs (tcgen05 cta_group::2).  Variants 0 and 2 do
+    the same arithmetic and must agree bit for bit; variant 1 differs by the bf16 hi/lo rounding of the bias MMA."""
     params = T(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=3))
     z_in = T(synthetic_noise(1, N, D, seed=8).astype(np.float32)).cuda()
     packed = ops.tc_pack(params.cuda()[0], D, U, L, True)
     out = {}
     try:
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             _lib.lib().tnf_tc_set_variant(variant)
             for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
                 z, ld = ops.coupling_tc(z_in, packed, D, U, L, True, direction)
@@ -86,6 +87,8 @@ def test_coupling_tc_first_kernel_variant(D, U, L, N):
     for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
         z0, l0 = out[(0, direction)]
         z1, l1 = out[(1, direction)]
+        z2, l2 = out[(2, direction)]
+        assert torch.equal(z0, z2) and torch.equal(l0, l2)
         assert (z0 - z1).abs().max().item() < 2e-2 * L
         assert (l0 - l1).abs().max().item() < 2e-2 * L
         ze, lde = O.coupling_bf16_emulated(z_in.cpu(), params, D, L, U, True, direction == ops.TNF_INVERSE)
