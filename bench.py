@@ -278,7 +278,7 @@ def main():
                 traffic = json.load(fh).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
-                    "kernel": "coupling_tc3_kernel", "launches_timed": len(kern_ms), "avg_launch_ms": avg,
+                    "kernel": "coupling_tc4_kernel", "launches_timed": len(kern_ms), "avg_launch_ms": avg,
                     "peak_source": pk["source"] + " (sustained bf16 GEMM; burst %.1f -> frac %.3f)" % (
                         pk["tflops_burst"], achieved / pk["tflops_burst"]),
                     "kernel_share_of_step": sum(kern_ms) / ms,
