@@ -72,3 +72,27 @@ for g in range(2):
     starts = [c for t, c in ev if t == 100]
     if len(starts) > 2:
         print("  cycles per tile (steady):", np.diff(starts)[1:].mean())
+
+if "timeline" in sys.argv:
+    # merged timeline of group 0, group 1 and the MMA warp (leader CTA 0) over two steady tiles
+    ev = []
+    for g in range(2):
+        for tg, c in d[g]:
+            if tg != 0:
+                ev.append((int(c), "G%d %s" % (g, label(int(tg)))))
+    m = raw[3072:3072 + 960].reshape(480, 2)
+    jobs = {0: "t0", 1: "t1", 2: "tF", 3: "s0", 4: "s1", 5: "sF"}
+    for tg, c in m:
+        if tg != 0:
+            tg = int(tg)
+            kind = "issue begins" if tg < 2000 else "issued+committed"
+            ev.append((int(c), "        MMA %s  group %d job %s" % (kind, (tg % 1000) // 100, jobs.get(tg % 100, str(tg % 100)))))
+    ev.sort()
+    starts = [c for c, s_ in ev if s_ == "G0 tile start"]
+    if len(starts) > 12:
+        lo, hi = starts[10], starts[12]
+        prev = lo
+        for c, s_ in ev:
+            if lo <= c <= hi:
+                print("%8d +%5d  %s" % (c - lo, c - prev, s_))
+                prev = c

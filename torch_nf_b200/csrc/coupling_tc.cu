@@ -1469,12 +1469,20 @@ __global__ void __launch_bounds__(kThreads3, 1) coupling_tc3_kernel(Args a) {
     if (elect_one()) {
       uint32_t slot = 0, phase = 0;
       const int64_t n_steps = cnt[0] * JT + shift;
+      // per-group job counters kept incrementally: no 64-bit division in the scheduling loops (a lone warp spends
+      // hundreds of cycles on one)
+      int jj2[2] = {0, 0};
+      const int64_t total[2] = {cnt[0] * JT, cnt[1] * JT};
+      int64_t todo[2] = {total[0], total[1]};
       for (int64_t n = 0; n < n_steps; ++n) {
         for (int g = 0; g < 2; ++g) {
-          const int64_t j = n - (g ? shift : 0);
-          if (j < 0 || j >= cnt[g] * JT) continue;
-          const int jj = (int)(j % JT);
-          const int net = jj / (sh.L + 1), l = jj % (sh.L + 1);
+          if ((g == 1 && n < shift) || todo[g] == 0) continue;
+          const int jj = jj2[g];
+          const bool first_job = todo[g] == total[g];
+          --todo[g];
+          if (++jj2[g] == JT) jj2[g] = 0;
+          const int net = jj > sh.L ? 1 : 0, l = jj > sh.L ? jj - (sh.L + 1) : jj;
+          (void)first_job; (void)net;
           size_t off = 0;
           for (int i = 0; i < l; ++i) off += (size_t)2 * sh.K_of(i) * sh.J_of(i) * 2;
           const int K = sh.K_of(l), J = sh.J_of(l), N = sh.N_of(l);
@@ -1516,15 +1524,23 @@ __global__ void __launch_bounds__(kThreads3, 1) coupling_tc3_kernel(Args a) {
     const uint32_t bF_lo = (uint32_t)bF_desc + ring16, bF_hi = (uint32_t)(bF_desc >> 32);
     const uint32_t ones_lo = (uint32_t)make_desc(smem_u32(sOnes), kTileM);
     const int64_t n_steps = cnt[0] * JT + shift;
+    // per-group job counters kept incrementally: no 64-bit division in the scheduling loops (a lone warp spends
+    // hundreds of cycles on one)
+    int jj2[2] = {0, 0};
+    const int64_t total[2] = {cnt[0] * JT, cnt[1] * JT};
+    int64_t todo[2] = {total[0], total[1]};
     for (int64_t n = 0; n < n_steps; ++n) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        const int64_t j = n - (g ? shift : 0);
-        if (j < 0 || j >= cnt[g] * JT) continue;
-        const int jj = (int)(j % JT);
-        const int net = jj / (sh.L + 1), l = jj % (sh.L + 1);
+        if ((g == 1 && n < shift) || todo[g] == 0) continue;
+        const int jj = jj2[g];
+        const bool first_job = todo[g] == total[g];
+        --todo[g];
+        if (++jj2[g] == JT) jj2[g] = 0;
+        const int net = jj > sh.L ? 1 : 0, l = jj > sh.L ? jj - (sh.L + 1) : jj;
+        (void)first_job; (void)net;
         const long long c0 = a.dbg != nullptr ? clock64() : 0;
-        if (j > 0) {   // the group's previous epilogue phase: accumulator drained, activations written
+        if (!first_job) {   // the group's previous epilogue phase: accumulator drained, activations written
           mbar_wait(&ct.e_done[g], (e_par >> g) & 1u);
           e_par ^= 1u << g;
         }
@@ -1911,7 +1927,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
   }
   constexpr int n_chunks = U_ / kChunk;
   const int JT = 2 * (sh.L + 1);     // jobs per tile
-  const int shift = sh.L + 1;        // group 1 runs half a tile behind group 0 (other shifts measured no better)
+  const int shift = sh.L;            // group 1 runs this many jobs behind group 0 (L = 2: shifts 1..5 measured, 2 is best)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&ct.w_full[i], 1); mbar_init(&ct.w_empty[i], 1); mbar_init(&ct.w_peer[i], 1); }
@@ -1953,12 +1969,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
     if (elect_one()) {
       uint32_t slot = 0, phase = 0;
       const int64_t n_steps = cnt[0] * JT + shift;
+      // per-group job counters kept incrementally: no 64-bit division in the scheduling loops (a lone warp spends
+      // hundreds of cycles on one)
+      int jj2[2] = {0, 0};
+      const int64_t total[2] = {cnt[0] * JT, cnt[1] * JT};
+      int64_t todo[2] = {total[0], total[1]};
       for (int64_t n = 0; n < n_steps; ++n) {
         for (int g = 0; g < 2; ++g) {
-          const int64_t j = n - (g ? shift : 0);
-          if (j < 0 || j >= cnt[g] * JT) continue;
-          const int jj = (int)(j % JT);
-          const int net = jj / (sh.L + 1), l = jj % (sh.L + 1);
+          if ((g == 1 && n < shift) || todo[g] == 0) continue;
+          const int jj = jj2[g];
+          const bool first_job = todo[g] == total[g];
+          --todo[g];
+          if (++jj2[g] == JT) jj2[g] = 0;
+          const int net = jj > sh.L ? 1 : 0, l = jj > sh.L ? jj - (sh.L + 1) : jj;
+          (void)first_job; (void)net;
           const int K = sh.K_of(l), NB = sh.J_of(l) / 2;
           const int ks = (kStageElems / NB) < K ? (kStageElems / NB) : K;
           const uint32_t bytes = (uint32_t)(ks * NB * 2);
@@ -1982,11 +2006,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
     // =============================== second CTA: forward "stage landed" to the leader ===============================
     uint32_t slot = 0, phase = 0;
     const int64_t n_steps = cnt[0] * JT + shift;
+    // per-group job counters kept incrementally: no 64-bit division in the scheduling loops (a lone warp spends
+    // hundreds of cycles on one)
+    int jj2[2] = {0, 0};
+    const int64_t total[2] = {cnt[0] * JT, cnt[1] * JT};
+    int64_t todo[2] = {total[0], total[1]};
     for (int64_t n = 0; n < n_steps; ++n) {
       for (int g = 0; g < 2; ++g) {
-        const int64_t j = n - (g ? shift : 0);
-        if (j < 0 || j >= cnt[g] * JT) continue;
-        const int l = (int)(j % JT) % (sh.L + 1);
+        if ((g == 1 && n < shift) || todo[g] == 0) continue;
+        const int jj = jj2[g];
+        --todo[g];
+        if (++jj2[g] == JT) jj2[g] = 0;
+        const int l = jj > sh.L ? jj - (sh.L + 1) : jj;
         const int K = sh.K_of(l), NB = sh.J_of(l) / 2;
         const int ks = (kStageElems / NB) < K ? (kStageElems / NB) : K;
         for (int st = 0; st < 1 + K / ks; ++st) {
@@ -2004,6 +2035,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
     const long long t_all = a.dbg != nullptr ? clock64() : 0;
     long long t_dep = 0, t_w3[3] = {0, 0, 0};
     const bool diag = a.dbg != nullptr;
+    int mma_n = 0;
     const uint32_t wfull0 = smem_u32(&ct.w_full[0]), wpeer0 = smem_u32(&ct.w_peer[0]), wempty0 = smem_u32(&ct.w_empty[0]);
     const uint32_t ring16 = smem_u32(ring) >> 4;
     const uint64_t a1_desc = make_desc(smem_u32(sA1), kTileM), act_desc = make_desc(smem_u32(sAct), kTileM);
@@ -2014,15 +2046,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
     const uint32_t bF_lo = (uint32_t)bF_desc + ring16, bF_hi = (uint32_t)(bF_desc >> 32);
     const uint32_t ones_lo = (uint32_t)make_desc(smem_u32(sOnes), kTileM);
     const int64_t n_steps = cnt[0] * JT + shift;
+    // per-group job counters kept incrementally: no 64-bit division in the scheduling loops (a lone warp spends
+    // hundreds of cycles on one)
+    int jj2[2] = {0, 0};
+    const int64_t total[2] = {cnt[0] * JT, cnt[1] * JT};
+    int64_t todo[2] = {total[0], total[1]};
     for (int64_t n = 0; n < n_steps; ++n) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        const int64_t j = n - (g ? shift : 0);
-        if (j < 0 || j >= cnt[g] * JT) continue;
-        const int jj = (int)(j % JT);
-        const int net = jj / (sh.L + 1), l = jj % (sh.L + 1);
+        if ((g == 1 && n < shift) || todo[g] == 0) continue;
+        const int jj = jj2[g];
+        const bool first_job = todo[g] == total[g];
+        --todo[g];
+        if (++jj2[g] == JT) jj2[g] = 0;
+        const int net = jj > sh.L ? 1 : 0, l = jj > sh.L ? jj - (sh.L + 1) : jj;
+        (void)first_job; (void)net;
         const long long c0 = a.dbg != nullptr ? clock64() : 0;
-        if (j > 0) {   // the group's previous epilogue phase in BOTH CTAs: accumulators drained, activations written
+        if (!first_job) {   // the group's previous epilogue phase in BOTH CTAs: accumulators drained, activations written
           mbar_wait_addr(smem_u32(&ct.e_done[g]), (e_par >> g) & 1u);
           e_par ^= 1u << g;
         }
@@ -2031,6 +2071,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
           a1_par ^= 1u << g;
         }
         if (a.dbg != nullptr) t_dep += clock64() - c0;
+        if (diag && blockIdx.x == 0 && leader && mma_n < 480) {
+          a.dbg[3072 + 2 * mma_n] = 1000 + g * 100 + jj; a.dbg[3072 + 2 * mma_n + 1] = clock64(); ++mma_n;
+        }
         const uint32_t d_tmem = tmem + (uint32_t)g * 256u;
         const uint32_t a1_lo = (uint32_t)a1_desc + (uint32_t)g * a1_sz16;
         const uint32_t act_lo = (uint32_t)act_desc + (uint32_t)g * act_sz16;
@@ -2043,6 +2086,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
         if (leader) {
           tc_commit2_addr(smem_u32(&ct.h_ready[g]));
           if (l == 0 && net == 1) tc_commit2_addr(smem_u32(&ct.a1_free[g]));
+        }
+        if (diag && blockIdx.x == 0 && leader && mma_n < 480) {
+          a.dbg[3072 + 2 * mma_n] = 2000 + g * 100 + jj; a.dbg[3072 + 2 * mma_n + 1] = clock64(); ++mma_n;
         }
         __syncwarp();
       }
