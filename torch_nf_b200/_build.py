@@ -4,6 +4,7 @@ The library exports exactly the ``extern "C"`` entry points declared in
 ``include/tnf.h``; it has no torch or Python dependency (plain pointers and
 sizes), so it is loaded with ``ctypes``.
 """
+import fcntl
 import hashlib
 import os
 import shutil
@@ -33,7 +34,7 @@ def source_digest():
     files.append(os.path.join(os.path.dirname(HERE), "include", "tnf.h"))
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())   # not the absolute path: the tree is copied to other roots
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -47,20 +48,35 @@ def is_current():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source into one shared library. Returns its path."""
+    """Compile every CUDA source into one shared library. Returns its path.
+
+    Safe under concurrent callers (torchrun starts one process per GPU): an exclusive file lock serialises the
+    builders, the library is written to a temporary name and renamed into place, and late comers find it current."""
     if not force and is_current():
         return LIB
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build torch_nf_b200/_C.so")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    with open(STAMP, "w") as fh:
-        fh.write(source_digest())
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():      # another process built it while we waited
+                return LIB
+            tmp = LIB + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            if verbose:
+                print(" ".join(cmd).replace(tmp, LIB))
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB)
+            with open(STAMP + ".tmp", "w") as fh:
+                fh.write(source_digest())
+            os.replace(STAMP + ".tmp", STAMP)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
