@@ -46,3 +46,18 @@ def test_argument_errors_without_gpu():
     assert rc < 0 and b"L=9" in lib.tnf_last_error()
     rc = lib.tnf_affine(p, p, p, p, 0, 1, 1, 4, 0, 7, None)
     assert rc < 0 and b"dtype" in lib.tnf_last_error()
+
+
+def test_build_digest_is_path_independent(tmp_path, monkeypatch):
+    """The in-tree library travels with the repository to other roots (GPU boxes run the snapshot from a scratch
+    path): whether it is current must depend on the source CONTENTS only, or every rank would rebuild it."""
+    import shutil
+    from torch_nf_b200 import _build
+    ref = _build.source_digest()
+    root = tmp_path / "elsewhere"
+    shutil.copytree(_build.CSRC, root / "torch_nf_b200" / "csrc")
+    (root / "include").mkdir()
+    shutil.copy(os.path.join(os.path.dirname(_build.HERE), "include", "tnf.h"), root / "include" / "tnf.h")
+    monkeypatch.setattr(_build, "HERE", str(root / "torch_nf_b200"))
+    monkeypatch.setattr(_build, "CSRC", str(root / "torch_nf_b200" / "csrc"))
+    assert _build.source_digest() == ref
