@@ -154,3 +154,29 @@ def test_coupling_tc_fused_column_stats():
         np.testing.assert_allclose(sums[:2 * D].cpu().numpy(), ref[:2 * D].cpu().numpy(), rtol=2e-5, atol=2e-3 * N ** 0.5)
         z2, _ = ops.coupling_tc(z_in, packed, D, U, L, upper, ops.TNF_FORWARD, pre_scale=ps, pre_shift=pb)
         assert torch.equal(z, z2)
+
+
+def test_cta_pair_kernel_matches_single_cta_kernel_at_scale():
+    """The CTA-pair kernel (cross-CTA mbarrier arrivals, multicast commits, forwarded stage barriers) against the
+    single-CTA two-tile kernel on many tiles per CTA and repeated launches: any lost ordering between the two CTAs of
+    a pair would show up as a bit difference somewhere in 2^18 rows."""
+    D, U, L, N = 64, 256, 2, (1 << 18) + 333
+    params = T(synthetic_params([("RealNVP", L, U, False)], D, 1, seed=12))
+    packed = ops.tc_pack(params.cuda()[0], D, U, L, False)
+    z_in = torch.randn(1, N, D, device="cuda")
+    ps = (torch.rand(D) + 0.5).cuda(); pb = torch.randn(D).cuda()
+    try:
+        _lib.lib().tnf_tc_set_variant(2)
+        ref = {}
+        for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
+            z, ld, sums = ops.coupling_tc(z_in, packed, D, U, L, False, direction, pre_scale=ps, pre_shift=pb, want_stats=True)
+            ref[direction] = (z.clone(), ld.clone(), sums.clone())
+        _lib.lib().tnf_tc_set_variant(0)
+        for rep in range(3):
+            for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
+                z, ld, sums = ops.coupling_tc(z_in, packed, D, U, L, False, direction, pre_scale=ps, pre_shift=pb, want_stats=True)
+                assert torch.equal(z, ref[direction][0]) and torch.equal(ld, ref[direction][1])
+                np.testing.assert_allclose(sums.cpu().numpy(), ref[direction][2].cpu().numpy(), rtol=2e-5, atol=2e-3 * N ** 0.5)
+    finally:
+        _lib.lib().tnf_tc_set_variant(0)
+    assert torch.isfinite(z).all()
