@@ -37,11 +37,12 @@
 extern "C" {
 #endif
 
-#define TNF_ABI_VERSION 1
+#define TNF_ABI_VERSION 2
 
 enum { TNF_F32 = 0, TNF_F64 = 1 };
 enum { TNF_FORWARD = 0, TNF_INVERSE = 1 };
 enum { TNF_LD_WRITE = 0, TNF_LD_ADD = 1, TNF_LD_SUB = -1 };
+enum { TNF_TC_BF16 = 0, TNF_TC_FP32 = 1 };
 enum { TNF_ERR_ARG = -1, TNF_ERR_UNSUPPORTED = -2, TNF_ERR_ALIGN = -3 };
 
 typedef void* tnf_stream_t; /* cudaStream_t */
@@ -104,23 +105,24 @@ int tnf_tc_supported(int D, int U, int L);
 /* diagnostic: out[128 x N] = bf16(A[128 x K]) . bf16(W[K x N]) through the same
  * operand images, UMMA descriptors and TMEM accumulator layout as the fused
  * kernel; a_in_tmem selects the A operand source (1: TMEM, 0: SMEM image). */
-/* diagnostic: when set to a device buffer of 2048 int64, CTA 0 of tnf_coupling_tc records
- * (tag, clock64) stamps of its epilogue phases (group g at offset 512*g*2); NULL disables. */
-void tnf_tc_set_debug(void* dev_buffer);
-/* diagnostic: 1 = only one epilogue group works (no tile ping-pong), 2 = default. */
-void tnf_tc_set_groups(int n_groups);
-/* diagnostic: kernel choice of tnf_coupling_tc: 0 = automatic (two-tile kernel for D <= 128, single-tile
- * pipelined kernel for D = 256), 1 = always the first (8 epilogue warp) kernel. */
-void tnf_tc_set_variant(int variant);
 int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N, int a_in_tmem,
                          tnf_stream_t stream);
-size_t tnf_tc_packed_bytes(int D, int U, int L);
+/* precision: TNF_TC_BF16 = bf16 operands (stated tolerance max|dz| <= 5e-2);
+ *            TNF_TC_FP32 = fp32-parity mode: operands split into fp16 hi + lo parts, three MMAs per
+ *            product into the same fp32 accumulator, tanh / exp to fp32 accuracy.
+ * The packed image of a layer depends on the precision. */
+size_t tnf_tc_packed_bytes(int D, int U, int L, int precision);
 int tnf_tc_pack(const float* params, void* packed, int D, int U, int L, int transform_upper,
-                tnf_stream_t stream);
+                int precision, tnf_stream_t stream);
+/* variant (diagnostic; no process-global state): 0 = kernel chosen by shape (CTA-pair two-tile kernel for
+ *   D <= 128, single-tile pipelined kernel for D = 256), 1 = the first (8 epilogue warp) kernel,
+ *   2 = two-tile kernel without CTA pairs; +16 = first kernel with one epilogue group only.
+ * debug (diagnostic, or NULL): device buffer of 4096 int64 receiving (tag, clock64) stamps of CTA 0. */
 int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void* packed,
                     int64_t rows, int D, int U, int L, int transform_upper, int direction,
                     int accum, const float* pre_scale, const float* pre_shift,
-                    double* col_stats, void* stats_workspace, tnf_stream_t stream);
+                    double* col_stats, void* stats_workspace, int precision, int variant, void* debug,
+                    tnf_stream_t stream);
 
 /* ---- Affine: replaces Affine.forward_and_log_det / inverse_and_log_det
  * (bijectors.py:277-315).  params row = [alpha(D), shift(D)].

@@ -13,26 +13,24 @@ if len(sys.argv) > 2:
 params = torch.tensor(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=0)).cuda()
 packed = ops.tc_pack(params[0], D, U, L, True)
 z = torch.randn(1, N, D, device="cuda")
+VARIANT = 0          # per-call diagnostic argument of tnf_coupling_tc (no process-global switches)
 if len(sys.argv) > 1 and sys.argv[1] == "solo":
-    _lib.lib().tnf_tc_set_variant(1)
-    _lib.lib().tnf_tc_set_groups(1)
+    VARIANT = 1 + 16
 elif len(sys.argv) > 1 and sys.argv[1] == "pingpong":
-    _lib.lib().tnf_tc_set_variant(1)
-elif len(sys.argv) > 1 and sys.argv[1].startswith("x"):
-    _lib.lib().tnf_tc_set_groups(int(sys.argv[1][1:]))
+    VARIANT = 1
+elif len(sys.argv) > 1 and sys.argv[1].startswith("v"):
+    VARIANT = int(sys.argv[1][1:])
 for _ in range(3):
-    ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)
+    ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE, variant=VARIANT)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(5):
-    ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)
+    ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE, variant=VARIANT)
 e1.record(); torch.cuda.synchronize()
 print("ms per launch: %.4f" % (e0.elapsed_time(e1) / 5))
 dbg = torch.zeros(2048 * 4, dtype=torch.int64, device="cuda")
-_lib.lib().tnf_tc_set_debug(dbg.data_ptr())
-ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE)
+ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE, variant=VARIANT, debug=dbg)
 torch.cuda.synchronize()
-_lib.lib().tnf_tc_set_debug(None)
 raw = dbg.cpu().numpy()
 print("MMA warp (CTA 0): cycles waiting on epilogue %d, on weights %d, total %d (first layers %d, hidden layers %d, final layers %d)" % (raw[2040], raw[2041], raw[2042], raw[2043], raw[2044], raw[2045]))
 d = raw[:2048].reshape(2, 512, 2)  # group g at int64 offset 1024*g

@@ -75,15 +75,11 @@ def test_coupling_tc_kernel_variants(D, U, L, N):
     z_in = T(synthetic_noise(1, N, D, seed=8).astype(np.float32)).cuda()
     packed = ops.tc_pack(params.cuda()[0], D, U, L, True)
     out = {}
-    try:
-        for variant in (0, 1, 2):
-            _lib.lib().tnf_tc_set_variant(variant)
-            for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
-                z, ld = ops.coupling_tc(z_in, packed, D, U, L, True, direction)
-                torch.cuda.synchronize()
-                out[(variant, direction)] = (z.cpu(), ld.cpu())
-    finally:
-        _lib.lib().tnf_tc_set_variant(0)
+    for variant in (0, 1, 2):
+        for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
+            z, ld = ops.coupling_tc(z_in, packed, D, U, L, True, direction, variant=variant)
+            torch.cuda.synchronize()
+            out[(variant, direction)] = (z.cpu(), ld.cpu())
     for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
         z0, l0 = out[(0, direction)]
         z1, l1 = out[(1, direction)]
@@ -165,18 +161,14 @@ def test_cta_pair_kernel_matches_single_cta_kernel_at_scale():
     packed = ops.tc_pack(params.cuda()[0], D, U, L, False)
     z_in = torch.randn(1, N, D, device="cuda")
     ps = (torch.rand(D) + 0.5).cuda(); pb = torch.randn(D).cuda()
-    try:
-        _lib.lib().tnf_tc_set_variant(2)
-        ref = {}
+    ref = {}
+    for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
+        z, ld, sums = ops.coupling_tc(z_in, packed, D, U, L, False, direction, pre_scale=ps, pre_shift=pb, want_stats=True,
+                                      variant=2)
+        ref[direction] = (z.clone(), ld.clone(), sums.clone())
+    for rep in range(3):
         for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
             z, ld, sums = ops.coupling_tc(z_in, packed, D, U, L, False, direction, pre_scale=ps, pre_shift=pb, want_stats=True)
-            ref[direction] = (z.clone(), ld.clone(), sums.clone())
-        _lib.lib().tnf_tc_set_variant(0)
-        for rep in range(3):
-            for direction in (ops.TNF_FORWARD, ops.TNF_INVERSE):
-                z, ld, sums = ops.coupling_tc(z_in, packed, D, U, L, False, direction, pre_scale=ps, pre_shift=pb, want_stats=True)
-                assert torch.equal(z, ref[direction][0]) and torch.equal(ld, ref[direction][1])
-                np.testing.assert_allclose(sums.cpu().numpy(), ref[direction][2].cpu().numpy(), rtol=2e-5, atol=2e-3 * N ** 0.5)
-    finally:
-        _lib.lib().tnf_tc_set_variant(0)
+            assert torch.equal(z, ref[direction][0]) and torch.equal(ld, ref[direction][1])
+            np.testing.assert_allclose(sums.cpu().numpy(), ref[direction][2].cpu().numpy(), rtol=2e-5, atol=2e-3 * N ** 0.5)
     assert torch.isfinite(z).all()

@@ -15,6 +15,7 @@ c_void_p, c_int, c_int64, c_double, c_size_t, c_uint64 = (
 TNF_F32, TNF_F64 = 0, 1
 TNF_FORWARD, TNF_INVERSE = 0, 1
 TNF_LD_WRITE, TNF_LD_ADD, TNF_LD_SUB = 0, 1, -1
+TNF_TC_BF16, TNF_TC_FP32 = 0, 1
 
 P, I, L, Dbl, Z, U64 = c_void_p, c_int, c_int64, c_double, c_size_t, c_uint64
 
@@ -28,13 +29,10 @@ PROTOTYPES = {
     "tnf_maf": (I, [P, P, P, P, L, P, L, L, I, I, I, I, I, I, P]),
     "tnf_maf_bwd": (I, [P, P, L, P, P, P, P, P, L, L, L, I, I, I, I, I, P]),
     "tnf_tc_supported": (I, [I, I, I]),
-    "tnf_tc_set_debug": (None, [P]),
-    "tnf_tc_set_groups": (None, [I]),
-    "tnf_tc_set_variant": (None, [I]),
     "tnf_tc_selftest_gemm": (I, [P, P, P, I, I, I, P]),
-    "tnf_tc_packed_bytes": (Z, [I, I, I]),
-    "tnf_tc_pack": (I, [P, P, I, I, I, I, P]),
-    "tnf_coupling_tc": (I, [P, P, P, P, L, I, I, I, I, I, I, P, P, P, P, P]),
+    "tnf_tc_packed_bytes": (Z, [I, I, I, I]),
+    "tnf_tc_pack": (I, [P, P, I, I, I, I, I, P]),
+    "tnf_coupling_tc": (I, [P, P, P, P, L, I, I, I, I, I, I, P, P, P, P, I, I, P, P]),
     "tnf_affine": (I, [P, P, P, P, L, L, L, I, I, I, P]),
     "tnf_affine_bwd": (I, [P, P, L, P, P, P, P, L, L, L, I, I, I, P]),
     "tnf_colstats_workspace_bytes": (Z, [I]),

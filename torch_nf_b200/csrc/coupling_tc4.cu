@@ -1,0 +1,556 @@
+// RealNVP coupling layer on tcgen05 tensor cores: the CTA-pair two-tile kernel (product path for D <= 128).
+// Shared definitions: tc_common.cuh.  Reference semantics: torch_nf/bijectors.py:145-242 (RealNVP).
+#include "tc_common.cuh"
+
+namespace tnf {
+namespace tc {
+
+template <int K, int N>
+__device__ __forceinline__ void mma_job2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo_ring, uint32_t b_hi,
+                                         uint32_t ones_lo, uint32_t wfull0, uint32_t wpeer0, uint32_t wempty0, uint32_t S,
+                                         uint32_t& slot, uint32_t& phase, bool leader, long long* t_w = nullptr) {
+  constexpr int NB = N / 2;                                            // B rows held per CTA
+  constexpr int KS = (kStageElems / NB) < K ? (kStageElems / NB) : K;  // K rows per weight stage
+  constexpr int CPS = KS / kChunk;                                     // chunks per stage
+  constexpr uint32_t kStage16 = kStageBytes >> 4;
+  const uint32_t idesc = make_idesc2(N);
+  {
+    const long long c0 = t_w ? clock64() : 0;
+    mbar_wait_addr(wfull0 + slot * 8u, phase);
+    mbar_wait_addr(wpeer0 + slot * 8u, phase);
+    if (t_w) *t_w += clock64() - c0;
+    tc_fence_after();
+    if (leader) {
+      umma2_ss2(d_tmem, ones_lo, a_hi, b_lo_ring + slot * kStage16, b_hi, idesc, 0u);
+      tc_commit2_addr(wempty0 + slot * 8u);
+    }
+    if (++slot == S) { slot = 0; phase ^= 1; }
+  }
+#pragma unroll
+  for (int c = 0; c < K / kChunk; ++c) {
+    if (c % CPS == 0) {
+      const long long c0 = t_w ? clock64() : 0;
+      mbar_wait_addr(wfull0 + slot * 8u, phase);
+      mbar_wait_addr(wpeer0 + slot * 8u, phase);
+      if (t_w) *t_w += clock64() - c0;
+      tc_fence_after();
+    }
+    if (leader) {
+      const uint32_t b_lo = b_lo_ring + slot * kStage16 + (uint32_t)((c % CPS) * 4 * NB);
+      umma2_ss2(d_tmem, a_lo + 512u * c, a_hi, b_lo, b_hi, idesc, 1u);
+      umma2_ss2(d_tmem, a_lo + 512u * c + 256u, a_hi, b_lo + 2u * NB, b_hi, idesc, 1u);
+      if (c % CPS == CPS - 1) tc_commit2_addr(wempty0 + slot * 8u);
+    }
+    if (c % CPS == CPS - 1) {
+      if (++slot == S) { slot = 0; phase ^= 1; }
+    }
+  }
+}
+
+// ================================================================ two-tile ping-pong kernel on CTA pairs (D <= 128)
+// The two-tile kernel above, run by clusters of two CTAs that share every weight operand (tcgen05 cta_group::2):
+// the pair's MMAs have M = 256 (128 rows = one tile per CTA and group), each CTA keeps only ITS half of the N
+// columns of a weight stage in shared memory, and the tensor cores of both SMs read both halves.  Per SM this
+// halves the weight stream from L2, the ring bytes per stage (a 16 KB slot now holds 64 K rows = four MMAs, so the
+// four-slot ring is twice as deep in MMA time) and the B-operand shared-memory reads.  The leader CTA (cluster
+// rank 0) issues all MMAs; commits are multicast to both CTAs' barriers; the epilogue and I/O warps of the second
+// CTA arrive on the leader's barriers through the cluster address space, and its otherwise idle MMA warp forwards
+// "weight stage landed" from its own ring to the leader.  (Semantics checked in profiles/microbench/umma_2cta.cu.)
+// Two tiles in flight per CTA.  Epilogue group g (8 warps: TMEM lane quadrant w%4, accumulator chunks of parity
+// (w/4)%2) owns tile (2k+g)*grid + cta, the 256 TMEM columns [256g, 256g+256) and its own A1 / activation images.
+// A layer's MMAs start when the group's previous epilogue phase is complete (one accumulator per group: the next
+// layer would overwrite what the epilogue is still reading), so a single group alternates between the MUFU pipe and
+// the tensor pipe - and the other group, half a tile out of phase, fills each pipe in the gaps.  Weights and the
+// bias operand images stream through the ring in the static job order of the MMA warp; biases are added by a bias
+// MMA (see mma_job), global I/O of the conditioning half is done by two dedicated warps with coalesced accesses.
+constexpr int kThreads4 = (kEpiWarps2 + 4) * 32;   // 16 epilogue, MMA, producer, 2 I/O
+
+struct __align__(16) Ctrl4 {
+  uint64_t w_full[kMaxStages];
+  uint64_t w_empty[kMaxStages];
+  uint64_t w_peer[kMaxStages];   // leader only: the second CTA's half of the stage has landed (forwarded by its MMA warp)
+  uint64_t a1_ready[2];   // per group, 2 I/O warps: A1 image of the group's next tile written
+  uint64_t a1_free[2];    // per group, tcgen05.commit: both layer-0 jobs of the tile have read the A1 image
+  uint64_t e_done[2];     // per group, 8 epilogue warps: accumulator drained (and activation image written)
+  uint64_t h_ready[2];    // per group, tcgen05.commit: accumulator of the group's current job complete
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+// dynamic shared memory:
+//   [ring: n_stages x 16 KB][A1 g0][A1 g1][Act g0][Act g1][ones 4 KB][Ctrl4][pre_scale D][pre_shift D][ld partial 2 x 128]
+size_t smem_bytes4(const Shape& sh, int n_stages) {
+  return (size_t)n_stages * sh.stage_elems() * 2 + 2 * sh.a1_bytes() + 2 * sh.act_bytes() + kOnesBytes + sizeof(Ctrl4) +
+         (size_t)(2 * sh.D + 2 * kTileM) * sizeof(float);
+}
+
+template <bool kInverse, int DH, int U_>   // DH = D/2 = d_in = d_out in {32, 64}; U_ = hidden units
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupling_tc4_kernel(Args a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const Shape sh(a.D, a.U, a.L, a.upper);
+  const int S = a.n_stages;
+  unsigned char* ring = smem_raw;
+  const uint32_t stage_bytes = (uint32_t)sh.stage_elems() * 2;
+  unsigned char* sA1 = ring + (size_t)S * stage_bytes;             // 2 images (group)
+  unsigned char* sAct = sA1 + 2 * sh.a1_bytes();                    // 2 images (group)
+  unsigned char* sOnes = sAct + 2 * sh.act_bytes();                 // constant A image for the bias MMA
+  Ctrl4& ct = *reinterpret_cast<Ctrl4*>(sOnes + kOnesBytes);
+  float* s_pscale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl4));
+  float* s_pshift = s_pscale + sh.D;
+  float* s_ldp = s_pshift + sh.D;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int64_t P = gridDim.x / 2, pair = blockIdx.x / 2;
+  const int64_t n_super = (n_tiles + 1) / 2;          // 256-row super tiles: one tile per CTA of the pair
+  // tiles of group g: 2 * ((2k + g) * P + pair) + rank, k = 0 .. cnt[g] - 1 (the same count in both CTAs)
+  int64_t cnt[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int64_t first = (int64_t)g * P + pair;
+    cnt[g] = first < n_super ? (n_super - first + 2 * P - 1) / (2 * P) : 0;
+  }
+  constexpr int n_chunks = U_ / kChunk;
+  const int JT = 2 * (sh.L + 1);     // jobs per tile
+  const int shift = sh.L;            // group 1 runs this many jobs behind group 0 (L = 2: shifts 1..5 measured, 2 is best)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&ct.w_full[i], 1); mbar_init(&ct.w_empty[i], 1); mbar_init(&ct.w_peer[i], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&ct.a1_ready[g], 4);                  // the I/O warps of both CTAs (leader's barrier)
+      mbar_init(&ct.a1_free[g], 1);
+      mbar_init(&ct.e_done[g], kEpiWarps2);           // the group's epilogue warps of both CTAs (leader's barrier)
+      mbar_init(&ct.h_ready[g], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kEpiWarps2) tmem_alloc2(&ct.tmem_base, 512);
+  {
+    for (int i = threadIdx.x; i < kOnesBytes / 4; i += blockDim.x)   // row r: K columns 0 and 1 are 1.0 (bf16 0x3f80)
+      reinterpret_cast<uint32_t*>(sOnes)[i] = (i < kTileM * 4 && (i & 3) == 0) ? 0x3f803f80u : 0u;
+    fence_async_smem();
+    for (int i = threadIdx.x; i < sh.D; i += blockDim.x) {
+      s_pscale[i] = a.pre_scale ? a.pre_scale[i] : 1.0f;
+      s_pshift[i] = a.pre_shift ? a.pre_shift[i] : 0.0f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers and images exist before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem = ct.tmem_base;
+  // the leader's barriers that both CTAs arrive on, as cluster addresses
+  const uint32_t lead_e_done = mapa_u32(smem_u32(&ct.e_done[0]), 0u), lead_a1_ready = mapa_u32(smem_u32(&ct.a1_ready[0]), 0u);
+  const uint32_t lead_w_peer = mapa_u32(smem_u32(&ct.w_peer[0]), 0u);
+  const bool want_stats = a.stat_partials != nullptr;
+  float io_sv1[4] = {0.f, 0.f, 0.f, 0.f}, io_sv2[4] = {0.f, 0.f, 0.f, 0.f};   // I/O warps: sums of columns col..col+3
+  // per-warp statistics rows ([2*D] doubles, own columns only) are gathered in the (then dead) activation images
+  double* stat_rows = reinterpret_cast<double*>(sAct);
+  constexpr int kStatWarps = kEpiWarps2 + 2;
+
+  if (warp == kEpiWarps2 + 1) {
+    // =============================== weight producer (one elected lane) ===============================
+    // streams THIS CTA's half of every stage (N/2 of the N weight columns, 64 K rows per 16 KB slot at N = 256)
+    if (elect_one()) {
+      uint32_t slot = 0, phase = 0;
+      const int64_t n_steps = cnt[0] * JT + shift;
+      // per-group job counters kept incrementally: no 64-bit division in the scheduling loops (a lone warp spends
+      // hundreds of cycles on one)
+      int jj2[2] = {0, 0};
+      const int64_t total[2] = {cnt[0] * JT, cnt[1] * JT};
+      int64_t todo[2] = {total[0], total[1]};
+      for (int64_t n = 0; n < n_steps; ++n) {
+        for (int g = 0; g < 2; ++g) {
+          if ((g == 1 && n < shift) || todo[g] == 0) continue;
+          const int jj = jj2[g];
+          const bool first_job = todo[g] == total[g];
+          --todo[g];
+          if (++jj2[g] == JT) jj2[g] = 0;
+          const int net = jj > sh.L ? 1 : 0, l = jj > sh.L ? jj - (sh.L + 1) : jj;
+          (void)first_job; (void)net;
+          const int K = sh.K_of(l), NB = sh.J_of(l) / 2;
+          const int ks = (kStageElems / NB) < K ? (kStageElems / NB) : K;
+          const uint32_t bytes = (uint32_t)(ks * NB * 2);
+          const unsigned char* nsrc = a.packed + sh.split_w_off(l, net, (int)rank);
+          {   // the job's bias operand image travels as a stage of its own, ahead of the weights
+            mbar_wait(&ct.w_empty[slot], phase ^ 1);
+            mbar_arrive_expect_tx(&ct.w_full[slot], (uint32_t)NB * 32u);
+            bulk_g2s(ring + (size_t)slot * stage_bytes, a.packed + sh.split_b_off(l, net, (int)rank), (uint32_t)NB * 32u, &ct.w_full[slot]);
+          }
+          if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+          for (int st = 0; st < K / ks; ++st) {
+            mbar_wait(&ct.w_empty[slot], phase ^ 1);
+            mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
+            bulk_g2s(ring + (size_t)slot * stage_bytes, nsrc + (size_t)st * bytes, bytes, &ct.w_full[slot]);
+            if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps2 && rank != 0) {
+    // =============================== second CTA: forward "stage landed" to the leader ===============================
+    uint32_t slot = 0, phase = 0;
+    const int64_t n_steps = cnt[0] * JT + shift;
+    // per-group job counters kept incrementally: no 64-bit division in the scheduling loops (a lone warp spends
+    // hundreds of cycles on one)
+    int jj2[2] = {0, 0};
+    const int64_t total[2] = {cnt[0] * JT, cnt[1] * JT};
+    int64_t todo[2] = {total[0], total[1]};
+    for (int64_t n = 0; n < n_steps; ++n) {
+      for (int g = 0; g < 2; ++g) {
+        if ((g == 1 && n < shift) || todo[g] == 0) continue;
+        const int jj = jj2[g];
+        --todo[g];
+        if (++jj2[g] == JT) jj2[g] = 0;
+        const int l = jj > sh.L ? jj - (sh.L + 1) : jj;
+        const int K = sh.K_of(l), NB = sh.J_of(l) / 2;
+        const int ks = (kStageElems / NB) < K ? (kStageElems / NB) : K;
+        for (int st = 0; st < 1 + K / ks; ++st) {
+          mbar_wait(&ct.w_full[slot], phase);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(lead_w_peer + slot * 8u);
+          if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps2) {
+    // =============================== leader CTA: MMA issuer (warp-uniform, elected lane issues) ===============================
+    const bool leader = elect_one();
+    uint32_t slot = 0, phase = 0, e_par = 0, a1_par = 0;   // parities: bit g
+    const long long t_all = a.dbg != nullptr ? clock64() : 0;
+    long long t_dep = 0, t_w3[3] = {0, 0, 0};
+    const bool diag = a.dbg != nullptr;
+    int mma_n = 0;
+    const uint32_t wfull0 = smem_u32(&ct.w_full[0]), wpeer0 = smem_u32(&ct.w_peer[0]), wempty0 = smem_u32(&ct.w_empty[0]);
+    const uint32_t ring16 = smem_u32(ring) >> 4;
+    const uint64_t a1_desc = make_desc(smem_u32(sA1), kTileM), act_desc = make_desc(smem_u32(sAct), kTileM);
+    const uint32_t a_hi = (uint32_t)(a1_desc >> 32);
+    const uint32_t a1_sz16 = (uint32_t)sh.a1_bytes() >> 4, act_sz16 = (uint32_t)sh.act_bytes() >> 4;
+    const uint64_t bU_desc = make_desc(0u, U_ / 2), bF_desc = make_desc(0u, DH / 2);   // each CTA holds half of the N rows
+    const uint32_t bU_lo = (uint32_t)bU_desc + ring16, bU_hi = (uint32_t)(bU_desc >> 32);
+    const uint32_t bF_lo = (uint32_t)bF_desc + ring16, bF_hi = (uint32_t)(bF_desc >> 32);
+    const uint32_t ones_lo = (uint32_t)make_desc(smem_u32(sOnes), kTileM);
+    const int64_t n_steps = cnt[0] * JT + shift;
+    // per-group job counters kept incrementally: no 64-bit division in the scheduling loops (a lone warp spends
+    // hundreds of cycles on one)
+    int jj2[2] = {0, 0};
+    const int64_t total[2] = {cnt[0] * JT, cnt[1] * JT};
+    int64_t todo[2] = {total[0], total[1]};
+    for (int64_t n = 0; n < n_steps; ++n) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if ((g == 1 && n < shift) || todo[g] == 0) continue;
+        const int jj = jj2[g];
+        const bool first_job = todo[g] == total[g];
+        --todo[g];
+        if (++jj2[g] == JT) jj2[g] = 0;
+        const int net = jj > sh.L ? 1 : 0, l = jj > sh.L ? jj - (sh.L + 1) : jj;
+        (void)first_job; (void)net;
+        const long long c0 = a.dbg != nullptr ? clock64() : 0;
+        if (!first_job) {   // the group's previous epilogue phase in BOTH CTAs: accumulators drained, activations written
+          mbar_wait_addr(smem_u32(&ct.e_done[g]), (e_par >> g) & 1u);
+          e_par ^= 1u << g;
+        }
+        if (jj == 0) {
+          mbar_wait_addr(smem_u32(&ct.a1_ready[g]), (a1_par >> g) & 1u);
+          a1_par ^= 1u << g;
+        }
+        if (a.dbg != nullptr) t_dep += clock64() - c0;
+        if (diag && blockIdx.x == 0 && leader && mma_n < 480) {
+          a.dbg[3072 + 2 * mma_n] = 1000 + g * 100 + jj; a.dbg[3072 + 2 * mma_n + 1] = clock64(); ++mma_n;
+        }
+        const uint32_t d_tmem = tmem + (uint32_t)g * 256u;
+        const uint32_t a1_lo = (uint32_t)a1_desc + (uint32_t)g * a1_sz16;
+        const uint32_t act_lo = (uint32_t)act_desc + (uint32_t)g * act_sz16;
+        if (l == 0)
+          mma_job2<DH, U_>(d_tmem, a1_lo, a_hi, bU_lo, bU_hi, ones_lo, wfull0, wpeer0, wempty0, (uint32_t)S, slot, phase, leader, diag ? &t_w3[0] : nullptr);
+        else if (l < sh.L)
+          mma_job2<U_, U_>(d_tmem, act_lo, a_hi, bU_lo, bU_hi, ones_lo, wfull0, wpeer0, wempty0, (uint32_t)S, slot, phase, leader, diag ? &t_w3[1] : nullptr);
+        else
+          mma_job2<U_, DH>(d_tmem, act_lo, a_hi, bF_lo, bF_hi, ones_lo, wfull0, wpeer0, wempty0, (uint32_t)S, slot, phase, leader, diag ? &t_w3[2] : nullptr);
+        if (leader) {
+          tc_commit2_addr(smem_u32(&ct.h_ready[g]));
+          if (l == 0 && net == 1) tc_commit2_addr(smem_u32(&ct.a1_free[g]));
+        }
+        if (diag && blockIdx.x == 0 && leader && mma_n < 480) {
+          a.dbg[3072 + 2 * mma_n] = 2000 + g * 100 + jj; a.dbg[3072 + 2 * mma_n + 1] = clock64(); ++mma_n;
+        }
+        __syncwarp();
+      }
+    }
+    if (a.dbg != nullptr && blockIdx.x == 0 && leader) {
+      a.dbg[2040] = t_dep; a.dbg[2041] = t_w3[0] + t_w3[1] + t_w3[2]; a.dbg[2042] = clock64() - t_all;
+      a.dbg[2043] = t_w3[0]; a.dbg[2044] = t_w3[1]; a.dbg[2045] = t_w3[2];
+    }
+  } else if (warp < kEpiWarps2) {
+    // =============================== epilogue warps ===============================
+    const int g = warp >> 3, q = warp & 3, par = (warp >> 2) & 1;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int r_tile = q * 32 + lane;
+    constexpr int W = DH / 2;                 // final-layer columns per thread (16 or 32)
+    const float kLog2e = 1.4426950408889634f;
+    const uint32_t hcol = tmem + lane_addr + (uint32_t)g * 256u;
+    unsigned char* myAct = sAct + (size_t)g * sh.act_bytes();
+    uint32_t h_par = 0;
+    float st_y = 0.f, st_y2 = 0.f;            // per-lane column sums of the transformed half (column par*W + lane%W)
+
+    int dbg_n = 0;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && q == 0 && par == 0 && lane == 0;
+    long long* dbg = a.dbg + g * 1024;
+#define TNF_STAMP(tag)                                                                     \
+  do {                                                                                     \
+    if (dbg_on && dbg_n < 500) { dbg[2 * dbg_n] = (tag); dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; } \
+  } while (0)
+
+    // accumulator chunk c (bias already added by the bias MMA) -> MUFU.TANH -> bf16 -> A image.  No software pipelining
+    // inside the warp (a double-buffered variant measured no faster): the other warps of the sub-partition cover it.
+    auto epi_step = [&](int c) {
+      uint32_t x[32];
+      tmem_ld32(hcol + (uint32_t)(c * kChunk), x);
+      tc_wait_ld();
+      unsigned char* dst = myAct + img_off(r_tile, c * kChunk, kTileM);
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[j + e] = __float_as_uint(tanh_fast(__uint_as_float(x[j + e])));
+        *reinterpret_cast<uint4*>(dst + (j >> 3) * (kTileM * 16)) =
+            make_uint4(pack_bf16(__uint_as_float(x[j]), __uint_as_float(x[j + 1])),
+                       pack_bf16(__uint_as_float(x[j + 2]), __uint_as_float(x[j + 3])),
+                       pack_bf16(__uint_as_float(x[j + 4]), __uint_as_float(x[j + 5])),
+                       pack_bf16(__uint_as_float(x[j + 6]), __uint_as_float(x[j + 7])));
+      }
+    };
+    // end of an epilogue phase: accumulator reads done, activation image visible to the async proxy
+    auto phase_done = [&]() {
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(lead_e_done + (uint32_t)g * 8u);
+    };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + g * 4 + q) : "memory"); };
+
+    for (int64_t k = 0; k < cnt[g]; ++k) {
+      const int64_t tile = 2 * ((2 * k + g) * P + pair) + rank;
+      const int64_t row = tile * kTileM + r_tile;
+      const bool valid = row < a.rows;
+      const float* zrow = a.z_in + row * sh.D + sh.t_off + par * W;
+      TNF_STAMP(100);
+      float tv[W];
+#pragma unroll
+      for (int net = 0; net < 2; ++net) {
+#pragma unroll 1
+        for (int l = 0; l < sh.L; ++l) {
+          TNF_STAMP(200 + net * 10 + l);
+          mbar_wait(&ct.h_ready[g], h_par);
+          h_par ^= 1;
+          tc_fence_after();
+          TNF_STAMP(300 + net * 10 + l);
+#pragma unroll 1
+          for (int c = par; c < n_chunks; c += 2) epi_step(c);
+          phase_done();
+        }
+        // ---- final layer of this net: W columns per thread
+        float zin[W];
+        float ld_old = 0.f;
+        if (net == 1) {   // the transformed half and the old log-det arrive while the final-layer MMAs run
+#pragma unroll
+          for (int j = 0; j < W; j += 4) {
+            const float4 t4 = valid ? __ldg(reinterpret_cast<const float4*>(zrow + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            zin[j] = t4.x; zin[j + 1] = t4.y; zin[j + 2] = t4.z; zin[j + 3] = t4.w;
+          }
+          if (par == 0 && valid && a.accum != TNF_LD_WRITE) ld_old = a.log_det[row];
+        }
+        TNF_STAMP(400 + net);
+        mbar_wait(&ct.h_ready[g], h_par);
+        h_par ^= 1;
+        tc_fence_after();
+        TNF_STAMP(500 + net);
+        uint32_t o[W];
+        if (W == 16) tmem_ld16(hcol + (uint32_t)(par * W), reinterpret_cast<uint32_t(&)[16]>(o));
+        else tmem_ld32(hcol + (uint32_t)(par * W), reinterpret_cast<uint32_t(&)[32]>(o));
+        tc_wait_ld();
+        if (net == 0) {
+#pragma unroll
+          for (int j = 0; j < W; ++j) tv[j] = __uint_as_float(o[j]);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(lead_e_done + (uint32_t)g * 8u);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(lead_e_done + (uint32_t)g * 8u);   // accumulator free: the next tile's first job may start
+          float ld_sum = 0.f;
+          float (&y)[W] = zin;   // transformed in place
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            const int col = sh.t_off + par * W + j;
+            const float zz = fmaf(zin[j], s_pscale[col], s_pshift[col]);
+            const float sv = __uint_as_float(o[j]);
+            ld_sum += sv;
+            y[j] = kInverse ? (zz - tv[j]) * exp2_fast(-sv * kLog2e) : fmaf(zz, exp2_fast(sv * kLog2e), tv[j]);
+          }
+          TNF_STAMP(601);
+          if (valid) {
+            float* orow = a.z_out + row * sh.D + sh.t_off + par * W;
+#pragma unroll
+            for (int j = 0; j < W; j += 4)
+              *reinterpret_cast<float4*>(orow + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          }
+          if (par == 1) s_ldp[g * kTileM + r_tile] = ld_sum;
+          pair_sync();
+          if (par == 0 && valid) {
+            const float tot = ld_sum + s_ldp[g * kTileM + r_tile];
+            float* op = a.log_det + row;
+            if (a.accum == TNF_LD_WRITE) *op = tot;
+            else if (a.accum == TNF_LD_ADD) *op = ld_old + tot;
+            else *op = ld_old - tot;
+          }
+          if (want_stats) {
+            float s1[W], s2[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) { s1[j] = valid ? y[j] : 0.f; s2[j] = s1[j] * s1[j]; }
+            if (W == 16) {
+              st_y += warp_transpose_sum16(reinterpret_cast<float(&)[16]>(s1), lane);
+              st_y2 += warp_transpose_sum16(reinterpret_cast<float(&)[16]>(s2), lane);
+            } else {
+              st_y += warp_transpose_sum(reinterpret_cast<float(&)[32]>(s1), lane);
+              st_y2 += warp_transpose_sum(reinterpret_cast<float(&)[32]>(s2), lane);
+            }
+          }
+        }
+      }
+      TNF_STAMP(600);
+    }
+#undef TNF_STAMP
+    if (want_stats) {
+      __syncwarp();
+      asm volatile("bar.sync 9, %0;" ::"r"(kEpiWarps2 * 32) : "memory");   // all epilogue warps are past their last phase
+      double* rowp = stat_rows + (size_t)warp * 2 * sh.D;
+      for (int i = lane; i < 2 * sh.D; i += 32) rowp[i] = 0.0;
+      __syncwarp();
+      if (lane < W) {
+        rowp[sh.t_off + par * W + lane] = (double)st_y;
+        rowp[sh.D + sh.t_off + par * W + lane] = (double)st_y2;
+      }
+    }
+  } else {
+    // =============================== I/O warps: conditioning half, coalesced ===============================
+    const int w2 = warp - (kEpiWarps2 + 2);   // warps 18, 19
+    const int row0 = w2 * (kTileM / 2);
+    constexpr int LPR = DH / 4;          // lanes per row of the conditioning half (16 B each)
+    constexpr int RPI = 32 / LPR;        // rows per warp instruction
+    constexpr int NI = (kTileM / 2) / RPI;
+    const int hc = 4 * (lane % LPR);     // column inside the half
+    const int col = sh.c_off + hc;
+    const int rsub = lane / LPR;
+    const float4 ps = *reinterpret_cast<const float4*>(s_pscale + col);
+    const float4 pb = *reinterpret_cast<const float4*>(s_pshift + col);
+    auto load_tile = [&](int g, int64_t k) {
+      const int64_t tile = 2 * ((2 * k + g) * P + pair) + rank;
+      unsigned char* a1 = sA1 + (size_t)g * sh.a1_bytes();
+#pragma unroll 1
+      for (int n0 = 0; n0 < NI; n0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = row0 + (n0 + u) * RPI + rsub;
+          const int64_t grow = tile * kTileM + r;
+          v[u] = grow < a.rows ? __ldg(reinterpret_cast<const float4*>(a.z_in + grow * sh.D + col))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = row0 + (n0 + u) * RPI + rsub;
+          const int64_t grow = tile * kTileM + r;
+          float4 x;
+          x.x = fmaf(v[u].x, ps.x, pb.x); x.y = fmaf(v[u].y, ps.y, pb.y);
+          x.z = fmaf(v[u].z, ps.z, pb.z); x.w = fmaf(v[u].w, ps.w, pb.w);
+          *reinterpret_cast<uint2*>(a1 + img_off(r, hc, kTileM)) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+          if (grow < a.rows) {
+            *reinterpret_cast<float4*>(a.z_out + grow * sh.D + col) = x;
+            if (want_stats) {
+              io_sv1[0] += x.x; io_sv1[1] += x.y; io_sv1[2] += x.z; io_sv1[3] += x.w;
+              io_sv2[0] = fmaf(x.x, x.x, io_sv2[0]); io_sv2[1] = fmaf(x.y, x.y, io_sv2[1]);
+              io_sv2[2] = fmaf(x.z, x.z, io_sv2[2]); io_sv2[3] = fmaf(x.w, x.w, io_sv2[3]);
+            }
+          }
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(lead_a1_ready + (uint32_t)g * 8u);
+    };
+    for (int g = 0; g < 2; ++g)
+      if (cnt[g] > 0) load_tile(g, 0);
+    for (int64_t k = 0; k < cnt[0]; ++k) {
+      for (int g = 0; g < 2; ++g) {
+        if (k + 1 < cnt[g]) {
+          mbar_wait(&ct.a1_free[g], (uint32_t)(k & 1));   // layer-0 jobs of the group's tile k are done with the image
+          load_tile(g, k + 1);
+        }
+      }
+    }
+    if (want_stats) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+          io_sv1[e] += __shfl_xor_sync(0xffffffffu, io_sv1[e], o);
+          io_sv2[e] += __shfl_xor_sync(0xffffffffu, io_sv2[e], o);
+        }
+      }
+    }
+  }
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (want_stats) {
+    // gather: one [2*D] row of doubles per CTA = fixed-order sum over the epilogue warps' rows and the I/O warps' sums
+    if (warp == kEpiWarps2 + 2 || warp == kEpiWarps2 + 3) {   // I/O warps: expand their sums into rows kEpiWarps2 + w2
+      const int w2 = warp - (kEpiWarps2 + 2);
+      constexpr int LPR = DH / 4;
+      double* rowp = stat_rows + (size_t)(kEpiWarps2 + w2) * 2 * sh.D;
+      for (int i = lane; i < 2 * sh.D; i += 32) rowp[i] = 0.0;
+      __syncwarp();
+      if (lane < LPR) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          rowp[sh.c_off + 4 * lane + e] = (double)io_sv1[e];
+          rowp[sh.D + sh.c_off + 4 * lane + e] = (double)io_sv2[e];
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * sh.D; i += blockDim.x) {
+      double acc = 0.0;
+      for (int w = 0; w < kStatWarps; ++w) acc += stat_rows[(size_t)w * 2 * sh.D + i];
+      a.stat_partials[(size_t)blockIdx.x * 2 * sh.D + i] = acc;
+    }
+  }
+  cluster_sync_all();   // no CTA leaves (or frees TMEM) while its partner can still signal it
+  if (warp == kEpiWarps2) tmem_dealloc2(tmem, 512);
+}
+
+int launch_tc4(const Args& a, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+#define TNF_TC4_LAUNCH(INV, DHV, UV)                                                                              \
+  do {                                                                                                            \
+    e = cudaFuncSetAttribute(coupling_tc4_kernel<INV, DHV, UV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                             (int)smem);                                                                          \
+    if (e == cudaSuccess) coupling_tc4_kernel<INV, DHV, UV><<<grid, kThreads4, smem, st>>>(a);                    \
+  } while (0)
+#define TNF_TC4_U(INV, DHV)                                   \
+  do {                                                        \
+    if (a.U == 256) TNF_TC4_LAUNCH(INV, DHV, 256);            \
+    else if (a.U == 128) TNF_TC4_LAUNCH(INV, DHV, 128);       \
+    else TNF_TC4_LAUNCH(INV, DHV, 64);                        \
+  } while (0)
+  if (a.D == 64) { if (a.inverse) TNF_TC4_U(true, 32); else TNF_TC4_U(false, 32); }
+  else { if (a.inverse) TNF_TC4_U(true, 64); else TNF_TC4_U(false, 64); }
+#undef TNF_TC4_U
+#undef TNF_TC4_LAUNCH
+  return (int)e;
+}
+
+}  // namespace tc
+}  // namespace tnf

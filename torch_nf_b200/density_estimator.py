@@ -196,12 +196,13 @@ class NormFlow(DensityEstimator):
         log_q_z (M,N) float64)`` on the device of ``params``."""
         home = params.device
         pd = ops.to_device(params, torch.float32)
+        self._check_params(pd)
         M = pd.size(0)
         z, log_q = self._base(M, N, pd.device, omega)
         if torch.is_grad_enabled() and pd.requires_grad:
             z, log_q = self._forward_autograd(z, log_q, pd, freeze_bn)
         else:
-            z, log_q = self._forward_plan(z, log_q, pd.detach(), freeze_bn, home)
+            z, log_q = self._forward_plan(z, log_q, pd.detach(), freeze_bn, home, src=params)
         return _to(z, home), _to(log_q, home)
 
     def _base(self, M, N, device, omega):
@@ -231,14 +232,30 @@ class NormFlow(DensityEstimator):
                 and b.name == "RealNVP" and z.shape[0] * z.shape[1] >= config.tc_min_rows()
                 and ops.tc_supported(b.D, b.num_units, b.num_layers))
 
-    def _packed(self, b, idx, n, pd):
-        key = (id(b), pd.data_ptr(), pd._version, idx)
-        hit = self._tc_cache.get(id(b))
-        if hit is not None and hit[0] == key:
-            return hit[1]
+    def _packed(self, b, idx, n, pd, src=None):
+        """Packed tensor-core operand images of bijector ``b``'s weights (``pd[0, idx:idx+n]``).
+
+        Cached per bijector, keyed on the CALLER's parameter tensor ``src``: the entry holds a strong reference to
+        it (its address cannot be recycled by another tensor while the entry lives) and is valid only for that very
+        object at the same in-place version.  A device copy made for this call (``pd`` when ``src`` lives on the
+        host) is never a key: the caching allocator hands its address out again.  Without ``src`` the weights are
+        repacked (one ~60 us kernel per layer)."""
+        mode = config.conditioner_precision()
+        if src is not None:
+            hit = self._tc_cache.get(id(b))
+            if (hit is not None and hit[0] is src and hit[1] == src._version and hit[2] == (idx, mode)
+                    and hit[3].device == pd.device):
+                return hit[3]
         packed = ops.tc_pack(pd[0, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper)
-        self._tc_cache[id(b)] = (key, packed)
+        if src is not None:
+            self._tc_cache[id(b)] = (src, src._version, (idx, mode), packed)
         return packed
+
+    def _check_params(self, pd):
+        """The reference's ``params[:, idx:idx+n].view(...)`` raises on a short parameter matrix
+        (bijectors.py:224-235); the kernels would read out of bounds instead."""
+        if pd.dim() != 2 or pd.shape[1] < self.D_params:
+            raise ValueError("NormFlow needs a (M, >=%d) parameter matrix, got %s" % (self.D_params, tuple(pd.shape)))
 
     def _can_fold(self, pd, z):
         """BatchNorm / Affine are folded into the next tensor-core coupling kernel when every coupling
@@ -246,7 +263,7 @@ class NormFlow(DensityEstimator):
         cps = [b for b in self.bijectors if b.name == "RealNVP"]
         return bool(cps) and all(self._use_tc(b, pd, z) for b in cps)
 
-    def _forward_plan(self, z, log_q, pd, freeze_bn, home=None):
+    def _forward_plan(self, z, log_q, pd, freeze_bn, home=None, src=None):
         M, N, D = z.shape
         Mp = pd.shape[0]
         ld_acc = torch.zeros((M, N), dtype=torch.float32, device=z.device)
@@ -260,7 +277,7 @@ class NormFlow(DensityEstimator):
                 if self._use_tc(b, pd, z):
                     nxt = slices[i + 1][0].name if i + 1 < len(slices) else None
                     fuse_stats = (nxt == "BatchNorm" and not freeze_bn and D <= 128)
-                    res = ops.coupling_tc(z, self._packed(b, idx, n, pd), b.D, b.num_units, b.num_layers,
+                    res = ops.coupling_tc(z, self._packed(b, idx, n, pd, src), b.D, b.num_units, b.num_layers,
                                           b.transform_upper, TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD,
                                           pre_scale=pend[0] if pend else None, pre_shift=pend[1] if pend else None,
                                           want_stats=fuse_stats)
@@ -334,24 +351,27 @@ class NormFlow(DensityEstimator):
         home = z.device
         zd = ops.to_device(z if z.dtype in (torch.float32, torch.float64) else z.float())
         pd = ops.to_device(params, zd.dtype)
+        self._check_params(pd)
         if torch.is_grad_enabled() and (pd.requires_grad or zd.requires_grad):
             z0, sld = self._inverse_autograd(zd, pd)
         else:
-            z0, ld_acc, scal, div = self._inverse_plan(zd.detach().contiguous(), pd.detach())
+            z0, ld_acc, scal, div = self._inverse_plan(zd.detach().contiguous(), pd.detach(), src=params)
             sld = ops.accum_bcast(ld_acc, scal, div)
         return _to(z0, home), _to(sld, home)
 
-    def _inverse_plan(self, z, pd):
+    def _inverse_plan(self, z, pd, src=None, use_tc=None):
+        """``use_tc``: tensor-core eligibility decided by the caller on the WHOLE batch (the host pipeline hands in
+        row chunks; a chunk must not pick a different precision path than the one-shot call would)."""
         M, N, D = z.shape
         Mp = pd.shape[0]
         ld_acc = torch.zeros((M, N), dtype=z.dtype, device=z.device)
         scal = torch.zeros(Mp, dtype=z.dtype, device=z.device)
-        fold = self._can_fold(pd, z)
+        fold = self._can_fold(pd, z) if use_tc is None else use_tc
         pend = None
         for (b, idx, n) in reversed(self._slices()):
             if b.name == "RealNVP":
-                if self._use_tc(b, pd, z):
-                    z, _ = ops.coupling_tc(z, self._packed(b, idx, n, pd), b.D, b.num_units, b.num_layers,
+                if (self._use_tc(b, pd, z) if use_tc is None else use_tc):
+                    z, _ = ops.coupling_tc(z, self._packed(b, idx, n, pd, src), b.D, b.num_units, b.num_layers,
                                            b.transform_upper, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD,
                                            pre_scale=pend[0] if pend else None, pre_shift=pend[1] if pend else None)
                     pend = None
@@ -402,7 +422,7 @@ class NormFlow(DensityEstimator):
             sum_log_det = sum_log_det + log_det
         return z, sum_log_det
 
-    def _log_prob_host_pipelined(self, z, pd):
+    def _log_prob_host_pipelined(self, z, pd, src=None):
         """``log_prob`` of host samples ``z (1, N, D)`` in row chunks: the host->device copy of chunk i+1 (copy stream)
         overlaps the inverse chain of chunk i (current stream).  Exact: no bijector couples samples in this direction
         (BatchNorm.inverse_and_log_det uses its stored statistics, bijectors.py:420-426)."""
@@ -418,6 +438,7 @@ class NormFlow(DensityEstimator):
         ready.record(compute)                                  # zd's block may still be in use by earlier kernels
         copy.wait_event(ready)
         bounds = [(lo, min(N, lo + step)) for lo in range(0, N, step)]
+        use_tc = self._can_fold(pd, z)        # decided once, on the full batch
 
         def issue_copy(lo, hi):
             with torch.cuda.stream(copy):
@@ -429,7 +450,7 @@ class NormFlow(DensityEstimator):
         ev = issue_copy(*bounds[0])
         for i, (lo, hi) in enumerate(bounds):
             compute.wait_event(ev)
-            z0, ld_acc, scal, div = self._inverse_plan(zd[:, lo:hi], pd)
+            z0, ld_acc, scal, div = self._inverse_plan(zd[:, lo:hi], pd, src=src, use_tc=use_tc)
             lp[:, lo:hi] = ops.base_logprob(z0, ld_acc, scal, div)
             if i + 1 < len(bounds):                            # queued after chunk i's kernels: a pageable source blocks
                 ev = issue_copy(*bounds[i + 1])                # the host here while the GPU works on chunk i
@@ -446,14 +467,17 @@ class NormFlow(DensityEstimator):
         if (not z.is_cuda and not needs_grad and z.dim() == 3 and z.shape[0] == 1 and params.shape[0] == 1
                 and z.shape[1] >= config.host_pipeline_min_rows() and config.host_pipeline_chunks() > 1):
             ops.require_cuda()
-            return _to(self._log_prob_host_pipelined(z.detach().contiguous(), ops.to_device(params.detach(), z.dtype)), home)
+            pd = ops.to_device(params.detach(), z.dtype)
+            self._check_params(pd)
+            return _to(self._log_prob_host_pipelined(z.detach().contiguous(), pd, src=params), home)
         zd = ops.to_device(z)
         pd = ops.to_device(params, zd.dtype)
+        self._check_params(pd)
         if torch.is_grad_enabled() and (pd.requires_grad or zd.requires_grad):
             z0, sld = self._inverse_autograd(zd, pd)
             lp = _BaseLogProbFn.apply(z0) - sld
         else:
-            z0, ld_acc, scal, div = self._inverse_plan(zd.detach().contiguous(), pd.detach())
+            z0, ld_acc, scal, div = self._inverse_plan(zd.detach().contiguous(), pd.detach(), src=params)
             lp = ops.base_logprob(z0, ld_acc, scal, div)
         return _to(lp, home)
 

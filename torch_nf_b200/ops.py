@@ -100,11 +100,18 @@ def _match_rows(z, params):
 
 
 # ----------------------------------------------------------------- coupling
+def coupling_num_params(D, U, L, upper):
+    """Parameters one RealNVP layer consumes (reference bijectors.py:244-262)."""
+    h = D // 2
+    d_in, d_out = (h, D - h) if upper else (D - h, h)
+    return 2 * (d_in * U + d_out * U + d_out + U + (L - 1) * (U + 1) * U)
+
+
 def coupling(z, params, D, U, L, upper, direction, ld=None, accum=TNF_LD_WRITE):
     """RealNVP layer on the exact CUDA-core path. Returns (z_out, log_det (M,N))."""
     z = _check3(z)
     M, N, _ = z.shape
-    params, pstride = param_view(params, 0)
+    params, pstride = param_view(params, coupling_num_params(D, U, L, upper))
     Mp = _match_rows(z, params)
     z_out = torch.empty_like(z)
     if ld is None:
@@ -121,7 +128,7 @@ def coupling_bwd(z_in, params, g_z_out, g_ld, g_params, D, U, L, upper, directio
     """Accumulates into ``g_params`` (same row layout as ``params``); returns g_z_in."""
     z_in = _check3(z_in)
     M, N, _ = z_in.shape
-    params, pstride = param_view(params, 0)
+    params, pstride = param_view(params, coupling_num_params(D, U, L, upper))
     Mp = _match_rows(z_in, params)
     assert g_params.shape[0] == Mp and (g_params.shape[1] <= 1 or g_params.stride(1) == 1)
     gstride = g_params.stride(0) if Mp > 1 else 0
@@ -175,20 +182,29 @@ def tc_supported(D, U, L):
     return bool(_lib.lib().tnf_tc_supported(D, U, L))
 
 
-def tc_pack(params_row, D, U, L, upper):
-    """fp32 parameter row -> packed bf16 UMMA operand image (+ fp32 biases)."""
-    nbytes = _lib.lib().tnf_tc_packed_bytes(D, U, L)
+TC_PRECISION = {"bf16": _lib.TNF_TC_BF16, "fp32_tc": _lib.TNF_TC_FP32}
+
+
+def tc_pack(params_row, D, U, L, upper, precision="bf16"):
+    """fp32 parameter row -> packed UMMA operand images (bf16, or fp16 hi/lo for the fp32-parity mode)."""
+    nbytes = _lib.lib().tnf_tc_packed_bytes(D, U, L, TC_PRECISION[precision])
+    if nbytes == 0:
+        raise ValueError("tensor-core path: D=%d U=%d L=%d precision=%s not supported" % (D, U, L, precision))
     packed = torch.empty(nbytes, dtype=torch.uint8, device=params_row.device)
     p = params_row.reshape(-1)
+    need = coupling_num_params(D, U, L, upper)
+    if p.numel() < need:
+        raise ValueError("tc_pack: parameter row has %d values, the layer needs %d" % (p.numel(), need))
     if p.dtype != torch.float32 or not p.is_contiguous():
         p = p.float().contiguous()
-    rc = _lib.lib().tnf_tc_pack(p.data_ptr(), packed.data_ptr(), D, U, L, int(upper), _stream())
+    rc = _lib.lib().tnf_tc_pack(p.data_ptr(), packed.data_ptr(), D, U, L, int(upper), TC_PRECISION[precision],
+                                _stream())
     _lib.check(rc, "tnf_tc_pack")
     return packed
 
 
 def coupling_tc(z, packed, D, U, L, upper, direction, ld=None, accum=TNF_LD_WRITE, pre_scale=None, pre_shift=None,
-                want_stats=False, out=None):
+                want_stats=False, out=None, precision="bf16", variant=0, debug=None):
     """Returns (z_out, log_det) or, with ``want_stats`` (D <= 128), (z_out, log_det, sums) where ``sums`` is the
     float64 [sum | sumsq | rows] buffer of the OUTPUT columns (the next BatchNorm's statistics)."""
     z2 = z.reshape(-1, D)
@@ -209,7 +225,7 @@ def coupling_tc(z, packed, D, U, L, upper, direction, ld=None, accum=TNF_LD_WRIT
         e0.record()
     rc = _lib.lib().tnf_coupling_tc(z2.data_ptr(), z_out.data_ptr(), ld.data_ptr(), packed.data_ptr(), rows, D, U, L,
                                     int(upper), direction, accum, _ptr(pre_scale), _ptr(pre_shift), _ptr(sums),
-                                    _ptr(ws), _stream())
+                                    _ptr(ws), TC_PRECISION[precision], int(variant), _ptr(debug), _stream())
     if timer is not None:
         e1.record()
         timer.append((e0, e1))
@@ -256,7 +272,9 @@ _ws_cache = {}
 
 
 def _workspace(D, device):
-    key = (D, device)
+    """Per-CTA partial sums of the column-statistics kernels.  One buffer per (D, device, STREAM): launches on
+    different streams must not share partials; launches on one stream are ordered."""
+    key = (D, device, torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None:
         ws = torch.empty(_lib.lib().tnf_colstats_workspace_bytes(D), dtype=torch.uint8, device=device)
