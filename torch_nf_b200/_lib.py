@@ -84,7 +84,7 @@ def lib():
         fn = getattr(handle, name)   # AttributeError = missing symbol: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if handle.tnf_abi_version() != 1:
+    if handle.tnf_abi_version() != 2:
         raise RuntimeError("torch_nf_b200: ABI version mismatch")
     _LIB = handle
     return _LIB
