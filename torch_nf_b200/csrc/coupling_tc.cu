@@ -79,6 +79,11 @@ __global__ void pack_kernel(const float* __restrict__ params, unsigned char* __r
     *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(w);
     const int NB = J / 2;   // split-N copy for the CTA-pair kernel
     *reinterpret_cast<__nv_bfloat16*>(packed + sh.split_w_off(l, net, j / NB) + img_off(j % NB, k, NB)) = __float2bfloat16_rn(w);
+    if (sh.L >= 2 && l == sh.L - 1) {   // N-half copy of the last hidden layer: half h = j / (U/2), rank = (j / (U/4)) % 2
+      const int Q = sh.U / 4;
+      *reinterpret_cast<__nv_bfloat16*>(packed + sh.half_w_off(net, j / (2 * Q), (j / Q) & 1) + img_off(j % Q, k, Q)) =
+          __float2bfloat16_rn(w);
+    }
   }
   const int nb = sh.net_bias_elems();
   float* bias_dst = reinterpret_cast<float*>(packed + 2 * per_net * 2);
@@ -103,6 +108,16 @@ __global__ void pack_kernel(const float* __restrict__ params, unsigned char* __r
       const __nv_bfloat16 v = kk == 0 ? hi : (kk == 1 ? lo : __float2bfloat16_rn(0.f));
       *reinterpret_cast<__nv_bfloat16*>(img + img_off(rem, kk, J)) = v;
       *reinterpret_cast<__nv_bfloat16*>(img2 + img_off(rem % (J / 2), kk, J / 2)) = v;
+    }
+    if (sh.L >= 2) {   // resident 8-K-row bias blocks of coupling_tc5_kernel
+      const bool split = l == sh.L - 1;
+      const int Q = sh.U / 4;
+      const int rk = split ? (rem / Q) & 1 : rem / (J / 2);
+      const int h = split ? rem / (2 * Q) : 0;
+      const int n = split ? rem % Q : rem % (J / 2);
+      __nv_bfloat16* blk = reinterpret_cast<__nv_bfloat16*>(packed + sh.bias8_base(rk) + sh.bias8_off(l, net, h) + (int64_t)n * 16);
+      blk[0] = hi; blk[1] = lo;
+      for (int kk = 2; kk < 8; ++kk) blk[kk] = __float2bfloat16_rn(0.f);
     }
   }
 }
@@ -1576,6 +1591,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   // kernel choice: D <= 128 -> two-tile kernel; D = 256 -> single-tile pipelined kernel; variant 1 -> the first kernel
   const bool pingpong2 = tc::shape_supported2(D, U, L) && g_tc_variant != 1;
   const bool pairs = pingpong2 && g_tc_variant != 2;      // clusters of two CTAs sharing the weight operands
+  const bool pairs5 = pairs && g_tc_variant == 3 && tc::shape_supported5(D, U, L);   // N-half / TMEM-fed variant
   const bool pipelined = D == 256 && g_tc_variant != 1;
   if (pairs) {   // one 256-row super tile per CTA pair and group; the grid is a whole number of pairs
     const int64_t n_super = (n_tiles + 1) / 2;
@@ -1585,7 +1601,10 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   // as many 16 KB weight stages as fit next to the activation images (227 KB per CTA)
   int n_stages = tc::kMaxStages;
   size_t smem;
-  if (pairs) {
+  if (pairs5) {
+    while (n_stages > 2 && tc::smem_bytes5(sh, n_stages) > 227 * 1024) --n_stages;
+    smem = tc::smem_bytes5(sh, n_stages);
+  } else if (pairs) {
     while (n_stages > 2 && tc::smem_bytes4(sh, n_stages) > 227 * 1024) --n_stages;
     smem = tc::smem_bytes4(sh, n_stages);
   } else if (pingpong2) {
@@ -1600,7 +1619,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   }
   TNF_REQUIRE(smem <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem);
   tc::Args a{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
-             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_groups,
+             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_groups, variant >> 8,
              col_stats ? (double*)stats_workspace : nullptr, g_tc_debug};
 #define TNF_TC_LAUNCH(KERNEL, THREADS, INV, DHV)                                                              \
   do {                                                                                                        \
@@ -1622,7 +1641,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   int stat_blocks = grid * tc::kEpiWarps;
   if (pairs) {
     stat_blocks = grid;
-    e = (cudaError_t)tc::launch_tc4(a, grid, smem, st);
+    e = (cudaError_t)(pairs5 ? tc::launch_tc5(a, grid, smem, st) : tc::launch_tc4(a, grid, smem, st));
   } else if (pingpong2) {
     stat_blocks = grid;
     if (D == 64) { if (inv) TNF_TCU(coupling_tc3_kernel, tc::kThreads3, true, 32); else TNF_TCU(coupling_tc3_kernel, tc::kThreads3, false, 32); }

@@ -1,49 +1,67 @@
-// RealNVP coupling layer on tcgen05 tensor cores: the CTA-pair two-tile kernel (product path for D <= 128).
+// RealNVP coupling layer on tcgen05 tensor cores: the CTA-pair two-tile kernel with
+//   * the LAST hidden job (layer L-1, L >= 2) issued as two N = U/2 halves, each with its own commit: the group's
+//     tanh phase starts on the first half of the accumulator while the tensor pipe computes the second half;
+//   * the output of that tanh phase written back as bf16 INTO the accumulator columns it has just consumed
+//     (tcgen05.st) and the final-layer MMAs fed from tensor memory (A operand in TMEM): no st.shared / shared-memory
+//     A reads for that layer, and no write-after-read hazard on the activation image the second half still reads.
+// Everything else is coupling_tc4_kernel (coupling_tc4.cu).
 // Shared definitions: tc_common.cuh.  Reference semantics: torch_nf/bijectors.py:145-242 (RealNVP).
 #include "tc_common.cuh"
 
 namespace tnf {
 namespace tc {
 
-template <int K, int N>
-__device__ __forceinline__ void mma_job2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo_ring, uint32_t b_hi,
-                                         uint32_t ones_lo, uint32_t wfull0, uint32_t wpeer0, uint32_t wempty0, uint32_t S,
-                                         uint32_t& slot, uint32_t& phase, bool leader, long long* t_w = nullptr) {
+// TMEM column (relative to the group's accumulator) of the 8 packed bf16 columns holding the activations of units
+// [16*kk, 16*kk + 16) after the last tanh phase: chunk c = kk/2 of parity p = ci%2 (ci = index inside its N-half h)
+// was written by its own warp to (U/2)*h + 32*p + 16*(ci/2)  -- columns that warp had already consumed.
+template <int U_>
+__host__ __device__ constexpr uint32_t act_col5(int kk) {
+  const int nc = U_ / kChunk, c = kk / 2, sub = kk % 2;
+  const int h = c / (nc / 2), ci = c % (nc / 2), p = ci % 2, i = ci / 2;
+  return (uint32_t)((U_ / 2) * h + 32 * p + 16 * i + 8 * sub);
+}
+template <int U_>
+__host__ __device__ constexpr uint32_t fin_col5() { return U_ == 256 ? 64u : 128u; }   // free columns for the final accumulator
+
+constexpr uint32_t kStages5 = 4;   // weight ring depth (compile-time: slot = counter & 3)
+
+// One GEMM job of the MMA warp (see mma_job in coupling_tc.cu): the bias MMA first (accumulator := ones image x the
+// job's RESIDENT bias block, no barrier), then per 32-wide K chunk two K=16 MMAs with compile-time descriptor offsets,
+// an mbarrier wait pair (own stage landed / partner's stage landed) when a weight stage begins and a commit when it
+// is used up.  `cnt` counts ring stages since kernel start: slot = cnt & 3, parity = (cnt >> 2) & 1.
+template <int K, int N, bool kTS, int U_>
+__device__ __forceinline__ void mma_job5(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo_ring, uint32_t b_hi,
+                                         uint32_t ones_lo, uint32_t bias_lo, uint32_t wfull0, uint32_t wpeer0,
+                                         uint32_t wempty0, uint32_t& cnt, bool leader, long long* t_w) {
   constexpr int NB = N / 2;                                            // B rows held per CTA
   constexpr int KS = (kStageElems / NB) < K ? (kStageElems / NB) : K;  // K rows per weight stage
   constexpr int CPS = KS / kChunk;                                     // chunks per stage
   constexpr uint32_t kStage16 = kStageBytes >> 4;
   const uint32_t idesc = make_idesc2(N);
-  {
-    const long long c0 = t_w ? clock64() : 0;
-    mbar_wait_addr(wfull0 + slot * 8u, phase);
-    mbar_wait_addr(wpeer0 + slot * 8u, phase);
-    if (t_w) *t_w += clock64() - c0;
-    tc_fence_after();
-    if (leader) {
-      umma2_ss2(d_tmem, ones_lo, a_hi, b_lo_ring + slot * kStage16, b_hi, idesc, 0u);
-      tc_commit2_addr(wempty0 + slot * 8u);
-    }
-    if (++slot == S) { slot = 0; phase ^= 1; }
-  }
+  if (leader) umma2_ss2(d_tmem, ones_lo, a_hi, bias_lo, b_hi, idesc, 0u);
 #pragma unroll
   for (int c = 0; c < K / kChunk; ++c) {
+    const uint32_t slot = cnt & (kStages5 - 1);
     if (c % CPS == 0) {
       const long long c0 = t_w ? clock64() : 0;
-      mbar_wait_addr(wfull0 + slot * 8u, phase);
-      mbar_wait_addr(wpeer0 + slot * 8u, phase);
+      const uint32_t par = (cnt >> 2) & 1u;
+      mbar_wait_addr(wfull0 + slot * 8u, par);
+      mbar_wait_addr(wpeer0 + slot * 8u, par);
       if (t_w) *t_w += clock64() - c0;
       tc_fence_after();
     }
     if (leader) {
       const uint32_t b_lo = b_lo_ring + slot * kStage16 + (uint32_t)((c % CPS) * 4 * NB);
-      umma2_ss2(d_tmem, a_lo + 512u * c, a_hi, b_lo, b_hi, idesc, 1u);
-      umma2_ss2(d_tmem, a_lo + 512u * c + 256u, a_hi, b_lo + 2u * NB, b_hi, idesc, 1u);
+      if (kTS) {   // A operand = the bf16 activations the last tanh phase left in the accumulator's own columns
+        umma2_ts2(d_tmem, a_lo + act_col5<U_>(2 * c), b_lo, b_hi, idesc, 1u);
+        umma2_ts2(d_tmem, a_lo + act_col5<U_>(2 * c + 1), b_lo + 2u * NB, b_hi, idesc, 1u);
+      } else {
+        umma2_ss2(d_tmem, a_lo + 512u * c, a_hi, b_lo, b_hi, idesc, 1u);
+        umma2_ss2(d_tmem, a_lo + 512u * c + 256u, a_hi, b_lo + 2u * NB, b_hi, idesc, 1u);
+      }
       if (c % CPS == CPS - 1) tc_commit2_addr(wempty0 + slot * 8u);
     }
-    if (c % CPS == CPS - 1) {
-      if (++slot == S) { slot = 0; phase ^= 1; }
-    }
+    if (c % CPS == CPS - 1) ++cnt;
   }
 }
 
@@ -63,9 +81,9 @@ __device__ __forceinline__ void mma_job2(uint32_t d_tmem, uint32_t a_lo, uint32_
 // the tensor pipe - and the other group, half a tile out of phase, fills each pipe in the gaps.  Weights and the
 // bias operand images stream through the ring in the static job order of the MMA warp; biases are added by a bias
 // MMA (see mma_job), global I/O of the conditioning half is done by two dedicated warps with coalesced accesses.
-constexpr int kThreads4 = (kEpiWarps2 + 4) * 32;   // 16 epilogue, MMA, producer, 2 I/O
+constexpr int kThreads5 = (kEpiWarps2 + 4) * 32;   // 16 epilogue, MMA, producer, 2 I/O
 
-struct __align__(16) Ctrl4 {
+struct __align__(16) Ctrl5 {
   uint64_t w_full[kMaxStages];
   uint64_t w_empty[kMaxStages];
   uint64_t w_peer[kMaxStages];   // leader only: the second CTA's half of the stage has landed (forwarded by its MMA warp)
@@ -73,31 +91,36 @@ struct __align__(16) Ctrl4 {
   uint64_t a1_free[2];    // per group, tcgen05.commit: both layer-0 jobs of the tile have read the A1 image
   uint64_t e_done[2];     // per group, 8 epilogue warps: accumulator drained (and activation image written)
   uint64_t h_ready[2];    // per group, tcgen05.commit: accumulator of the group's current job complete
+  uint64_t h_ready_b[2];  // per group, tcgen05.commit: second N-half of the split job complete
   uint32_t tmem_base;
   uint32_t pad;
 };
 // dynamic shared memory:
-//   [ring: n_stages x 16 KB][A1 g0][A1 g1][Act g0][Act g1][ones 4 KB][Ctrl4][pre_scale D][pre_shift D][ld partial 2 x 128]
-size_t smem_bytes4(const Shape& sh, int n_stages) {
-  return (size_t)n_stages * sh.stage_elems() * 2 + 2 * sh.a1_bytes() + 2 * sh.act_bytes() + kOnesBytes + sizeof(Ctrl4) +
-         (size_t)(2 * sh.D + 2 * kTileM) * sizeof(float);
+//   [ring: 4 x 16 KB][A1 g0][A1 g1][Act g0][Act g1][ones 4 KB][Ctrl5][pre_scale D][pre_shift D][ld partial 2 x 128]
+//   [resident bias blocks of this rank][2 KB zeros]
+constexpr int kBiasPad5 = 2048;   // zero block after the resident bias region (second K group of the last bias MMA)
+size_t smem_bytes5(const Shape& sh, int n_stages) {
+  return (size_t)n_stages * sh.stage_elems() * 2 + 2 * sh.a1_bytes() + 2 * sh.act_bytes() + kOnesBytes + sizeof(Ctrl5) +
+         (size_t)(2 * sh.D + 2 * kTileM) * sizeof(float) + (size_t)sh.bias8_rank_bytes() + kBiasPad5;
 }
 
 // FT: of every 8 activations, FT are evaluated by tanh_poly on the FMA pipe, the rest by MUFU.TANH
-template <bool kInverse, int DH, int U_, int FT>   // DH = D/2 = d_in = d_out in {32, 64}; U_ = hidden units
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupling_tc4_kernel(Args a) {
+template <bool kInverse, int DH, int U_, int FT>   // DH = D/2 = d_in = d_out in {32, 64}; U_ = hidden units; L = 2
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupling_tc5_kernel(Args a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const Shape sh(a.D, a.U, a.L, a.upper);
-  const int S = a.n_stages;
+  constexpr int L_ = 2;
+  const Shape sh(a.D, a.U, L_, a.upper);
+  constexpr int S = (int)kStages5;
   unsigned char* ring = smem_raw;
   const uint32_t stage_bytes = (uint32_t)sh.stage_elems() * 2;
   unsigned char* sA1 = ring + (size_t)S * stage_bytes;             // 2 images (group)
   unsigned char* sAct = sA1 + 2 * sh.a1_bytes();                    // 2 images (group)
   unsigned char* sOnes = sAct + 2 * sh.act_bytes();                 // constant A image for the bias MMA
-  Ctrl4& ct = *reinterpret_cast<Ctrl4*>(sOnes + kOnesBytes);
-  float* s_pscale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl4));
+  Ctrl5& ct = *reinterpret_cast<Ctrl5*>(sOnes + kOnesBytes);
+  float* s_pscale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl5));
   float* s_pshift = s_pscale + sh.D;
   float* s_ldp = s_pshift + sh.D;
+  unsigned char* sBias = reinterpret_cast<unsigned char*>(s_ldp + 2 * kTileM);   // resident bias blocks (+ zero pad)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
@@ -112,8 +135,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
     cnt[g] = first < n_super ? (n_super - first + 2 * P - 1) / (2 * P) : 0;
   }
   constexpr int n_chunks = U_ / kChunk;
-  const int JT = 2 * (sh.L + 1);     // jobs per tile
-  const int shift = sh.L;            // group 1 runs this many jobs behind group 0 (L = 2: shifts 1..5 measured, 2 is best)
+  constexpr int JT = 2 * (L_ + 1);   // jobs per tile: t0 t1 tF s0 s1 sF
+  constexpr int SH = L_;             // group 1 runs this many jobs behind group 0 (shifts 1..5 measured, 2 is best)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&ct.w_full[i], 1); mbar_init(&ct.w_empty[i], 1); mbar_init(&ct.w_peer[i], 1); }
@@ -122,6 +145,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
       mbar_init(&ct.a1_free[g], 1);
       mbar_init(&ct.e_done[g], kEpiWarps2);           // the group's epilogue warps of both CTAs (leader's barrier)
       mbar_init(&ct.h_ready[g], 1);
+      mbar_init(&ct.h_ready_b[g], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -134,6 +158,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
       s_pscale[i] = a.pre_scale ? a.pre_scale[i] : 1.0f;
       s_pshift[i] = a.pre_shift ? a.pre_shift[i] : 0.0f;
     }
+    const int nb16 = (int)(sh.bias8_rank_bytes() / 16);
+    const uint4* gb = reinterpret_cast<const uint4*>(a.packed + sh.bias8_base((int)cluster_ctarank()));
+    for (int i = threadIdx.x; i < nb16 + kBiasPad5 / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(sBias)[i] = i < nb16 ? __ldg(gb + i) : make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -149,78 +178,74 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
   double* stat_rows = reinterpret_cast<double*>(sAct);
   constexpr int kStatWarps = kEpiWarps2 + 2;
 
+  // Static job schedule (L = 2): per tile and group six jobs j = 0..5 = t0 t1 tF s0 s1 sF (net j/3, layer j%3); step
+  // n = it*6 + s serves group 0's job s of its tile `it`, then group 1's job (s-2) mod 6 of its tile it (s >= 2) or
+  // it-1.  The three control warps walk the same sequence with the job type a compile-time constant.
+#define TNF_FOR_JOBS(...)                                                               \
+  for (int64_t it = 0; it <= cnt[0]; ++it) {                                            \
+    _Pragma("unroll") for (int s = 0; s < JT; ++s) {                                    \
+      if (it < cnt[0]) { constexpr int g = 0; const int j = s; __VA_ARGS__ }                   \
+      {                                                                                 \
+        const int64_t t1 = s >= SH ? it : it - 1;                                       \
+        if (t1 >= 0 && t1 < cnt[1]) { constexpr int g = 1; const int j = (s + JT - SH) % JT; __VA_ARGS__ } \
+      }                                                                                 \
+    }                                                                                   \
+  }
   if (warp == kEpiWarps2 + 1) {
     // =============================== weight producer (one elected lane) ===============================
-    // streams THIS CTA's half of every stage (N/2 of the N weight columns, 64 K rows per 16 KB slot at N = 256)
+    // streams THIS CTA's half of every weight stage; biases are resident.  Stages per job: t0/s0 one (DH x U/2), t1/s1
+    // 2 x K/KSh (two N-halves of U x U/4), tF/sF one (U x DH/2)
     if (elect_one()) {
-      uint32_t slot = 0, phase = 0;
-      const int64_t n_steps = cnt[0] * JT + shift;
-      // per-group job counters kept incrementally: no 64-bit division in the scheduling loops (a lone warp spends
-      // hundreds of cycles on one)
-      int jj2[2] = {0, 0};
-      const int64_t total[2] = {cnt[0] * JT, cnt[1] * JT};
-      int64_t todo[2] = {total[0], total[1]};
-      for (int64_t n = 0; n < n_steps; ++n) {
-        for (int g = 0; g < 2; ++g) {
-          if ((g == 1 && n < shift) || todo[g] == 0) continue;
-          const int jj = jj2[g];
-          const bool first_job = todo[g] == total[g];
-          --todo[g];
-          if (++jj2[g] == JT) jj2[g] = 0;
-          const int net = jj > sh.L ? 1 : 0, l = jj > sh.L ? jj - (sh.L + 1) : jj;
-          (void)first_job; (void)net;
-          const int K = sh.K_of(l), NB = sh.J_of(l) / 2;
-          const int ks = (kStageElems / NB) < K ? (kStageElems / NB) : K;
-          const uint32_t bytes = (uint32_t)(ks * NB * 2);
-          const unsigned char* nsrc = a.packed + sh.split_w_off(l, net, (int)rank);
-          {   // the job's bias operand image travels as a stage of its own, ahead of the weights
-            mbar_wait(&ct.w_empty[slot], phase ^ 1);
-            mbar_arrive_expect_tx(&ct.w_full[slot], (uint32_t)NB * 32u);
-            bulk_g2s(ring + (size_t)slot * stage_bytes, a.packed + sh.split_b_off(l, net, (int)rank), (uint32_t)NB * 32u, &ct.w_full[slot]);
-          }
-          if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
-          for (int st = 0; st < K / ks; ++st) {
-            mbar_wait(&ct.w_empty[slot], phase ^ 1);
-            mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
-            bulk_g2s(ring + (size_t)slot * stage_bytes, nsrc + (size_t)st * bytes, bytes, &ct.w_full[slot]);
-            if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
-          }
-        }
-      }
+      uint32_t cntp = 0;
+      auto push = [&](const unsigned char* src, uint32_t bytes) {
+        const uint32_t slot = cntp & (kStages5 - 1), par = (cntp >> 2) & 1u;
+        mbar_wait(&ct.w_empty[slot], par ^ 1u);
+        mbar_arrive_expect_tx(&ct.w_full[slot], bytes);
+        bulk_g2s(ring + (size_t)slot * kStageBytes, src, bytes, &ct.w_full[slot]);
+        ++cntp;
+      };
+      const unsigned char* w0[2] = {a.packed + sh.split_w_off(0, 0, (int)rank), a.packed + sh.split_w_off(0, 1, (int)rank)};
+      const unsigned char* wF[2] = {a.packed + sh.split_w_off(L_, 0, (int)rank), a.packed + sh.split_w_off(L_, 1, (int)rank)};
+      const unsigned char* wH[2][2] = {{a.packed + sh.half_w_off(0, 0, (int)rank), a.packed + sh.half_w_off(0, 1, (int)rank)},
+                                       {a.packed + sh.half_w_off(1, 0, (int)rank), a.packed + sh.half_w_off(1, 1, (int)rank)}};
+      constexpr int KSH = (kStageElems / (U_ / 4)) < U_ ? (kStageElems / (U_ / 4)) : U_;   // K rows per stage of an N-half
+      constexpr uint32_t kHB = (uint32_t)(KSH * (U_ / 4) * 2);
+      TNF_FOR_JOBS({
+        (void)g;
+        const int net = j / 3, l = j % 3;
+        if (l == 0) push(w0[net], (uint32_t)(DH * (U_ / 2) * 2));
+        else if (l == 1) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int st = 0; st < U_ / KSH; ++st) push(wH[net][h] + (size_t)st * kHB, kHB);
+        } else push(wF[net], (uint32_t)(U_ * (DH / 2) * 2));
+      })
     }
   } else if (warp == kEpiWarps2 && rank != 0) {
     // =============================== second CTA: forward "stage landed" to the leader ===============================
-    uint32_t slot = 0, phase = 0;
-    const int64_t n_steps = cnt[0] * JT + shift;
-    // per-group job counters kept incrementally: no 64-bit division in the scheduling loops (a lone warp spends
-    // hundreds of cycles on one)
-    int jj2[2] = {0, 0};
-    const int64_t total[2] = {cnt[0] * JT, cnt[1] * JT};
-    int64_t todo[2] = {total[0], total[1]};
-    for (int64_t n = 0; n < n_steps; ++n) {
-      for (int g = 0; g < 2; ++g) {
-        if ((g == 1 && n < shift) || todo[g] == 0) continue;
-        const int jj = jj2[g];
-        --todo[g];
-        if (++jj2[g] == JT) jj2[g] = 0;
-        const int l = jj > sh.L ? jj - (sh.L + 1) : jj;
-        const int K = sh.K_of(l), NB = sh.J_of(l) / 2;
-        const int ks = (kStageElems / NB) < K ? (kStageElems / NB) : K;
-        for (int st = 0; st < 1 + K / ks; ++st) {
-          mbar_wait(&ct.w_full[slot], phase);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed(lead_w_peer + slot * 8u);
-          if (++slot == (uint32_t)S) { slot = 0; phase ^= 1; }
-        }
+    uint32_t cntf = 0;
+    constexpr int KSH = (kStageElems / (U_ / 4)) < U_ ? (kStageElems / (U_ / 4)) : U_;
+    TNF_FOR_JOBS({
+      (void)g;
+      const int l = j % 3;
+      const int n_st = l == 1 ? 2 * (U_ / KSH) : 1;
+      for (int st = 0; st < n_st; ++st) {
+        const uint32_t slot = cntf & (kStages5 - 1), par = (cntf >> 2) & 1u;
+        mbar_wait(&ct.w_full[slot], par);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(lead_w_peer + slot * 8u);
+        ++cntf;
       }
-    }
+    })
   } else if (warp == kEpiWarps2) {
     // =============================== leader CTA: MMA issuer (warp-uniform, elected lane issues) ===============================
     const bool leader = elect_one();
-    uint32_t slot = 0, phase = 0, e_par = 0, a1_par = 0;   // parities: bit g
-    const long long t_all = a.dbg != nullptr ? clock64() : 0;
-    long long t_dep = 0, t_w3[3] = {0, 0, 0};
+    uint32_t cntm = 0, e_par = 0, a1_par = 0;   // parities: bit g
+    bool started[2] = {false, false};
     const bool diag = a.dbg != nullptr;
+    const long long t_all = diag ? clock64() : 0;
+    long long t_dep = 0, t_w3[3] = {0, 0, 0};
     int mma_n = 0;
     const uint32_t wfull0 = smem_u32(&ct.w_full[0]), wpeer0 = smem_u32(&ct.w_peer[0]), wempty0 = smem_u32(&ct.w_empty[0]);
     const uint32_t ring16 = smem_u32(ring) >> 4;
@@ -230,59 +255,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
     const uint64_t bU_desc = make_desc(0u, U_ / 2), bF_desc = make_desc(0u, DH / 2);   // each CTA holds half of the N rows
     const uint32_t bU_lo = (uint32_t)bU_desc + ring16, bU_hi = (uint32_t)(bU_desc >> 32);
     const uint32_t bF_lo = (uint32_t)bF_desc + ring16, bF_hi = (uint32_t)(bF_desc >> 32);
+    const uint64_t bH_desc = make_desc(0u, U_ / 4);      // N-half jobs: each CTA holds U/4 of the half's U/2 weight rows
+    const uint32_t bH_lo = (uint32_t)bH_desc + ring16, bH_hi = (uint32_t)(bH_desc >> 32);
     const uint32_t ones_lo = (uint32_t)make_desc(smem_u32(sOnes), kTileM);
-    const int64_t n_steps = cnt[0] * JT + shift;
-    // per-group job counters kept incrementally: no 64-bit division in the scheduling loops (a lone warp spends
-    // hundreds of cycles on one)
-    int jj2[2] = {0, 0};
-    const int64_t total[2] = {cnt[0] * JT, cnt[1] * JT};
-    int64_t todo[2] = {total[0], total[1]};
-    for (int64_t n = 0; n < n_steps; ++n) {
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if ((g == 1 && n < shift) || todo[g] == 0) continue;
-        const int jj = jj2[g];
-        const bool first_job = todo[g] == total[g];
-        --todo[g];
-        if (++jj2[g] == JT) jj2[g] = 0;
-        const int net = jj > sh.L ? 1 : 0, l = jj > sh.L ? jj - (sh.L + 1) : jj;
-        (void)first_job; (void)net;
-        const long long c0 = a.dbg != nullptr ? clock64() : 0;
-        if (!first_job) {   // the group's previous epilogue phase in BOTH CTAs: accumulators drained, activations written
-          mbar_wait_addr(smem_u32(&ct.e_done[g]), (e_par >> g) & 1u);
-          e_par ^= 1u << g;
-        }
-        if (jj == 0) {
-          mbar_wait_addr(smem_u32(&ct.a1_ready[g]), (a1_par >> g) & 1u);
-          a1_par ^= 1u << g;
-        }
-        if (a.dbg != nullptr) t_dep += clock64() - c0;
-        if (diag && blockIdx.x == 0 && leader && mma_n < 480) {
-          a.dbg[3072 + 2 * mma_n] = 1000 + g * 100 + jj; a.dbg[3072 + 2 * mma_n + 1] = clock64(); ++mma_n;
-        }
-        const uint32_t d_tmem = tmem + (uint32_t)g * 256u;
-        const uint32_t a1_lo = (uint32_t)a1_desc + (uint32_t)g * a1_sz16;
-        const uint32_t act_lo = (uint32_t)act_desc + (uint32_t)g * act_sz16;
-        if (l == 0)
-          mma_job2<DH, U_>(d_tmem, a1_lo, a_hi, bU_lo, bU_hi, ones_lo, wfull0, wpeer0, wempty0, (uint32_t)S, slot, phase, leader, diag ? &t_w3[0] : nullptr);
-        else if (l < sh.L)
-          mma_job2<U_, U_>(d_tmem, act_lo, a_hi, bU_lo, bU_hi, ones_lo, wfull0, wpeer0, wempty0, (uint32_t)S, slot, phase, leader, diag ? &t_w3[1] : nullptr);
-        else
-          mma_job2<U_, DH>(d_tmem, act_lo, a_hi, bF_lo, bF_hi, ones_lo, wfull0, wpeer0, wempty0, (uint32_t)S, slot, phase, leader, diag ? &t_w3[2] : nullptr);
+    const uint32_t bias16 = smem_u32(sBias) >> 4;       // resident bias blocks: descriptor low word = (addr >> 4) | LBO field
+    const uint32_t lboU = (uint32_t)bU_desc, lboF = (uint32_t)bF_desc, lboH = (uint32_t)bH_desc;
+    TNF_FOR_JOBS({
+      const int net = j / 3, l = j % 3;
+      const long long c0 = diag ? clock64() : 0;
+      if (started[g]) {   // the group's previous epilogue phase in BOTH CTAs: accumulators drained, activations written
+        mbar_wait_addr(smem_u32(&ct.e_done[g]), (e_par >> g) & 1u);
+        e_par ^= 1u << g;
+      }
+      started[g] = true;
+      if (j == 0) {
+        mbar_wait_addr(smem_u32(&ct.a1_ready[g]), (a1_par >> g) & 1u);
+        a1_par ^= 1u << g;
+      }
+      tc_fence_after();
+      if (diag) t_dep += clock64() - c0;
+      if (diag && blockIdx.x == 0 && leader && mma_n < 480) {
+        a.dbg[3072 + 2 * mma_n] = 1000 + g * 100 + j; a.dbg[3072 + 2 * mma_n + 1] = clock64(); ++mma_n;
+      }
+      const uint32_t d_tmem = tmem + (uint32_t)g * 256u;
+      const uint32_t a1_lo = (uint32_t)a1_desc + (uint32_t)g * a1_sz16;
+      const uint32_t act_lo = (uint32_t)act_desc + (uint32_t)g * act_sz16;
+      if (l == 0) {
+        mma_job5<DH, U_, false, U_>(d_tmem, a1_lo, a_hi, bU_lo, bU_hi, ones_lo, lboU + bias16 + (uint32_t)(sh.bias8_off(0, net, 0) >> 4),
+                                    wfull0, wpeer0, wempty0, cntm, leader, diag ? &t_w3[0] : nullptr);
         if (leader) {
           tc_commit2_addr(smem_u32(&ct.h_ready[g]));
-          if (l == 0 && net == 1) tc_commit2_addr(smem_u32(&ct.a1_free[g]));
+          if (net == 1) tc_commit2_addr(smem_u32(&ct.a1_free[g]));
         }
-        if (diag && blockIdx.x == 0 && leader && mma_n < 480) {
-          a.dbg[3072 + 2 * mma_n] = 2000 + g * 100 + jj; a.dbg[3072 + 2 * mma_n + 1] = clock64(); ++mma_n;
-        }
-        __syncwarp();
+      } else if (l == 1) {   // last hidden job: N-half a -> commit -> N-half b (the group's tanh phase starts on half a)
+        mma_job5<U_, U_ / 2, false, U_>(d_tmem, act_lo, a_hi, bH_lo, bH_hi, ones_lo, lboH + bias16 + (uint32_t)(sh.bias8_off(1, net, 0) >> 4),
+                                        wfull0, wpeer0, wempty0, cntm, leader, diag ? &t_w3[1] : nullptr);
+        if (leader) tc_commit2_addr(smem_u32(&ct.h_ready[g]));
+        mma_job5<U_, U_ / 2, false, U_>(d_tmem + (uint32_t)(U_ / 2), act_lo, a_hi, bH_lo, bH_hi, ones_lo,
+                                        lboH + bias16 + (uint32_t)(sh.bias8_off(1, net, 1) >> 4), wfull0, wpeer0, wempty0, cntm, leader,
+                                        diag ? &t_w3[1] : nullptr);
+        if (leader) tc_commit2_addr(smem_u32(&ct.h_ready_b[g]));
+      } else {
+        mma_job5<U_, DH, true, U_>(d_tmem + fin_col5<U_>(), d_tmem, a_hi, bF_lo, bF_hi, ones_lo,
+                                   lboF + bias16 + (uint32_t)(sh.bias8_off(2, net, 0) >> 4), wfull0, wpeer0, wempty0, cntm, leader,
+                                   diag ? &t_w3[2] : nullptr);
+        if (leader) tc_commit2_addr(smem_u32(&ct.h_ready[g]));
       }
-    }
-    if (a.dbg != nullptr && blockIdx.x == 0 && leader) {
+      if (diag && blockIdx.x == 0 && leader && mma_n < 480) {
+        a.dbg[3072 + 2 * mma_n] = 2000 + g * 100 + j; a.dbg[3072 + 2 * mma_n + 1] = clock64(); ++mma_n;
+      }
+      __syncwarp();
+    })
+    if (diag && blockIdx.x == 0 && leader) {
       a.dbg[2040] = t_dep; a.dbg[2041] = t_w3[0] + t_w3[1] + t_w3[2]; a.dbg[2042] = clock64() - t_all;
       a.dbg[2043] = t_w3[0]; a.dbg[2044] = t_w3[1]; a.dbg[2045] = t_w3[2];
     }
+#undef TNF_FOR_JOBS
   } else if (warp < kEpiWarps2) {
     // =============================== epilogue warps ===============================
     const int g = warp >> 3, q = warp & 3, par = (warp >> 2) & 1;
@@ -292,7 +320,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
     const float kLog2e = 1.4426950408889634f;
     const uint32_t hcol = tmem + lane_addr + (uint32_t)g * 256u;
     unsigned char* myAct = sAct + (size_t)g * sh.act_bytes();
-    uint32_t h_par = 0;
+    uint32_t h_par = 0, hb_par = 0;
     float st_y = 0.f, st_y2 = 0.f;            // per-lane column sums of the transformed half (column par*W + lane%W)
 
     int dbg_n = 0;
@@ -322,6 +350,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
                        pack_bf16(__uint_as_float(x[j + 6]), __uint_as_float(x[j + 7])));
       }
     };
+    // last tanh phase: the bf16 activations go back into accumulator columns this warp has already consumed
+    auto epi_step_tm = [&](int c) {
+      uint32_t x[32];
+      tmem_ld32(hcol + (uint32_t)(c * kChunk), x);
+      tc_wait_ld();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          x[j + e] = __float_as_uint(e < FT ? tanh_poly(__uint_as_float(x[j + e])) : tanh_fast(__uint_as_float(x[j + e])));
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) pk[(j + e) >> 1] = pack_bf16(__uint_as_float(x[j + e]), __uint_as_float(x[j + e + 1]));
+      }
+      tmem_st16(hcol + act_col5<U_>(2 * c), pk);
+    };
     // end of an epilogue phase: accumulator reads done, activation image visible to the async proxy
     auto phase_done = [&]() {
       fence_async_smem();
@@ -341,7 +385,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
 #pragma unroll
       for (int net = 0; net < 2; ++net) {
 #pragma unroll 1
-        for (int l = 0; l < sh.L; ++l) {
+        for (int l = 0; l < sh.L - 1; ++l) {
           TNF_STAMP(200 + net * 10 + l);
           mbar_wait(&ct.h_ready[g], h_par);
           h_par ^= 1;
@@ -350,6 +394,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
 #pragma unroll 1
           for (int c = par; c < n_chunks; c += 2) epi_step(c);
           phase_done();
+        }
+        {   // last tanh phase, on the split job: N-half a while the tensor pipe still computes N-half b
+          TNF_STAMP(200 + net * 10 + sh.L - 1);
+          mbar_wait(&ct.h_ready[g], h_par);
+          h_par ^= 1;
+          tc_fence_after();
+          TNF_STAMP(300 + net * 10 + sh.L - 1);
+#pragma unroll 1
+          for (int c = par; c < n_chunks / 2; c += 2) epi_step_tm(c);
+          TNF_STAMP(250 + net * 10);
+          mbar_wait(&ct.h_ready_b[g], hb_par);
+          hb_par ^= 1;
+          tc_fence_after();
+          TNF_STAMP(350 + net * 10);
+#pragma unroll 1
+          for (int c = n_chunks / 2 + par; c < n_chunks; c += 2) epi_step_tm(c);
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(lead_e_done + (uint32_t)g * 8u);
         }
         // ---- final layer of this net: W columns per thread
         float zin[W];
@@ -368,8 +432,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
         tc_fence_after();
         TNF_STAMP(500 + net);
         uint32_t o[W];
-        if (W == 16) tmem_ld16(hcol + (uint32_t)(par * W), reinterpret_cast<uint32_t(&)[16]>(o));
-        else tmem_ld32(hcol + (uint32_t)(par * W), reinterpret_cast<uint32_t(&)[32]>(o));
+        if (W == 16) tmem_ld16(hcol + fin_col5<U_>() + (uint32_t)(par * W), reinterpret_cast<uint32_t(&)[16]>(o));
+        else tmem_ld32(hcol + fin_col5<U_>() + (uint32_t)(par * W), reinterpret_cast<uint32_t(&)[32]>(o));
         tc_wait_ld();
         if (net == 0) {
 #pragma unroll
@@ -533,32 +597,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads4, 1) coupli
   if (warp == kEpiWarps2) tmem_dealloc2(tmem, 512);
 }
 
-constexpr int kDefaultFT = 0;
+constexpr int kDefaultFT5 = 0;
 
-int launch_tc4(const Args& a, int grid, size_t smem, cudaStream_t st) {
+int launch_tc5(const Args& a, int grid, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaSuccess;
-#define TNF_TC4_LAUNCH(INV, DHV, UV, FTV)                                                                         \
+  if (!shape_supported5(a.D, a.U, a.L)) return (int)cudaErrorInvalidValue;
+#define TNF_TC5_LAUNCH(INV, DHV, UV, FTV)                                                                         \
   do {                                                                                                            \
-    e = cudaFuncSetAttribute(coupling_tc4_kernel<INV, DHV, UV, FTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    e = cudaFuncSetAttribute(coupling_tc5_kernel<INV, DHV, UV, FTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int)smem);                                                                          \
-    if (e == cudaSuccess) coupling_tc4_kernel<INV, DHV, UV, FTV><<<grid, kThreads4, smem, st>>>(a);               \
+    if (e == cudaSuccess) coupling_tc5_kernel<INV, DHV, UV, FTV><<<grid, kThreads5, smem, st>>>(a);               \
   } while (0)
-#define TNF_TC4_U(INV, DHV)                                               \
+#define TNF_TC5_U(INV, DHV)                                               \
   do {                                                                    \
-    if (a.U == 256) TNF_TC4_LAUNCH(INV, DHV, 256, kDefaultFT);            \
-    else if (a.U == 128) TNF_TC4_LAUNCH(INV, DHV, 128, kDefaultFT);       \
-    else TNF_TC4_LAUNCH(INV, DHV, 64, kDefaultFT);                        \
+    if (a.U == 256) TNF_TC5_LAUNCH(INV, DHV, 256, kDefaultFT5);           \
+    else TNF_TC5_LAUNCH(INV, DHV, 128, kDefaultFT5);                      \
   } while (0)
   const int ft = a.tune & 15;    // diagnostic: FMA-pipe tanh share (per 8) for the C3 shape
   if (a.D == 64 && a.U == 256 && ft != 0) {
-    if (ft == 1) { if (a.inverse) TNF_TC4_LAUNCH(true, 32, 256, 1); else TNF_TC4_LAUNCH(false, 32, 256, 1); }
-    else if (ft == 2) { if (a.inverse) TNF_TC4_LAUNCH(true, 32, 256, 2); else TNF_TC4_LAUNCH(false, 32, 256, 2); }
-    else if (ft == 3) { if (a.inverse) TNF_TC4_LAUNCH(true, 32, 256, 3); else TNF_TC4_LAUNCH(false, 32, 256, 3); }
-    else { if (a.inverse) TNF_TC4_LAUNCH(true, 32, 256, 4); else TNF_TC4_LAUNCH(false, 32, 256, 4); }
-  } else if (a.D == 64) { if (a.inverse) TNF_TC4_U(true, 32); else TNF_TC4_U(false, 32); }
-  else { if (a.inverse) TNF_TC4_U(true, 64); else TNF_TC4_U(false, 64); }
-#undef TNF_TC4_U
-#undef TNF_TC4_LAUNCH
+    if (a.inverse) TNF_TC5_LAUNCH(true, 32, 256, 1); else TNF_TC5_LAUNCH(false, 32, 256, 1);
+  } else if (a.D == 64) { if (a.inverse) TNF_TC5_U(true, 32); else TNF_TC5_U(false, 32); }
+  else { if (a.inverse) TNF_TC5_U(true, 64); else TNF_TC5_U(false, 64); }
+#undef TNF_TC5_U
+#undef TNF_TC5_LAUNCH
   return (int)e;
 }
 

@@ -68,7 +68,26 @@ struct Shape {
     for (int i = 0; i < l; ++i) off += 2 * (int64_t)J_of(i) * 32;
     return off + (int64_t)net * J_of(l) * 32 + (int64_t)rank * (J_of(l) / 2) * 32;
   }
-  __host__ __device__ int64_t packed_bytes() const { return unsplit_bytes() + 2 * net_weight_elems() * 2 + bias_img_bytes(); }
+  __host__ __device__ int64_t pair_bytes() const { return unsplit_bytes() + 2 * net_weight_elems() * 2 + bias_img_bytes(); }
+  // coupling_tc5_kernel (L >= 2): the LAST hidden layer (l = L-1) is issued as two N = U/2 halves: per net, half h,
+  // rank r one [U x U/4] weight image (units U/2*h + U/4*r ..)
+  __host__ __device__ int64_t half_w_off(int net, int h, int rank) const {
+    return pair_bytes() + (int64_t)((net * 2 + h) * 2 + rank) * U * (U / 4) * 2;
+  }
+  // ... and the biases stay RESIDENT in shared memory as 8-K-row blocks (unit n at byte 16*n: k = 0 bf16(b),
+  // k = 1 bf16(b - bf16(b)), k = 2..7 zero), per rank one contiguous region: for net: for layer: block(s) of this
+  // rank's units (the split layer: half a block, half b block)
+  __host__ __device__ int64_t bias8_rank_bytes() const { return 2 * 16 * ((int64_t)L * (U / 2) + d_out / 2); }
+  __host__ __device__ int64_t bias8_off(int l, int net, int h) const {
+    int64_t off = (int64_t)net * (bias8_rank_bytes() / 2);
+    for (int i = 0; i < l; ++i) off += (int64_t)(J_of(i) / 2) * 16;
+    return off + (int64_t)h * (J_of(l) / 4) * 16;
+  }
+  __host__ __device__ int64_t bias8_base(int rank) const {
+    return pair_bytes() + 2 * (int64_t)U * U * 2 + (int64_t)rank * bias8_rank_bytes();
+  }
+  __host__ __device__ int64_t half_bytes() const { return L >= 2 ? 2 * (int64_t)U * U * 2 + 2 * bias8_rank_bytes() : 0; }
+  __host__ __device__ int64_t packed_bytes() const { return pair_bytes() + half_bytes(); }
   __host__ __device__ size_t a1_bytes() const { return (size_t)kTileM * d_in * 2; }
   __host__ __device__ size_t act_bytes() const { return (size_t)kTileM * U * 2; }
 };
@@ -209,6 +228,17 @@ __device__ __forceinline__ void umma2_ss2(uint32_t d_tmem, uint32_t a_lo, uint32
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// pair MMA with the A operand in tensor memory (each CTA's own 128 rows at the same TMEM address)
+__device__ __forceinline__ void umma2_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit2_addr(uint32_t bar_addr) {   // arrives on this barrier in BOTH CTAs of the pair
   const uint16_t mask = 0x3;
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -286,10 +316,32 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// tanh on the FMA pipe: odd minimax polynomial x*P(x^2) on |x| <= 3.3, input clamped (beyond it tanh rounds to +-1 in
+// bf16 anyway).  Max abs error 1.4e-3 (bf16 rounding of the result: up to 2e-3); 10 FMA-pipe instructions against 8
+// issue cycles of the 16-lane MUFU pipe, used for a share of the activations to take load off that pipe.
+__device__ __forceinline__ float tanh_poly(float x) {
+  const float xc = fminf(fmaxf(x, -3.3f), 3.3f);
+  const float t = xc * xc;
+  float p = fmaf(2.4607425075373612e-06f, t, -0.00010122240928467363f);
+  p = fmaf(p, t, 0.0017052673501893878f);
+  p = fmaf(p, t, -0.015382171608507633f);
+  p = fmaf(p, t, 0.08308329433202744f);
+  p = fmaf(p, t, -0.29954469203948975f);
+  p = fmaf(p, t, 0.9929457902908325f);
+  return p * xc;
 }
 // low half = first (lower K index) element
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -304,6 +356,7 @@ struct Args {
   const float* pre_scale; const float* pre_shift;
   int64_t rows;
   int D, U, L, upper, inverse, accum, n_stages, n_groups;
+  int tune;   // diagnostic knob of the kernel under development (bits 8.. of `variant`); 0 = shipped configuration
   double* stat_partials;   // [grid*8 warps][2][D] per-warp column sums of the OUTPUT (NULL = off)
   long long* dbg;   // diagnostics: per-phase clock64 stamps of CTA 0 (NULL = off)
 };
@@ -372,6 +425,12 @@ __device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) 
 // coupling_tc4.cu: launches the CTA-pair two-tile kernel (the product path for D <= 128); returns cudaError_t
 int launch_tc4(const Args& a, int grid, size_t smem, cudaStream_t st);
 size_t smem_bytes4(const Shape& sh, int n_stages);
+// coupling_tc5.cu: tc4 with the last hidden job issued as two N-halves and the final layer fed from tensor memory
+int launch_tc5(const Args& a, int grid, size_t smem, cudaStream_t st);
+size_t smem_bytes5(const Shape& sh, int n_stages);
+__host__ __device__ inline bool shape_supported5(int D, int U, int L) {
+  return shape_supported2(D, U, L) && U >= 128 && L == 2;
+}
 
 }  // namespace tc
 }  // namespace tnf
