@@ -114,9 +114,10 @@ int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int 
 size_t tnf_tc_packed_bytes(int D, int U, int L, int precision);
 int tnf_tc_pack(const float* params, void* packed, int D, int U, int L, int transform_upper,
                 int precision, tnf_stream_t stream);
-/* variant (diagnostic; no process-global state): 0 = kernel chosen by shape (CTA-pair two-tile kernel for
- *   D <= 128, single-tile pipelined kernel for D = 256), 1 = the first (8 epilogue warp) kernel,
- *   2 = two-tile kernel without CTA pairs; +16 = first kernel with one epilogue group only.
+/* variant (diagnostic; no process-global state): 0 = kernel chosen by shape (D <= 128: CTA-pair two-tile kernel,
+ *   for L = 2 and U >= 128 its N-half / TMEM-fed form coupling_tc5_kernel; D = 256: single-tile pipelined
+ *   kernel), 1 = the first (8 epilogue warp) kernel, 2 = two-tile kernel without CTA pairs, 3 = coupling_tc5_kernel
+ *   without its FMA-pipe tanh share, 4 = coupling_tc4_kernel; +16 = first kernel with one epilogue group only.
  * debug (diagnostic, or NULL): device buffer of 4096 int64 receiving (tag, clock64) stamps of CTA 0. */
 int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void* packed,
                     int64_t rows, int D, int U, int L, int transform_upper, int direction,

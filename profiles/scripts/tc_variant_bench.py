@@ -32,7 +32,7 @@ for v in variants:
             zo, ld = ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_INVERSE, variant=v)
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) / 10)
-    zf, ldf = ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_FORWARD, variant=v)
+    zf, ldf = ops.coupling_tc(z, packed, D, U, L, True, ops.TNF_FORWARD, variant=v & 0xFFF)
     torch.cuda.synchronize()
     if base is None:
         base = (zo.clone(), ld.clone(), zf.clone())

@@ -34,7 +34,7 @@ torch.cuda.synchronize()
 raw = dbg.cpu().numpy()
 print("MMA warp (CTA 0): cycles waiting on epilogue %d, on weights %d, total %d (first layers %d, hidden layers %d, final layers %d)" % (raw[2040], raw[2041], raw[2042], raw[2043], raw[2044], raw[2045]))
 d = raw[:2048].reshape(2, 512, 2)  # group g at int64 offset 1024*g
-names = {250: "wait Hb net0", 260: "wait Hb net1", 350: "got  Hb net0", 360: "got  Hb net1", 100: "tile start", 101: "A1 published", 600: "tile end", 601: "y computed", 602: "next A1 published", 610: "A1 image written", 611: "A1 proxy fence done",
+names = {602: "s read, acc freed", 603: "zin landed", 604: "z stored", 605: "pair synced", 250: "wait Hb net0", 260: "wait Hb net1", 350: "got  Hb net0", 360: "got  Hb net1", 100: "tile start", 101: "A1 published", 600: "tile end", 601: "y computed", 602: "next A1 published", 610: "A1 image written", 611: "A1 proxy fence done",
          700: "step: chunk landed", 701: "step: tanh+stores issued", 702: "step: chunk published", 703: "step: begin"}
 for g in range(2):
     ev = [(int(t), int(c)) for t, c in d[g] if t != 0]

@@ -1591,7 +1591,10 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   // kernel choice: D <= 128 -> two-tile kernel; D = 256 -> single-tile pipelined kernel; variant 1 -> the first kernel
   const bool pingpong2 = tc::shape_supported2(D, U, L) && g_tc_variant != 1;
   const bool pairs = pingpong2 && g_tc_variant != 2;      // clusters of two CTAs sharing the weight operands
-  const bool pairs5 = pairs && g_tc_variant == 3 && tc::shape_supported5(D, U, L);   // N-half / TMEM-fed variant
+  // N-half / TMEM-fed kernel: the default where it applies (L = 2, U >= 128); variant 4 forces the older pair kernel,
+  // variant 3 runs it without the FMA-pipe tanh share (then bit-identical to variant 4)
+  const bool pairs5 = pairs && g_tc_variant != 4 && tc::shape_supported5(D, U, L) &&
+                      tc::smem_bytes5(tc::Shape(D, U, L, 1), 4) <= 227 * 1024;   // its weight ring is 4 stages, fixed
   const bool pipelined = D == 256 && g_tc_variant != 1;
   if (pairs) {   // one 256-row super tile per CTA pair and group; the grid is a whole number of pairs
     const int64_t n_super = (n_tiles + 1) / 2;
@@ -1602,7 +1605,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   int n_stages = tc::kMaxStages;
   size_t smem;
   if (pairs5) {
-    while (n_stages > 2 && tc::smem_bytes5(sh, n_stages) > 227 * 1024) --n_stages;
+    n_stages = 4;
     smem = tc::smem_bytes5(sh, n_stages);
   } else if (pairs) {
     while (n_stages > 2 && tc::smem_bytes4(sh, n_stages) > 227 * 1024) --n_stages;
@@ -1619,7 +1622,8 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   }
   TNF_REQUIRE(smem <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem);
   tc::Args a{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
-             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_groups, variant >> 8,
+             D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_groups,
+             (variant >> 8) | ((variant & 15) == 3 ? 0x100 : 0),
              col_stats ? (double*)stats_workspace : nullptr, g_tc_debug};
 #define TNF_TC_LAUNCH(KERNEL, THREADS, INV, DHV)                                                              \
   do {                                                                                                        \

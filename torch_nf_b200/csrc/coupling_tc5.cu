@@ -613,8 +613,10 @@ int launch_tc5(const Args& a, int grid, size_t smem, cudaStream_t st) {
     if (a.U == 256) TNF_TC5_LAUNCH(INV, DHV, 256, kDefaultFT5);           \
     else TNF_TC5_LAUNCH(INV, DHV, 128, kDefaultFT5);                      \
   } while (0)
-  const int ft = a.tune & 15;    // diagnostic: FMA-pipe tanh share (per 8) for the C3 shape
-  if (a.D == 64 && a.U == 256 && ft != 0) {
+  // FMA-pipe tanh share: 1 of 8 activations at the C3 shape (measured best: 0 -> 0.416, 1 -> 0.400, 2+ slower);
+  // tune bit 8 (variant 3) turns it off = the arithmetic of coupling_tc4_kernel bit for bit
+  const bool ft_off = (a.tune & 0x100) != 0;
+  if (a.D == 64 && a.U == 256 && !ft_off) {
     if (a.inverse) TNF_TC5_LAUNCH(true, 32, 256, 1); else TNF_TC5_LAUNCH(false, 32, 256, 1);
   } else if (a.D == 64) { if (a.inverse) TNF_TC5_U(true, 32); else TNF_TC5_U(false, 32); }
   else { if (a.inverse) TNF_TC5_U(true, 64); else TNF_TC5_U(false, 64); }

@@ -66,6 +66,20 @@ class DensityEstimator(object):
         raise NotImplementedError()
 
 
+class MoGOutOfScope(NotImplementedError):
+    pass
+
+
+class MoG(DensityEstimator):
+    """Mixture of Gaussians (reference density_estimator.py:58-237) is NOT part of the bijector-chain hot path
+    (no chain, sampling is a host-side scipy loop); the name exists so that the reference's
+    ``de.MoG`` lookups fail with a clear message instead of an AttributeError."""
+
+    def __init__(self, *args, **kwargs):
+        raise MoGOutOfScope("MoG is outside the B200 hot path of torch_nf_b200 (SURVEY.md section 2); "
+                            "use the reference implementation for it")
+
+
 class NormFlow(DensityEstimator):
     """Normalizing flow (reference density_estimator.py:240-421).
 
