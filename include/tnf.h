@@ -101,7 +101,7 @@ int tnf_maf_bwd(const void* z_in, const void* params, int64_t param_row_stride, 
  * (:401-410), accumulated inside the kernel (fp32 per warp, float64 across warps);
  * needs stats_workspace of tnf_colstats_workspace_bytes(D) bytes; D <= 128 (variant 1: D = 64 only).
  * z_out must not alias z_in. */
-int tnf_tc_supported(int D, int U, int L);
+int tnf_tc_supported(int D, int U, int L, int precision);
 /* diagnostic: out[128 x N] = bf16(A[128 x K]) . bf16(W[K x N]) through the same
  * operand images, UMMA descriptors and TMEM accumulator layout as the fused
  * kernel; a_in_tmem selects the A operand source (1: TMEM, 0: SMEM image). */

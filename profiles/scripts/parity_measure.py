@@ -13,7 +13,7 @@ rel = lambda a, b: float((np.abs(a - b) / np.maximum(1.0, np.abs(b))).max())
 for name in ("flow_c3", "flow_c5"):
     g = G(name)
     D, stages, L, U, M, N, pseed, oseed = [int(v) for v in g["cfg"]]
-    for mode in ("fp32", "bf16"):
+    for mode in ("fp32_cc", "fp32", "bf16"):
         tnf.set_conditioner_precision(mode)
         nf = de.NormFlow(D, True, "coupling", stages, L, U)
         params = T(synthetic_params(chain_spec(nf.bijectors), D, M, seed=pseed)).cuda()
@@ -34,7 +34,7 @@ for (D, stages, L, U, N) in ((64, 4, 2, 256, 1 << 16), (256, 8, 2, 256, 1 << 13)
     with torch.no_grad():
         zo, lqo, st = O.normflow_forward(chain, D, params, omega)
         lpo = O.normflow_log_prob(chain, D, zo, params, st)
-    for mode in ("fp32", "bf16"):
+    for mode in ("fp32_cc", "fp32", "bf16"):
         tnf.set_conditioner_precision(mode)
         with torch.no_grad():
             z, lq = nf.forward(params.cuda(), N, omega=omega)

@@ -118,6 +118,39 @@ def test_coupling_tc_accum_and_preaffine():
         assert (ld.cpu() - (base.cpu() + sign * lde.view(-1))).abs().max().item() < 4e-2
 
 
+@pytest.mark.parametrize("D,U,L,N,upper", [(64, 256, 2, 1000, True), (64, 256, 2, 333, False), (64, 128, 2, 257, True),
+                                            (128, 256, 2, 384, True), (64, 256, 1, 300, True), (64, 256, 3, 500, False),
+                                            (128, 128, 2, 129, False), (64, 256, 5, 140, True)])
+def test_coupling_fp32_parity_on_tensor_cores(D, U, L, N, upper):
+    """TNF_TC_FP32 (fp16 hi/lo operand split, three MMAs per product, fp32-accurate tanh / exp) against the fp32
+    oracle with the FP32 tolerance of the north star: max|dz|/max(1,|z|) <= 1e-5, log-det <= 1e-4 relative."""
+    from torch_nf_b200 import config
+    params = T(synthetic_params([("RealNVP", L, U, upper)], D, 1, seed=3))
+    z = torch.randn(1, N, D, generator=torch.Generator().manual_seed(1)) * 1.3
+    packed = ops.tc_pack(params.cuda()[0], D, U, L, upper, precision="fp32_tc")
+    ps = (torch.rand(D) + 0.5); pb = torch.randn(D) * 0.3
+    for direction, fn in ((ops.TNF_FORWARD, O.coupling_forward), (ops.TNF_INVERSE, O.coupling_inverse)):
+        zo, ldo = fn(z, params, D, L, U, upper)
+        before = _lib.launch_count()
+        zd, ld = ops.coupling_tc(z.cuda(), packed, D, U, L, upper, direction, precision="fp32_tc")
+        assert _lib.launch_count() == before + 1
+        h = D // 2
+        keep = slice(0, h) if upper else slice(h, D)
+        assert torch.equal(zd.cpu()[:, :, keep], z[:, :, keep])          # pass-through half bit-identical
+        rz = ((zd.cpu() - zo).abs() / zo.abs().clamp(min=1)).max().item()
+        rl = ((ld.cpu().view(1, N) - ldo).abs() / ldo.abs().clamp(min=1)).max().item()
+        print("fp32_tc D=%d U=%d L=%d dir=%d: rel z %.3g, rel log-det %.3g" % (D, U, L, direction, rz, rl))
+        assert rz <= config.FP32_TOL_Z and rl <= config.FP32_TOL_LOGP, (rz, rl)
+        # folded pre-affine and log-det accumulation
+        base = torch.randn(N)
+        ld2 = base.clone().cuda()
+        z2, _ = ops.coupling_tc(z.cuda(), packed, D, U, L, upper, direction, ld=ld2, accum=ops.TNF_LD_SUB,
+                                pre_scale=ps.cuda(), pre_shift=pb.cuda(), precision="fp32_tc")
+        zo2, ldo2 = fn(z * ps + pb, params, D, L, U, upper)
+        assert ((z2.cpu() - zo2).abs() / zo2.abs().clamp(min=1)).max().item() <= config.FP32_TOL_Z
+        assert ((ld2.cpu() - (base - ldo2.view(-1))).abs()).max().item() <= 1e-4 * max(1.0, float(ldo2.abs().max()))
+
+
 def _bf16_chain_vs_golden(golden, name):
     """Whole chain in bf16-conditioner mode vs the reference's golden vectors with THE stated bf16 tolerance
     (torch_nf_b200.config.BF16_TOL_Z / BF16_TOL_LOGP)."""

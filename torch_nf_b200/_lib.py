@@ -28,7 +28,7 @@ PROTOTYPES = {
     "tnf_coupling_bwd": (I, [P, P, L, P, P, P, P, L, L, L, I, I, I, I, I, I, P]),
     "tnf_maf": (I, [P, P, P, P, L, P, L, L, I, I, I, I, I, I, P]),
     "tnf_maf_bwd": (I, [P, P, L, P, P, P, P, P, L, L, L, I, I, I, I, I, P]),
-    "tnf_tc_supported": (I, [I, I, I]),
+    "tnf_tc_supported": (I, [I, I, I, I]),
     "tnf_tc_selftest_gemm": (I, [P, P, P, I, I, I, P]),
     "tnf_tc_packed_bytes": (Z, [I, I, I, I]),
     "tnf_tc_pack": (I, [P, P, I, I, I, I, I, P]),

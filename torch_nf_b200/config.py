@@ -1,9 +1,14 @@
 """Run-time switches of the hot path.
 
 ``conditioner precision``
-    ``"fp32"`` (default): conditioner GEMMs on CUDA cores in the input dtype;
-    matches the reference within fp32 rounding (max|dz|/max(1,|z|) <= 1e-5,
-    |d log_prob| <= 1e-4*max(1,|log_prob|)).
+    ``"fp32"`` (default): the reference's precision.  Shared-weight coupling layers with
+    D in {64, 128}, U in {128, 256} run on tcgen05 tensor cores in the fp32-PARITY mode
+    (operands split into fp16 hi + lo parts, three MMAs per product, fp32 accumulation,
+    tanh / exp to fp32 accuracy: coupling_tc6.cu); every other case (per-sample weights,
+    float64, odd or small D, autograd) runs the exact CUDA-core kernel in the input dtype.
+    Stated tolerance, both: max|dz|/max(1,|z|) <= FP32_TOL_Z = 1e-5 and
+    |d log_prob| <= FP32_TOL_LOGP = 1e-4*max(1,|log_prob|) on the reference's golden vectors.
+    ``"fp32_cc"``: the same tolerance with the CUDA-core kernel everywhere (~50x slower at C3).
     ``"bf16"``: shared-weight coupling layers run on tcgen05 tensor cores with
     bf16 operands, fp32 accumulation, fp32 affine transform and log-det.
     Stated tolerance (ONE statement, asserted as written by tests/test_gpu_tc.py, per
@@ -35,13 +40,18 @@ _tc_min_rows = int(os.environ.get("TNF_TC_MIN_ROWS", "128"))
 
 def set_conditioner_precision(mode):
     global _precision
-    if mode not in ("fp32", "bf16"):
-        raise ValueError('conditioner precision must be "fp32" or "bf16"')
+    if mode not in ("fp32", "fp32_cc", "bf16"):
+        raise ValueError('conditioner precision must be "fp32", "fp32_cc" or "bf16"')
     _precision = mode
 
 
 def conditioner_precision():
     return _precision
+
+
+def tc_precision():
+    """Tensor-core kernel family of the current mode ("bf16" / "fp32_tc"), or None (CUDA cores only)."""
+    return {"bf16": "bf16", "fp32": "fp32_tc"}.get(_precision)
 
 
 def set_tc_min_rows(n):

@@ -1545,20 +1545,27 @@ using namespace tnf;
 
 extern "C" {
 
-int tnf_tc_supported(int D, int U, int L) { return tc::shape_supported(D, U, L) ? 1 : 0; }
+int tnf_tc_supported(int D, int U, int L, int precision) {
+  if (precision == TNF_TC_FP32) return tc::shape_supported6(D, U, L) ? 1 : 0;
+  return precision == TNF_TC_BF16 && tc::shape_supported(D, U, L) ? 1 : 0;
+}
 
 size_t tnf_tc_packed_bytes(int D, int U, int L, int precision) {
+  if (precision == TNF_TC_FP32) return tc::shape_supported6(D, U, L) ? tc::packed_bytes6(D, U, L) : 0;
   if (!tc::shape_supported(D, U, L) || precision != TNF_TC_BF16) return 0;
   return (size_t)tc::Shape(D, U, L, 1).packed_bytes();
 }
 
 int tnf_tc_pack(const float* params, void* packed, int D, int U, int L, int transform_upper, int precision,
                 tnf_stream_t stream) {
-  TNF_REQUIRE(tc::shape_supported(D, U, L), TNF_ERR_UNSUPPORTED, "tnf_tc_pack: shape D=%d U=%d L=%d not supported", D,
-              U, L);
-  TNF_REQUIRE(precision == TNF_TC_BF16, TNF_ERR_UNSUPPORTED, "tnf_tc_pack: precision %d not supported", precision);
+  TNF_REQUIRE(tnf_tc_supported(D, U, L, precision), TNF_ERR_UNSUPPORTED,
+              "tnf_tc_pack: shape D=%d U=%d L=%d not supported at precision %d", D, U, L, precision);
   TNF_REQUIRE(params && packed, TNF_ERR_ARG, "tnf_tc_pack: null pointer");
   TNF_REQUIRE(((uintptr_t)packed & 15) == 0, TNF_ERR_ALIGN, "tnf_tc_pack: packed buffer must be 16-byte aligned");
+  if (precision == TNF_TC_FP32) {
+    tc::pack6_launch(params, packed, D, U, L, transform_upper != 0, (cudaStream_t)stream);
+    return check_launch("tnf_tc_pack");
+  }
   tc::Shape sh(D, U, L, transform_upper != 0);
   tc::pack_kernel<<<num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(params, (unsigned char*)packed, sh);
   return check_launch("tnf_tc_pack");
@@ -1568,9 +1575,31 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
                     int L, int transform_upper, int direction, int accum, const float* pre_scale,
                     const float* pre_shift, double* col_stats, void* stats_workspace, int precision, int variant,
                     void* debug, tnf_stream_t stream) {
-  TNF_REQUIRE(tc::shape_supported(D, U, L), TNF_ERR_UNSUPPORTED,
-              "tnf_coupling_tc: shape D=%d U=%d L=%d not supported", D, U, L);
-  TNF_REQUIRE(precision == TNF_TC_BF16, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: precision %d not supported", precision);
+  TNF_REQUIRE(tnf_tc_supported(D, U, L, precision), TNF_ERR_UNSUPPORTED,
+              "tnf_coupling_tc: shape D=%d U=%d L=%d not supported at precision %d", D, U, L, precision);
+  if (precision == TNF_TC_FP32) {   // fp32-parity kernel: own packed format, one tile per CTA, CTA pairs
+    TNF_REQUIRE(rows >= 0, TNF_ERR_ARG, "tnf_coupling_tc: rows < 0");
+    if (rows == 0) return 0;
+    TNF_REQUIRE(z_in && z_out && log_det && packed, TNF_ERR_ARG, "tnf_coupling_tc: null pointer");
+    TNF_REQUIRE((((uintptr_t)z_in | (uintptr_t)z_out | (uintptr_t)packed) & 15) == 0, TNF_ERR_ALIGN,
+                "tnf_coupling_tc: z and packed weights must be 16-byte aligned");
+    TNF_REQUIRE(col_stats == nullptr, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: no fused column statistics in fp32 mode");
+    const int64_t n_super6 = ((rows + tc::kTileM - 1) / tc::kTileM + 1) / 2;
+    const int64_t max_pairs6 = num_sms() / 2;
+    const int grid6 = 2 * (int)(n_super6 < max_pairs6 ? n_super6 : max_pairs6);
+    int ns = 10;
+    while (ns > 2 && tc::smem_bytes6(D, U, L, ns) > 227 * 1024) --ns;
+    const size_t smem6 = tc::smem_bytes6(D, U, L, ns);
+    TNF_REQUIRE(smem6 <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem6);
+    tc::Args a6{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
+                D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, ns, 2, variant >> 8, nullptr, (long long*)debug};
+    cudaError_t e6 = (cudaError_t)tc::launch_tc6(a6, grid6, ns, smem6, (cudaStream_t)stream);
+    if (e6 != cudaSuccess) {
+      set_error("tnf_coupling_tc: cudaFuncSetAttribute(%zu B smem): %s", smem6, cudaGetErrorString(e6));
+      return (int)e6;
+    }
+    return check_launch("tnf_coupling_tc");
+  }
   const int g_tc_variant = variant & 15, g_tc_groups = (variant & 16) ? 1 : 2;   // per-call diagnostics, no global state
   long long* const g_tc_debug = (long long*)debug;
   TNF_REQUIRE(rows >= 0, TNF_ERR_ARG, "tnf_coupling_tc: rows < 0");

@@ -316,6 +316,23 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
@@ -428,6 +445,12 @@ size_t smem_bytes4(const Shape& sh, int n_stages);
 // coupling_tc5.cu: tc4 with the last hidden job issued as two N-halves and the final layer fed from tensor memory
 int launch_tc5(const Args& a, int grid, size_t smem, cudaStream_t st);
 size_t smem_bytes5(const Shape& sh, int n_stages);
+// coupling_tc6.cu: fp32-parity mode (fp16 hi / lo operand split, three MMAs per product, activations in TMEM)
+bool shape_supported6(int D, int U, int L);
+size_t packed_bytes6(int D, int U, int L);
+int pack6_launch(const float* params, void* packed, int D, int U, int L, int upper, cudaStream_t st);
+size_t smem_bytes6(int D, int U, int L, int n_stages);
+int launch_tc6(const Args& a, int grid, int n_stages, size_t smem, cudaStream_t st);
 __host__ __device__ inline bool shape_supported5(int D, int U, int L) {
   return shape_supported2(D, U, L) && U >= 128 && L == 2;
 }

@@ -242,9 +242,10 @@ class NormFlow(DensityEstimator):
         return out
 
     def _use_tc(self, b, pd, z):
-        return (config.conditioner_precision() == "bf16" and pd.shape[0] == 1 and z.dtype == torch.float32
+        mode = config.tc_precision()
+        return (mode is not None and pd.shape[0] == 1 and z.dtype == torch.float32
                 and b.name == "RealNVP" and z.shape[0] * z.shape[1] >= config.tc_min_rows()
-                and ops.tc_supported(b.D, b.num_units, b.num_layers))
+                and ops.tc_supported(b.D, b.num_units, b.num_layers, mode))
 
     def _packed(self, b, idx, n, pd, src=None):
         """Packed tensor-core operand images of bijector ``b``'s weights (``pd[0, idx:idx+n]``).
@@ -254,13 +255,13 @@ class NormFlow(DensityEstimator):
         object at the same in-place version.  A device copy made for this call (``pd`` when ``src`` lives on the
         host) is never a key: the caching allocator hands its address out again.  Without ``src`` the weights are
         repacked (one ~60 us kernel per layer)."""
-        mode = config.conditioner_precision()
+        mode = config.tc_precision()
         if src is not None:
             hit = self._tc_cache.get(id(b))
             if (hit is not None and hit[0] is src and hit[1] == src._version and hit[2] == (idx, mode)
                     and hit[3].device == pd.device):
                 return hit[3]
-        packed = ops.tc_pack(pd[0, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper)
+        packed = ops.tc_pack(pd[0, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper, precision=mode)
         if src is not None:
             self._tc_cache[id(b)] = (src, src._version, (idx, mode), packed)
         return packed
@@ -290,11 +291,12 @@ class NormFlow(DensityEstimator):
             if b.name == "RealNVP":
                 if self._use_tc(b, pd, z):
                     nxt = slices[i + 1][0].name if i + 1 < len(slices) else None
-                    fuse_stats = (nxt == "BatchNorm" and not freeze_bn and D <= 128)
+                    mode = config.tc_precision()
+                    fuse_stats = (nxt == "BatchNorm" and not freeze_bn and D <= 128 and mode == "bf16")
                     res = ops.coupling_tc(z, self._packed(b, idx, n, pd, src), b.D, b.num_units, b.num_layers,
                                           b.transform_upper, TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD,
                                           pre_scale=pend[0] if pend else None, pre_shift=pend[1] if pend else None,
-                                          want_stats=fuse_stats)
+                                          want_stats=fuse_stats, precision=mode)
                     z, stats = res[0], (res[2] if fuse_stats else None)
                     pend = None
                 else:
@@ -387,7 +389,8 @@ class NormFlow(DensityEstimator):
                 if (self._use_tc(b, pd, z) if use_tc is None else use_tc):
                     z, _ = ops.coupling_tc(z, self._packed(b, idx, n, pd, src), b.D, b.num_units, b.num_layers,
                                            b.transform_upper, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD,
-                                           pre_scale=pend[0] if pend else None, pre_shift=pend[1] if pend else None)
+                                           pre_scale=pend[0] if pend else None, pre_shift=pend[1] if pend else None,
+                                           precision=config.tc_precision())
                     pend = None
                 else:
                     z, _ = ops.coupling(z, pd[:, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper,

@@ -178,11 +178,11 @@ def maf_bwd(z_in, params, mask, g_z_out, g_ld, g_params, D, U, L, direction):
 
 
 # ----------------------------------------------------------------- tensor-core coupling
-def tc_supported(D, U, L):
-    return bool(_lib.lib().tnf_tc_supported(D, U, L))
-
-
 TC_PRECISION = {"bf16": _lib.TNF_TC_BF16, "fp32_tc": _lib.TNF_TC_FP32}
+
+
+def tc_supported(D, U, L, precision="bf16"):
+    return bool(_lib.lib().tnf_tc_supported(D, U, L, TC_PRECISION[precision]))
 
 
 def tc_pack(params_row, D, U, L, upper, precision="bf16"):
