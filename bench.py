@@ -13,7 +13,9 @@ so every rank normalises with the global batch).  Prints ONE JSON line.
 
 `value`   device-resident throughput (weights and samples stay in HBM),
           conditioner GEMMs in bf16 on tcgen05 (dtype "bf16"; affine transform,
-          log-det and BatchNorm in fp32).
+          log-det and BatchNorm in fp32).  The same step at the REFERENCE'S
+          precision (fp32 parity on tensor cores, fp16 hi/lo operand split) is
+          measured in the same run and reported in the `fp32` object.
 `e2e`     the same step through the public API with HOST tensors (pinned):
           parameters and samples cross PCIe inside the timed region.
 `--impl reference`  times the reference's CPU algorithm (the oracle port, torch
@@ -215,8 +217,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_sample_rows_per_step": n_rows},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "reference_sample_rows_per_step": n_rows, "same_config": False,
+                   "note": "bounded sample: 2^14 of the 2^20 rows per step, same flow and weights"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+                         "same_config": False, "rows_per_step": n_rows},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -231,6 +235,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32_cc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-parity measurement of the same step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -316,22 +321,56 @@ def main():
     # dominant kernel: CUDA events recorded around every tensor-core coupling launch of the timed region
     kern_ms = [a.elapsed_time(b) for (a, b) in timer]
     pk = peaks()
-    roofline = None
-    if kern_ms:
+
+    def roofline_of(kern_ms, step_ms, steps, kernel, split_factor):
+        if not kern_ms:
+            return None
         avg = sum(kern_ms) / len(kern_ms)
         achieved = FLOP_PER_SAMPLE_LAYER * B / (avg * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "tc_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch")
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
-                    "kernel": "coupling_tc4_kernel", "launches_timed": len(kern_ms), "avg_launch_ms": avg,
-                    "peak_source": pk["source"] + " (sustained bf16 GEMM; burst %.1f -> frac %.3f)" % (
-                        pk["tflops_burst"], achieved / pk["tflops_burst"]),
-                    "kernel_share_of_step": sum(kern_ms) / ms,
-                    "hbm_gbs_at_algorithmic_bytes": BYTES_PER_SAMPLE_LAYER * B / (avg * 1e-3) / 1e9}
+        if os.path.exists(tpath):       # dram__bytes_read+write per launch from the committed `ncu --set full` capture,
+            with open(tpath) as fh:     # valid only for the kernel source it was taken on (digest checked here)
+                tj = json.load(fh)
+            ent = tj.get(kernel)
+            if ent:
+                from torch_nf_b200 import _build
+                import hashlib
+                with open(os.path.join(_build.CSRC, ent["source"]), "rb") as fh:
+                    dig = hashlib.sha256(fh.read()).hexdigest()[:16]
+                traffic = ent["dram_bytes_per_launch"]
+                traffic_src = "ncu capture %s (%s)" % (ent["capture"], "current source" if dig == ent["source_sha256_16"]
+                                                      else "STALE: kernel source changed since the capture")
+        return {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tflops_burst"], "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": kernel, "launches_timed": len(kern_ms), "avg_launch_ms": avg,
+                "peak_source": pk["source"] + " (burst bf16 GEMM: the timed region is ~0.1 s at full clocks; sustained %.1f -> frac %.3f)" % (
+                    pk["tflops_sustained"], achieved / pk["tflops_sustained"]),
+                "algorithmic_flop_per_launch": FLOP_PER_SAMPLE_LAYER * B, "mma_passes_per_product": split_factor,
+                "kernel_share_of_step": sum(kern_ms) / (step_ms * steps),
+                "chain_roofline_frac": (world * B * steps / (step_ms * steps * 1e-3)) / world / (
+                    1.0 / (2 * N_LAYERS * FLOP_PER_SAMPLE_LAYER / (pk["tflops_burst"] * 1e12))),
+                "hbm_gbs_at_algorithmic_bytes": BYTES_PER_SAMPLE_LAYER * B / (avg * 1e-3) / 1e9}
+
+    roofline = roofline_of(kern_ms, ms / args.steps, args.steps,
+                           "coupling_tc5_kernel" if args.precision == "bf16" else "coupling_tc6_kernel",
+                           1 if args.precision == "bf16" else 3)
+
+    # the same step at the reference's precision (fp32 parity mode), device resident, a few steps
+    fp32 = None
+    if args.precision == "bf16" and not args.no_fp32:
+        tnf.set_conditioner_precision("fp32")
+        t32 = []
+        f_steps = max(2, min(args.steps, 4))
+        ms32, _, out32 = timed(step_resident, f_steps, 3, t32)
+        tnf.set_conditioner_precision(args.precision)
+        k32 = [a.elapsed_time(b) for (a, b) in t32]
+        z32, lq32, lp32 = out32
+        fp32 = {"value": world * B * f_steps / (ms32 * 1e-3), "unit": "samples/s", "ms_per_step": ms32 / f_steps, "steps": f_steps,
+                "dtype": "fp32 parity: fp16 hi/lo operand split on tcgen05, fp32 accumulate, rel 1e-5 on samples",
+                "max_abs_logq_minus_logprob": float((lq32.float() - lp32).abs().max().item()),
+                "roofline": roofline_of(k32, ms32 / f_steps, f_steps, "coupling_tc6_kernel", 3)}
+        del out32, z32, lq32, lp32
 
     e2e = None
     if not args.no_e2e:
@@ -348,8 +387,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         v, secs = cpu_port_throughput(1 << 14, 3, threads)
-        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": "2^14 of 2^20 rows, 1 warm-up + best of 3 (%.2f s/pass), oracle port on torch CPU ops" % secs}
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "same_config": False,
+               "rows_per_step": 1 << 14, "gpu_rows_per_step": B,
+               "sample": "2^14 of 2^20 rows per step (same flow, same weights; samples/s is per-row), 1 warm-up + best of 3 "
+                         "(%.2f s/pass), oracle port on torch CPU ops" % secs}
 
     if rank == 0:
         line = {
@@ -359,7 +400,7 @@ def main():
             "config": {"workload": WORKLOAD, "global_batch": world * B, "l2": "inputs_larger_than_l2 (z = 268 MB per pass)",
                        "parallelism": "dp%d over sample rows" % world, "weights": "fan-in scaled synthetic, seed 0",
                        "noise": "device Philox4x32-10"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
+            "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
             "clocks": clock_info,
             "checks": {"finite": finite, "max_abs_logq_minus_logprob": consistency},
         }

@@ -224,6 +224,55 @@ int tnf_base_logq(const float* omega, double* log_q, int64_t rows, int D, tnf_st
 int tnf_finish_logq(double* log_q, const void* ld_acc, const void* scal, int64_t scal_div,
                     int64_t rows, int dtype, tnf_stream_t stream);
 
+/* ---- whole chains: replace the dispatch loops of NormFlow.forward
+ * (density_estimator.py:374-388) and NormFlow.inverse_and_log_det + log_prob (:393-416).
+ * The caller describes the chain once, in chain order, as an array of PODs; `params` is the flat
+ * (M, D_params) float32 matrix (row stride 0 = one shared row) and every bijector reads its slice at
+ * `param_offset` (:379-384, :398-402).  float32 z only.
+ *   kind              TNF_BIJ_*
+ *   num_layers, num_units, transform_upper   RealNVP arguments (ToSimplex: num_units = its D attribute)
+ *   packed            RealNVP: tnf_tc_pack image at `tc_precision` -> tensor-core kernel; NULL -> exact CUDA-core
+ *                     kernel
+ *   bn_mean, bn_alpha, bn_log_det   BatchNorm state (D, D, 1 device floats): READ by tnf_chain_logprob and by
+ *                     tnf_chain_sample(freeze_bn != 0) (remembered statistics, bijectors.py:397-399,420-426), WRITTEN
+ *                     by tnf_chain_sample(freeze_bn == 0) (batch statistics, :401-415)
+ *   consts            ToInterval: the 7 x D constant table of tnf_tointerval
+ * Small shared-weight chains of RealNVP / BatchNorm / Affine (D <= 32, U <= 64, <= 32768 parameters; BatchNorm with
+ * remembered statistics) run as ONE kernel with z in registers for the whole chain; all other chains run the
+ * per-bijector kernels back to back (BatchNorm / Affine folded into the next tensor-core coupling layer).
+ * tnf_chain_logprob:  log_prob (M, N) float32 = log N(z0; 0, I) - sum of log-dets.
+ * tnf_chain_sample:   z_out (M, N, D [+1 after ToSimplex]) float32 and log_q (M, N) float64; `omega` (device,
+ *   (M, N, D) float32) injects the base noise, NULL draws it on the device (Philox stream seed / offset).
+ *   `allreduce` (or NULL): data-parallel hook, called on the host after each BatchNorm's statistics kernel has been
+ *   enqueued; it must enqueue, on the same stream, an in-place sum over ranks of the 2*D+1 doubles in `stats_buf`
+ *   (caller-allocated device buffer, required with the hook) and return 0.
+ * `workspace`: tnf_chain_workspace_bytes(M, N, D) bytes of device memory, caller-owned. */
+enum { TNF_BIJ_REALNVP = 0, TNF_BIJ_BATCHNORM = 1, TNF_BIJ_AFFINE = 2, TNF_BIJ_TOINTERVAL = 3, TNF_BIJ_TOSIMPLEX = 4 };
+typedef struct tnf_bijector {
+  int kind;
+  int num_layers, num_units, transform_upper;
+  int64_t param_offset;
+  const void* packed;
+  float* bn_mean;
+  float* bn_alpha;
+  float* bn_log_det;
+  double bn_eps;
+  const float* consts;
+  void* ev_start; /* optional cudaEvent_t pair recorded on `stream` around this bijector's main kernel */
+  void* ev_stop;  /* (profiling: per-kernel device time inside a chain call); NULL = off */
+} tnf_bijector_t;
+typedef int (*tnf_allreduce_fn)(double* stats_buf, int count, void* user);
+size_t tnf_chain_workspace_bytes(int64_t M, int64_t N, int D);
+int tnf_chain_logprob(const tnf_bijector_t* chain, int n_bij, const float* z, const float* params,
+                      int64_t param_row_stride, int64_t M, int64_t N, int D, int tc_precision,
+                      float* log_prob, void* workspace, size_t workspace_bytes, tnf_stream_t stream);
+int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params,
+                     int64_t param_row_stride, int64_t M, int64_t N, int D, int tc_precision,
+                     const float* omega, uint64_t seed, uint64_t offset, int freeze_bn,
+                     tnf_allreduce_fn allreduce, void* allreduce_user, double* stats_buf,
+                     float* z_out, double* log_q, void* workspace, size_t workspace_bytes,
+                     tnf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,24 @@ PROTOTYPES = {
     "tnf_finish_logq": (I, [P, P, P, L, L, I, P]),
 }
 
+
+
+class Bijector(ctypes.Structure):
+    """tnf_bijector_t (include/tnf.h)."""
+    _fields_ = [("kind", c_int), ("num_layers", c_int), ("num_units", c_int), ("transform_upper", c_int),
+                ("param_offset", c_int64), ("packed", c_void_p), ("bn_mean", c_void_p), ("bn_alpha", c_void_p),
+                ("bn_log_det", c_void_p), ("bn_eps", c_double), ("consts", c_void_p), ("ev_start", c_void_p),
+                ("ev_stop", c_void_p)]
+
+
+TNF_BIJ_REALNVP, TNF_BIJ_BATCHNORM, TNF_BIJ_AFFINE, TNF_BIJ_TOINTERVAL, TNF_BIJ_TOSIMPLEX = 0, 1, 2, 3, 4
+ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_void_p)
+PROTOTYPES.update({
+    "tnf_chain_workspace_bytes": (Z, [L, L, I]),
+    "tnf_chain_logprob": (I, [P, I, P, P, L, L, L, I, I, P, P, Z, P]),
+    "tnf_chain_sample": (I, [P, I, P, L, L, L, I, I, P, U64, U64, I, ALLREDUCE_FN, P, P, P, P, P, Z, P]),
+})
+
 _LIB = None
 
 

@@ -81,3 +81,17 @@ def host_pipeline_min_rows():
 
 def host_pipeline_chunks():
     return _host_pipeline_chunks
+
+
+_chain_abi = os.environ.get("TNF_CHAIN_ABI", "1") != "0"
+
+
+def set_chain_abi(on):
+    """Route no-autograd float32 ``forward`` / ``log_prob`` through tnf_chain_sample / tnf_chain_logprob (default) or
+    through the per-bijector host plan (diagnostics)."""
+    global _chain_abi
+    _chain_abi = bool(on)
+
+
+def chain_abi():
+    return _chain_abi

@@ -1,0 +1,432 @@
+// Whole bijector chains behind one C-ABI call: tnf_chain_logprob / tnf_chain_sample.
+//
+// Replaces the dispatch loops of NormFlow.forward (torch_nf/density_estimator.py:374-388) and
+// NormFlow.inverse_and_log_det + log_prob (:393-416): the caller describes the chain once as a POD array
+// (tnf_bijector_t, chain order) and the library runs it.
+//
+//  * small shared-weight chains (RealNVP / BatchNorm with remembered statistics / Affine, D <= 32, U <= 64 - the
+//    reference's own test configurations and the LFI toy flows, C1 / C2a): ONE kernel, chain_small_kernel.  A thread
+//    owns a sample; z stays in registers for the whole chain, the chain's parameters (<= 128 KB) sit in shared memory
+//    and are read as broadcasts; the only HBM traffic is z in, log_prob (or z) out.  Those configurations are
+//    launch-bound (2^16 x D=8 samples are 3 us of HBM time), so the launch count is what matters.
+//  * everything else: the per-bijector kernels in the order and with the folding the host-side plan used
+//    (BatchNorm / Affine folded into the next tensor-core coupling kernel as a per-column pre-affine; the base
+//    density fused at the end), without returning to Python between launches.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace tnf {
+
+constexpr int kSmallMaxD = 32;
+constexpr int kSmallMaxU = 64;
+constexpr int kSmallMaxBij = 40;
+constexpr int kSmallMaxParams = 32768;   // floats of shared memory for the chain's parameter row (128 KB)
+
+struct SmallBij {
+  int kind, L, U, upper;
+  int poff;               // first parameter of this bijector inside the row
+  const float* a;         // BatchNorm: remembered mean (D)
+  const float* b;         // BatchNorm: remembered alpha (D)
+  const float* ld;        // BatchNorm: remembered log-det (1)
+};
+struct SmallChain {
+  int n, D, n_params, inverse;
+  SmallBij b[kSmallMaxBij];
+};
+
+// conditioner of one RealNVP layer for ONE sample: in[d_in] -> t[d_out], s[d_out]; parameters in shared memory
+__device__ __forceinline__ void small_conditioner(const float* __restrict__ p, const float* in, int d_in, int d_out, int U,
+                                                  int L, float* ht, float* hs, float* gt, float* gs, float* t,
+                                                  float* s) {
+  int K = d_in;
+  const float* src_t = in;
+  const float* src_s = in;
+  float* dst_t = ht;
+  float* dst_s = hs;
+  for (int l = 0; l <= L; ++l) {
+    const int J = l == L ? d_out : U;
+    const float* Wt = p;
+    const float* Ws = Wt + K * J;
+    const float* bt = Ws + K * J;
+    const float* bs = bt + J;
+    float* ot = l == L ? t : dst_t;
+    float* os = l == L ? s : dst_s;
+    for (int j = 0; j < J; ++j) {
+      float at = 0.f, as = 0.f;
+      for (int k = 0; k < K; ++k) {
+        at = fmaf(src_t[k], Wt[k * J + j], at);
+        as = fmaf(src_s[k], Ws[k * J + j], as);
+      }
+      at += bt[j];
+      as += bs[j];
+      ot[j] = l < L ? tanhf(at) : at;
+      os[j] = l < L ? tanhf(as) : as;
+    }
+    p = bs + J;
+    src_t = dst_t;
+    src_s = dst_s;
+    dst_t = dst_t == ht ? gt : ht;
+    dst_s = dst_s == hs ? gs : hs;
+    K = J;
+  }
+}
+
+// inverse != 0: z -> z0 through the chain backwards, out_lp = log N(z0) - sum log-dets (density_estimator.py:393-416);
+// inverse == 0 (remembered BatchNorm statistics only): omega -> z, log_q (f64) -= sum log-dets (:374-388)
+__global__ void __launch_bounds__(128) chain_small_kernel(SmallChain c, const float* __restrict__ z_in,
+                                                          const float* __restrict__ params, int64_t rows,
+                                                          float* __restrict__ z_out, float* __restrict__ out_lp,
+                                                          double* __restrict__ log_q) {
+  extern __shared__ float sp[];
+  for (int i = threadIdx.x; i < c.n_params; i += blockDim.x) sp[i] = params[i];
+  __syncthreads();
+  const int D = c.D;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    float z[kSmallMaxD];
+    float ht[kSmallMaxU], hs[kSmallMaxU], gt[kSmallMaxU], gs[kSmallMaxU], t[kSmallMaxD], s[kSmallMaxD];
+    for (int d = 0; d < D; ++d) z[d] = z_in[r * D + d];
+    float ld = 0.f;
+    for (int ii = 0; ii < c.n; ++ii) {
+      const SmallBij& b = c.b[c.inverse ? c.n - 1 - ii : ii];
+      if (b.kind == TNF_BIJ_REALNVP) {
+        const int h = D / 2;
+        const int d_in = b.upper ? h : D - h, d_out = D - d_in;
+        const int c_off = b.upper ? 0 : h, t_off = b.upper ? h : 0;
+        small_conditioner(sp + b.poff, z + c_off, d_in, d_out, b.U, b.L, ht, hs, gt, gs, t, s);
+        for (int j = 0; j < d_out; ++j) {
+          z[t_off + j] = c.inverse ? (z[t_off + j] - t[j]) / expf(s[j]) : t[j] + z[t_off + j] * expf(s[j]);
+          ld += s[j];
+        }
+      } else if (b.kind == TNF_BIJ_BATCHNORM) {
+        for (int d = 0; d < D; ++d) z[d] = c.inverse ? fmaf(z[d], b.b[d], b.a[d]) : (z[d] - b.a[d]) / b.b[d];
+        ld += b.ld[0];
+      } else {   // Affine: [alpha(D), shift(D)]
+        const float* al = sp + b.poff;
+        for (int d = 0; d < D; ++d) {
+          z[d] = c.inverse ? (z[d] - al[D + d]) / expf(al[d]) : fmaf(z[d], expf(al[d]), al[D + d]);
+          ld += al[d];
+        }
+      }
+    }
+    if (c.inverse) {
+      float ss = 0.f;
+      for (int d = 0; d < D; ++d) ss = fmaf(z[d], z[d], ss);
+      out_lp[r] = -0.5f * ss - (float)D * 0.91893853320467274178f - ld;
+    } else {
+      log_q[r] -= (double)ld;
+    }
+    if (z_out != nullptr)
+      for (int d = 0; d < D; ++d) z_out[r * D + d] = z[d];
+  }
+}
+
+// ---------------------------------------------------------------- executor helpers
+static bool small_chain_ok(const tnf_bijector_t* ch, int n, int D, int64_t Mp, int frozen_or_inverse) {
+  if (Mp != 1 || D > kSmallMaxD || n > kSmallMaxBij || !frozen_or_inverse) return false;
+  int64_t np = 0;
+  for (int i = 0; i < n; ++i) {
+    const tnf_bijector_t& b = ch[i];
+    if (b.kind == TNF_BIJ_REALNVP) {
+      if (b.packed != nullptr || b.num_units > kSmallMaxU || b.num_layers < 1 || b.num_layers > 5) return false;
+      const int h = D / 2, d_in = b.transform_upper ? h : D - h, d_out = D - d_in, U = b.num_units, L = b.num_layers;
+      np = b.param_offset + 2 * ((int64_t)d_in * U + (int64_t)d_out * U + d_out + U + (int64_t)(L - 1) * (U + 1) * U);
+    } else if (b.kind == TNF_BIJ_AFFINE) {
+      np = b.param_offset + 2 * D;
+    } else if (b.kind == TNF_BIJ_BATCHNORM) {
+      if (!b.bn_mean || !b.bn_alpha || !b.bn_log_det) return false;
+    } else {
+      return false;
+    }
+    if (np > kSmallMaxParams) return false;
+  }
+  return true;
+}
+
+static int launch_small(const tnf_bijector_t* ch, int n, int D, int inverse, const float* z_in, const float* params,
+                        int64_t rows, float* z_out, float* out_lp, double* log_q, cudaStream_t st) {
+  SmallChain c;
+  c.n = n; c.D = D; c.inverse = inverse; c.n_params = 0;
+  for (int i = 0; i < n; ++i) {
+    const tnf_bijector_t& b = ch[i];
+    c.b[i].kind = b.kind; c.b[i].L = b.num_layers; c.b[i].U = b.num_units; c.b[i].upper = b.transform_upper;
+    c.b[i].poff = (int)b.param_offset;
+    c.b[i].a = b.bn_mean; c.b[i].b = b.bn_alpha; c.b[i].ld = b.bn_log_det;
+    int64_t end = b.param_offset;
+    if (b.kind == TNF_BIJ_REALNVP) {
+      const int h = D / 2, d_in = b.transform_upper ? h : D - h, d_out = D - d_in, U = b.num_units, L = b.num_layers;
+      end += 2 * ((int64_t)d_in * U + (int64_t)d_out * U + d_out + U + (int64_t)(L - 1) * (U + 1) * U);
+    } else if (b.kind == TNF_BIJ_AFFINE) {
+      end += 2 * D;
+    }
+    if (end > c.n_params) c.n_params = (int)end;
+  }
+  const size_t smem = (size_t)c.n_params * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(chain_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("tnf_chain: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  int64_t blocks = (rows + 127) / 128;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  chain_small_kernel<<<(int)blocks, 128, smem, st>>>(c, z_in, params, rows, z_out, out_lp, log_q);
+  return check_launch("tnf_chain (fused small-chain kernel)");
+}
+
+struct Ws {   // carve the caller's workspace
+  unsigned char* p; size_t left;
+  void* take(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes > left) return nullptr;
+    void* r = p; p += bytes; left -= bytes; return r;
+  }
+};
+
+static bool all_tc(const tnf_bijector_t* ch, int n) {
+  bool any = false;
+  for (int i = 0; i < n; ++i)
+    if (ch[i].kind == TNF_BIJ_REALNVP) { if (!ch[i].packed) return false; any = true; }
+  return any;
+}
+
+}  // namespace tnf
+
+using namespace tnf;
+
+#define TNF_TRY(call)        \
+  do {                       \
+    int rc_ = (call);        \
+    if (rc_) return rc_;     \
+  } while (0)
+
+extern "C" {
+
+size_t tnf_chain_workspace_bytes(int64_t M, int64_t N, int D) {
+  const size_t rows = (size_t)(M * N);
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  return 2 * al(rows * (size_t)(D + 1) * 4) + al(rows * 4) + al((size_t)M * 4) + 4 * al((size_t)D * 4) +
+         al((size_t)(2 * D + 1) * 8) + al(tnf_colstats_workspace_bytes(D)) + 3 * al((size_t)D * 4) + 1024;
+}
+
+int tnf_chain_logprob(const tnf_bijector_t* chain, int n_bij, const float* z, const float* params,
+                      int64_t param_row_stride, int64_t M, int64_t N, int D, int tc_precision, float* log_prob,
+                      void* workspace, size_t workspace_bytes, tnf_stream_t stream) {
+  TNF_REQUIRE(chain && n_bij >= 1 && M >= 0 && N >= 0 && D >= 2, TNF_ERR_ARG, "tnf_chain_logprob: bad argument");
+  const int64_t rows = M * N;
+  if (rows == 0) return 0;
+  TNF_REQUIRE(z && params && log_prob, TNF_ERR_ARG, "tnf_chain_logprob: null pointer");
+  const int64_t Mp = param_row_stride == 0 ? 1 : M;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n_bij; ++i)
+    TNF_REQUIRE(chain[i].kind == TNF_BIJ_REALNVP || chain[i].kind == TNF_BIJ_BATCHNORM || chain[i].kind == TNF_BIJ_AFFINE ||
+                    chain[i].kind == TNF_BIJ_TOINTERVAL,
+                TNF_ERR_UNSUPPORTED, "tnf_chain_logprob: bijector kind %d has no inverse in a fused chain", chain[i].kind);
+  if (small_chain_ok(chain, n_bij, D, Mp, 1))
+    return launch_small(chain, n_bij, D, 1, z, params, rows, nullptr, log_prob, nullptr, st);
+
+  TNF_REQUIRE(workspace && workspace_bytes >= tnf_chain_workspace_bytes(M, N, D), TNF_ERR_ARG,
+              "tnf_chain_logprob: workspace of %zu bytes needed", tnf_chain_workspace_bytes(M, N, D));
+  Ws ws{(unsigned char*)workspace, workspace_bytes};
+  float* zb[2] = {(float*)ws.take((size_t)rows * (D + 1) * 4), (float*)ws.take((size_t)rows * (D + 1) * 4)};
+  float* ld_acc = (float*)ws.take((size_t)rows * 4);
+  float* scal = (float*)ws.take((size_t)Mp * 4);
+  float* pend[2][2] = {{(float*)ws.take((size_t)D * 4), (float*)ws.take((size_t)D * 4)},
+                       {(float*)ws.take((size_t)D * 4), (float*)ws.take((size_t)D * 4)}};
+  cudaMemsetAsync(ld_acc, 0, (size_t)rows * 4, st);
+  cudaMemsetAsync(scal, 0, (size_t)Mp * 4, st);
+  const bool fold = all_tc(chain, n_bij) && Mp == 1;
+  const int64_t Mk = Mp == 1 ? 1 : M, Nk = Mp == 1 ? rows : N;
+  const float* cur = z;
+  int nb = 0, np = 0;
+  bool have_pend = false;
+  auto out_buf = [&]() { float* o = zb[nb]; nb ^= 1; return o; };
+  auto flush_pend = [&]() -> int {
+    if (!have_pend) return 0;
+    float* o = out_buf();
+    TNF_TRY(tnf_colaffine(cur, o, pend[np ^ 1][0], pend[np ^ 1][1], rows, D, stream));
+    cur = o; have_pend = false;
+    return 0;
+  };
+  for (int i = n_bij - 1; i >= 0; --i) {
+    const tnf_bijector_t& b = chain[i];
+    const float* prm = params + b.param_offset;
+    if (b.kind == TNF_BIJ_REALNVP) {
+      float* o = out_buf();
+      if (b.packed) {
+        if (b.ev_start) cudaEventRecord((cudaEvent_t)b.ev_start, st);
+        TNF_TRY(tnf_coupling_tc(cur, o, ld_acc, b.packed, rows, D, b.num_units, b.num_layers, b.transform_upper, TNF_INVERSE,
+                                TNF_LD_ADD, have_pend ? pend[np ^ 1][0] : nullptr, have_pend ? pend[np ^ 1][1] : nullptr, nullptr,
+                                nullptr, tc_precision, 0, nullptr, stream));
+        if (b.ev_stop) cudaEventRecord((cudaEvent_t)b.ev_stop, st);
+        have_pend = false;
+      } else {
+        TNF_TRY(flush_pend());
+        TNF_TRY(tnf_coupling(cur, o, ld_acc, prm, param_row_stride, Mk, Nk, D, b.num_units, b.num_layers, b.transform_upper,
+                             TNF_INVERSE, TNF_LD_ADD, TNF_F32, stream));
+      }
+      cur = o;
+    } else if (b.kind == TNF_BIJ_BATCHNORM) {
+      TNF_REQUIRE(b.bn_mean && b.bn_alpha && b.bn_log_det, TNF_ERR_ARG, "tnf_chain_logprob: BatchNorm state missing");
+      if (fold) {
+        TNF_TRY(tnf_fold_colaffine(have_pend ? pend[np ^ 1][0] : nullptr, have_pend ? pend[np ^ 1][1] : nullptr, TNF_FOLD_BN_INV,
+                                   b.bn_mean, b.bn_alpha, pend[np][0], pend[np][1], nullptr, D, stream));
+        np ^= 1; have_pend = true;
+      } else {
+        float* o = out_buf();
+        TNF_TRY(tnf_bn_apply(cur, o, b.bn_mean, b.bn_alpha, rows, D, TNF_INVERSE, TNF_F32, stream));
+        cur = o;
+      }
+      TNF_TRY(tnf_accum_bcast(scal, b.bn_log_det, Mp, Mp, TNF_F32, stream));
+    } else if (b.kind == TNF_BIJ_AFFINE) {
+      if (fold) {
+        TNF_TRY(tnf_fold_colaffine(have_pend ? pend[np ^ 1][0] : nullptr, have_pend ? pend[np ^ 1][1] : nullptr, TNF_FOLD_AFF_INV,
+                                   prm, prm + D, pend[np][0], pend[np][1], scal, D, stream));
+        np ^= 1; have_pend = true;
+      } else {
+        float* o = out_buf();
+        float* ldm = o + (size_t)rows * D;   // (Mp) log-dets: each z buffer has `rows` extra floats at its tail
+        TNF_TRY(tnf_affine(cur, o, ldm, prm, param_row_stride, Mk, Nk, D, TNF_INVERSE, TNF_F32, stream));
+        TNF_TRY(tnf_accum_bcast(scal, ldm, Mp, 1, TNF_F32, stream));
+        cur = o;
+      }
+    } else {   // ToInterval
+      TNF_TRY(flush_pend());
+      float* o = out_buf();
+      TNF_TRY(tnf_tointerval(cur, o, ld_acc, b.consts, rows, D, TNF_INVERSE, TNF_LD_ADD, TNF_F32, stream));
+      cur = o;
+    }
+  }
+  TNF_TRY(flush_pend());
+  return tnf_base_logprob(cur, ld_acc, scal, Mp == M && M > 1 ? N : rows, log_prob, rows, D, TNF_F32, stream);
+}
+
+int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params, int64_t param_row_stride, int64_t M,
+                     int64_t N, int D, int tc_precision, const float* omega, uint64_t seed, uint64_t offset, int freeze_bn,
+                     tnf_allreduce_fn allreduce, void* allreduce_user, double* stats_buf, float* z_out, double* log_q,
+                     void* workspace, size_t workspace_bytes, tnf_stream_t stream) {
+  TNF_REQUIRE(chain && n_bij >= 1 && M >= 0 && N >= 0 && D >= 2, TNF_ERR_ARG, "tnf_chain_sample: bad argument");
+  const int64_t rows = M * N;
+  if (rows == 0) return 0;
+  TNF_REQUIRE(params && z_out && log_q, TNF_ERR_ARG, "tnf_chain_sample: null pointer");
+  const int64_t Mp = param_row_stride == 0 ? 1 : M;
+  cudaStream_t st = (cudaStream_t)stream;
+  int D_out = D;
+  for (int i = 0; i < n_bij; ++i) {
+    TNF_REQUIRE(chain[i].kind >= TNF_BIJ_REALNVP && chain[i].kind <= TNF_BIJ_TOSIMPLEX, TNF_ERR_UNSUPPORTED,
+                "tnf_chain_sample: bijector kind %d", chain[i].kind);
+    TNF_REQUIRE(chain[i].kind != TNF_BIJ_TOSIMPLEX || i == n_bij - 1, TNF_ERR_UNSUPPORTED,
+                "tnf_chain_sample: ToSimplex must be the last bijector");
+    if (chain[i].kind == TNF_BIJ_TOSIMPLEX) D_out = D + 1;
+  }
+  TNF_REQUIRE(workspace && workspace_bytes >= tnf_chain_workspace_bytes(M, N, D), TNF_ERR_ARG,
+              "tnf_chain_sample: workspace of %zu bytes needed", tnf_chain_workspace_bytes(M, N, D));
+  Ws ws{(unsigned char*)workspace, workspace_bytes};
+  float* zb[2] = {(float*)ws.take((size_t)rows * (D + 1) * 4), (float*)ws.take((size_t)rows * (D + 1) * 4)};
+  float* ld_acc = (float*)ws.take((size_t)rows * 4);
+  float* scal = (float*)ws.take((size_t)Mp * 4);
+  float* pend[2][2] = {{(float*)ws.take((size_t)D * 4), (float*)ws.take((size_t)D * 4)},
+                       {(float*)ws.take((size_t)D * 4), (float*)ws.take((size_t)D * 4)}};
+  double* sums_own = (double*)ws.take((size_t)(2 * D + 1) * 8);
+  void* stat_ws = ws.take(tnf_colstats_workspace_bytes(D));
+  double* sums = stats_buf ? stats_buf : sums_own;
+
+  // base draw (density_estimator.py:366-372): device Philox, or the injected omega
+  float* z0 = zb[0];
+  if (omega) {
+    cudaMemcpyAsync(z0, omega, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, st);
+    TNF_TRY(tnf_base_logq(z0, log_q, rows, D, stream));
+  } else {
+    TNF_TRY(tnf_base_sample(z0, log_q, rows, D, seed, offset, stream));
+  }
+  if (small_chain_ok(chain, n_bij, D, Mp, freeze_bn))
+    return launch_small(chain, n_bij, D, 0, z0, params, rows, z_out, nullptr, log_q, st);
+
+  cudaMemsetAsync(ld_acc, 0, (size_t)rows * 4, st);
+  cudaMemsetAsync(scal, 0, (size_t)Mp * 4, st);
+  const bool fold = all_tc(chain, n_bij) && Mp == 1;
+  const int64_t Mk = Mp == 1 ? 1 : M, Nk = Mp == 1 ? rows : N;
+  const float* cur = z0;
+  int nb = 1, np = 0;
+  bool have_pend = false, have_stats = false;
+  // the chain's last writer stores straight into z_out when nothing is pending after it
+  auto out_buf = [&]() { float* o = zb[nb]; nb ^= 1; return o; };
+  auto flush_pend = [&](float* dst) -> int {
+    if (!have_pend) return 0;
+    float* o = dst ? dst : out_buf();
+    TNF_TRY(tnf_colaffine(cur, o, pend[np ^ 1][0], pend[np ^ 1][1], rows, D, stream));
+    cur = o; have_pend = false;
+    return 0;
+  };
+  for (int i = 0; i < n_bij; ++i) {
+    const tnf_bijector_t& b = chain[i];
+    const float* prm = params + b.param_offset;
+    const bool last = i == n_bij - 1;
+    if (b.kind == TNF_BIJ_REALNVP) {
+      float* o = (last && D_out == D) ? z_out : out_buf();
+      if (b.packed) {
+        const bool want = !last && chain[i + 1].kind == TNF_BIJ_BATCHNORM && !freeze_bn && D <= 128 && tc_precision == TNF_TC_BF16;
+        if (b.ev_start) cudaEventRecord((cudaEvent_t)b.ev_start, st);
+        TNF_TRY(tnf_coupling_tc(cur, o, ld_acc, b.packed, rows, D, b.num_units, b.num_layers, b.transform_upper, TNF_FORWARD,
+                                TNF_LD_ADD, have_pend ? pend[np ^ 1][0] : nullptr, have_pend ? pend[np ^ 1][1] : nullptr,
+                                want ? sums : nullptr, want ? stat_ws : nullptr, tc_precision, 0, nullptr, stream));
+        if (b.ev_stop) cudaEventRecord((cudaEvent_t)b.ev_stop, st);
+        have_pend = false; have_stats = want;
+      } else {
+        TNF_TRY(flush_pend(nullptr));
+        TNF_TRY(tnf_coupling(cur, o, ld_acc, prm, param_row_stride, Mk, Nk, D, b.num_units, b.num_layers, b.transform_upper,
+                             TNF_FORWARD, TNF_LD_ADD, TNF_F32, stream));
+        have_stats = false;
+      }
+      cur = o;
+    } else if (b.kind == TNF_BIJ_BATCHNORM) {
+      TNF_REQUIRE(b.bn_mean && b.bn_alpha && b.bn_log_det, TNF_ERR_ARG, "tnf_chain_sample: BatchNorm state missing");
+      if (!freeze_bn) {
+        if (have_pend) { TNF_TRY(flush_pend(nullptr)); have_stats = false; }   // statistics are taken on the materialised tensor
+        if (!have_stats) TNF_TRY(tnf_colstats(cur, rows, D, sums, stat_ws, TNF_F32, stream));
+        if (allreduce) {
+          int rc = allreduce(sums, 2 * D + 1, allreduce_user);
+          TNF_REQUIRE(rc == 0, TNF_ERR_ARG, "tnf_chain_sample: the statistics all-reduce callback failed (%d)", rc);
+        }
+        TNF_TRY(tnf_bn_finalize(sums, D, b.bn_eps, b.bn_mean, b.bn_alpha, b.bn_log_det, TNF_F32, stream));
+      }
+      have_stats = false;
+      if (fold) {
+        TNF_TRY(tnf_fold_colaffine(have_pend ? pend[np ^ 1][0] : nullptr, have_pend ? pend[np ^ 1][1] : nullptr, TNF_FOLD_BN_FWD,
+                                   b.bn_mean, b.bn_alpha, pend[np][0], pend[np][1], nullptr, D, stream));
+        np ^= 1; have_pend = true;
+      } else {
+        float* o = (last && D_out == D) ? z_out : out_buf();
+        TNF_TRY(tnf_bn_apply(cur, o, b.bn_mean, b.bn_alpha, rows, D, TNF_FORWARD, TNF_F32, stream));
+        cur = o;
+      }
+      TNF_TRY(tnf_accum_bcast(scal, b.bn_log_det, Mp, Mp, TNF_F32, stream));
+    } else if (b.kind == TNF_BIJ_AFFINE) {
+      if (fold) {
+        TNF_TRY(tnf_fold_colaffine(have_pend ? pend[np ^ 1][0] : nullptr, have_pend ? pend[np ^ 1][1] : nullptr, TNF_FOLD_AFF_FWD,
+                                   prm, prm + D, pend[np][0], pend[np][1], scal, D, stream));
+        np ^= 1; have_pend = true;
+      } else {
+        float* o = out_buf();     // its log-det scratch lives in the buffer's tail, so never z_out
+        float* ldm = o + (size_t)rows * D;
+        TNF_TRY(tnf_affine(cur, o, ldm, prm, param_row_stride, Mk, Nk, D, TNF_FORWARD, TNF_F32, stream));
+        TNF_TRY(tnf_accum_bcast(scal, ldm, Mp, 1, TNF_F32, stream));
+        cur = o;
+      }
+      have_stats = false;
+    } else if (b.kind == TNF_BIJ_TOINTERVAL) {
+      TNF_TRY(flush_pend(nullptr));
+      float* o = last ? z_out : out_buf();
+      TNF_TRY(tnf_tointerval(cur, o, ld_acc, b.consts, rows, D, TNF_FORWARD, TNF_LD_ADD, TNF_F32, stream));
+      cur = o; have_stats = false;
+    } else {   // ToSimplex (last): (rows, D) -> (rows, D + 1)
+      TNF_TRY(flush_pend(nullptr));
+      TNF_TRY(tnf_tosimplex(cur, z_out, ld_acc, rows, D, b.num_units /* D attribute */, TNF_LD_ADD, TNF_F32, stream));
+      cur = z_out;
+    }
+  }
+  if (have_pend) TNF_TRY(flush_pend(z_out));
+  if (cur != z_out) cudaMemcpyAsync(z_out, cur, (size_t)rows * D_out * 4, cudaMemcpyDeviceToDevice, st);
+  return tnf_finish_logq(log_q, ld_acc, scal, Mp == M && M > 1 ? N : rows, rows, TNF_F32, stream);
+}
+
+}  // extern "C"

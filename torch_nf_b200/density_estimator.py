@@ -212,6 +212,10 @@ class NormFlow(DensityEstimator):
         pd = ops.to_device(params, torch.float32)
         self._check_params(pd)
         M = pd.size(0)
+        if not (torch.is_grad_enabled() and pd.requires_grad):
+            res = self._chain_sample(pd.detach(), M, N, omega, freeze_bn, home, src=params)
+            if res is not None:
+                return _to(res[0], home), _to(res[1], home)
         z, log_q = self._base(M, N, pd.device, omega)
         if torch.is_grad_enabled() and pd.requires_grad:
             z, log_q = self._forward_autograd(z, log_q, pd, freeze_bn)
@@ -277,6 +281,127 @@ class NormFlow(DensityEstimator):
         layer of the chain runs on that path (shared weights, fp32, bf16-conditioner mode)."""
         cps = [b for b in self.bijectors if b.name == "RealNVP"]
         return bool(cps) and all(self._use_tc(b, pd, z) for b in cps)
+
+    # ---- whole-chain C-ABI calls (tnf_chain_logprob / tnf_chain_sample) -----------------------------------
+    def _chain_pod(self, pd, z_like, src, sample, freeze_bn=False):
+        """The chain as a ``tnf_bijector_t`` array (include/tnf.h) plus the objects that must stay alive during the
+        call, or None when a bijector is outside the executor (MAF, user-defined bijectors)."""
+        from . import _lib
+        dev = pd.device
+        arr = (_lib.Bijector * len(self.bijectors))()
+        keep, bn_new = [], []
+        for i, (b, idx, n) in enumerate(self._slices()):
+            e = arr[i]
+            e.param_offset = idx
+            if b.name == "RealNVP":
+                e.kind, e.num_layers, e.num_units, e.transform_upper = _lib.TNF_BIJ_REALNVP, b.num_layers, b.num_units, int(b.transform_upper)
+                if self._use_tc(b, pd, z_like):
+                    packed = self._packed(b, idx, n, pd, src)
+                    keep.append(packed)
+                    e.packed = packed.data_ptr()
+                    if ops.kernel_timer is not None:      # bench.py: device time of every tensor-core coupling launch
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(); e1.record()          # creates the cudaEvent_t handles; re-recorded by the library
+                        e.ev_start, e.ev_stop = e0.cuda_event, e1.cuda_event
+                        ops.kernel_timer.append((e0, e1))
+            elif b.name == "BatchNorm":
+                e.kind, e.bn_eps = _lib.TNF_BIJ_BATCHNORM, float(b.eps)
+                if sample and not freeze_bn:     # the call WRITES the batch statistics
+                    mean = torch.empty(b.D, dtype=torch.float32, device=dev)
+                    alpha = torch.empty(b.D, dtype=torch.float32, device=dev)
+                    ld = torch.empty((), dtype=torch.float32, device=dev)
+                    bn_new.append((b, mean, alpha, ld))
+                else:
+                    mean, alpha = b._state_on(dev, torch.float32)
+                    ld = b._last_ld.to(device=dev, dtype=torch.float32)
+                keep += [mean, alpha, ld]
+                e.bn_mean, e.bn_alpha, e.bn_log_det = mean.data_ptr(), alpha.data_ptr(), ld.data_ptr()
+            elif b.name == "Affine":
+                e.kind = _lib.TNF_BIJ_AFFINE
+            elif b.name == "ToInterval":
+                e.kind = _lib.TNF_BIJ_TOINTERVAL
+                c = b._consts(dev)
+                keep.append(c)
+                e.consts = c.data_ptr()
+            elif b.name == "ToSimplex" and sample:
+                e.kind, e.num_units = _lib.TNF_BIJ_TOSIMPLEX, b.D
+            else:
+                return None
+        return arr, keep, bn_new
+
+    def _chain_logprob(self, zd, pd, src=None, use_tc=None):
+        """log_prob of device samples through ONE C-ABI call; None when the chain needs the per-bijector plan."""
+        from . import _lib
+        if zd.dtype != torch.float32 or pd.dtype != torch.float32 or not config.chain_abi():
+            return None
+        M, N, D = zd.shape
+        z_like = zd if use_tc is None else _Rows(M, (1 << 40) if use_tc else 0, zd.dtype)
+        pod = self._chain_pod(pd, z_like, src, sample=False)
+        if pod is None:
+            return None
+        arr, keep, _ = pod
+        Mp = pd.shape[0]
+        if Mp != M and Mp != 1:
+            raise ValueError("params has %d rows but z has M=%d" % (Mp, M))
+        lp = torch.empty((M, N), dtype=torch.float32, device=zd.device)
+        nbytes = _lib.lib().tnf_chain_workspace_bytes(M, N, D)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=zd.device)
+        prec = ops.TC_PRECISION.get(config.tc_precision(), 0)
+        rc = _lib.lib().tnf_chain_logprob(arr, len(self.bijectors), zd.data_ptr(), pd.data_ptr(),
+                                          pd.stride(0) if Mp > 1 else 0, M, N, D, prec, lp.data_ptr(), ws.data_ptr(),
+                                          nbytes, ops._stream())
+        _lib.check(rc, "tnf_chain_logprob")
+        return lp
+
+    def _chain_sample(self, pd, M, N, omega, freeze_bn, home, src=None):
+        """(z, log_q) through ONE C-ABI call; None when the chain needs the per-bijector plan."""
+        from . import _lib, dist
+        if pd.dtype != torch.float32 or not config.chain_abi():
+            return None
+        dev = pd.device
+        D = self.D
+        pod = self._chain_pod(pd, _Rows(M, N, torch.float32), src, sample=True, freeze_bn=freeze_bn)
+        if pod is None:
+            return None
+        arr, keep, bn_new = pod
+        Mp = pd.shape[0]
+        d_out = D + 1 if self.bijectors and self.bijectors[-1].name == "ToSimplex" else D
+        z = torch.empty((M, N, d_out), dtype=torch.float32, device=dev)
+        log_q = torch.empty((M, N), dtype=torch.float64, device=dev)
+        seed = 0
+        om_ptr = 0
+        if omega is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + 12345
+        else:
+            if isinstance(omega, np.ndarray):
+                omega = torch.from_numpy(np.ascontiguousarray(omega))
+            if tuple(omega.shape) != (M, N, D):
+                raise ValueError("omega must have shape %s, got %s" % ((M, N, D), tuple(omega.shape)))
+            omega = ops.to_device(omega, torch.float32).contiguous()
+            om_ptr = omega.data_ptr()
+        nbytes = _lib.lib().tnf_chain_workspace_bytes(M, N, D)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        stats = None
+        cb = _lib.ALLREDUCE_FN(0)
+        if dist.is_enabled() and dist.world_size() > 1 and not freeze_bn:
+            stats = torch.empty(2 * D + 1, dtype=torch.float64, device=dev)
+
+            def _hook(_ptr, _count, _user, _stats=stats):
+                try:
+                    dist.allreduce_stats(_stats)       # in place, enqueued on the current stream
+                    return 0
+                except Exception:                      # never unwind through the C frame
+                    return 1
+            cb = _lib.ALLREDUCE_FN(_hook)
+        prec = ops.TC_PRECISION.get(config.tc_precision(), 0)
+        rc = _lib.lib().tnf_chain_sample(arr, len(self.bijectors), pd.data_ptr(), pd.stride(0) if Mp > 1 else 0, M, N, D,
+                                         prec, om_ptr, seed & (2 ** 64 - 1), 0, int(bool(freeze_bn)), cb, None,
+                                         stats.data_ptr() if stats is not None else None, z.data_ptr(), log_q.data_ptr(),
+                                         ws.data_ptr(), nbytes, ops._stream())
+        _lib.check(rc, "tnf_chain_sample")
+        for (b, mean, alpha, ld) in bn_new:
+            b._set_state(mean, alpha, ld, home)
+        return z, log_q
 
     def _forward_plan(self, z, log_q, pd, freeze_bn, home=None, src=None):
         M, N, D = z.shape
@@ -467,8 +592,11 @@ class NormFlow(DensityEstimator):
         ev = issue_copy(*bounds[0])
         for i, (lo, hi) in enumerate(bounds):
             compute.wait_event(ev)
-            z0, ld_acc, scal, div = self._inverse_plan(zd[:, lo:hi], pd, src=src, use_tc=use_tc)
-            lp[:, lo:hi] = ops.base_logprob(z0, ld_acc, scal, div)
+            part = self._chain_logprob(zd[:, lo:hi], pd, src=src, use_tc=use_tc)
+            if part is None:
+                z0, ld_acc, scal, div = self._inverse_plan(zd[:, lo:hi], pd, src=src, use_tc=use_tc)
+                part = ops.base_logprob(z0, ld_acc, scal, div)
+            lp[:, lo:hi] = part
             if i + 1 < len(bounds):                            # queued after chunk i's kernels: a pageable source blocks
                 ev = issue_copy(*bounds[i + 1])                # the host here while the GPU works on chunk i
         return lp
@@ -494,9 +622,18 @@ class NormFlow(DensityEstimator):
             z0, sld = self._inverse_autograd(zd, pd)
             lp = _BaseLogProbFn.apply(z0) - sld
         else:
-            z0, ld_acc, scal, div = self._inverse_plan(zd.detach().contiguous(), pd.detach(), src=params)
-            lp = ops.base_logprob(z0, ld_acc, scal, div)
+            lp = self._chain_logprob(zd.detach().contiguous(), pd.detach(), src=params)
+            if lp is None:
+                z0, ld_acc, scal, div = self._inverse_plan(zd.detach().contiguous(), pd.detach(), src=params)
+                lp = ops.base_logprob(z0, ld_acc, scal, div)
         return _to(lp, home)
+
+
+class _Rows(object):
+    """Stand-in for a z tensor in ``_use_tc`` (shape and dtype are all it reads)."""
+
+    def __init__(self, M, N, dtype):
+        self.shape, self.dtype = (M, N, 0), dtype
 
 
 _copy_streams = {}
