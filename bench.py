@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="samples per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32_cc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch rows per GPU (default); strong: --batch rows in total, split over the ranks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-parity measurement of the same step")
     args = ap.parse_args()
@@ -263,7 +265,7 @@ def main():
     tnf.set_conditioner_precision(args.precision)
     _lib.lib()
 
-    B = args.batch
+    B = args.batch if args.scaling == "weak" else -(-args.batch // world)
     nf = de.NormFlow(D, True, "coupling", STAGES, L, U)
     params_host = torch.tensor(synthetic_params(chain_spec(nf.bijectors), D, 1, seed=0)).pin_memory()
     params = params_host.to(dev)
@@ -395,7 +397,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "l2": "inputs_larger_than_l2 (z = 268 MB per pass)",
                        "parallelism": "dp%d over sample rows" % world, "weights": "fan-in scaled synthetic, seed 0",

@@ -1550,8 +1550,12 @@ int tnf_tc_supported(int D, int U, int L, int precision) {
   return precision == TNF_TC_BF16 && tc::shape_supported(D, U, L) ? 1 : 0;
 }
 
+// the D = 256 bf16 layer runs on the TMEM-resident single-tile kernel (coupling_tc6.cu, unsplit) with ITS packed format
+static bool bf16_on_tc6(int D, int U, int L) { return D == 256 && tc::shape_supported6(D, U, L); }
+
 size_t tnf_tc_packed_bytes(int D, int U, int L, int precision) {
-  if (precision == TNF_TC_FP32) return tc::shape_supported6(D, U, L) ? tc::packed_bytes6(D, U, L) : 0;
+  if (precision == TNF_TC_FP32) return tc::shape_supported6(D, U, L) ? tc::packed_bytes6(D, U, L, 1) : 0;
+  if (precision == TNF_TC_BF16 && bf16_on_tc6(D, U, L)) return tc::packed_bytes6(D, U, L, 0);
   if (!tc::shape_supported(D, U, L) || precision != TNF_TC_BF16) return 0;
   return (size_t)tc::Shape(D, U, L, 1).packed_bytes();
 }
@@ -1562,8 +1566,8 @@ int tnf_tc_pack(const float* params, void* packed, int D, int U, int L, int tran
               "tnf_tc_pack: shape D=%d U=%d L=%d not supported at precision %d", D, U, L, precision);
   TNF_REQUIRE(params && packed, TNF_ERR_ARG, "tnf_tc_pack: null pointer");
   TNF_REQUIRE(((uintptr_t)packed & 15) == 0, TNF_ERR_ALIGN, "tnf_tc_pack: packed buffer must be 16-byte aligned");
-  if (precision == TNF_TC_FP32) {
-    tc::pack6_launch(params, packed, D, U, L, transform_upper != 0, (cudaStream_t)stream);
+  if (precision == TNF_TC_FP32 || bf16_on_tc6(D, U, L)) {
+    tc::pack6_launch(params, packed, D, U, L, transform_upper != 0, precision == TNF_TC_FP32, (cudaStream_t)stream);
     return check_launch("tnf_tc_pack");
   }
   tc::Shape sh(D, U, L, transform_upper != 0);
@@ -1577,23 +1581,26 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
                     void* debug, tnf_stream_t stream) {
   TNF_REQUIRE(tnf_tc_supported(D, U, L, precision), TNF_ERR_UNSUPPORTED,
               "tnf_coupling_tc: shape D=%d U=%d L=%d not supported at precision %d", D, U, L, precision);
-  if (precision == TNF_TC_FP32) {   // fp32-parity kernel: own packed format, one tile per CTA, CTA pairs
+  if (precision == TNF_TC_FP32 || bf16_on_tc6(D, U, L)) {   // TMEM-resident single-tile kernel
+    const int split6 = precision == TNF_TC_FP32;
+    TNF_REQUIRE((variant & 15) == 0, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: this shape / precision has one kernel (variant 0)");
     TNF_REQUIRE(rows >= 0, TNF_ERR_ARG, "tnf_coupling_tc: rows < 0");
     if (rows == 0) return 0;
     TNF_REQUIRE(z_in && z_out && log_det && packed, TNF_ERR_ARG, "tnf_coupling_tc: null pointer");
     TNF_REQUIRE((((uintptr_t)z_in | (uintptr_t)z_out | (uintptr_t)packed) & 15) == 0, TNF_ERR_ALIGN,
                 "tnf_coupling_tc: z and packed weights must be 16-byte aligned");
-    TNF_REQUIRE(col_stats == nullptr, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: no fused column statistics in fp32 mode");
+    TNF_REQUIRE(col_stats == nullptr, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: no fused column statistics in this kernel");
     const int64_t n_super6 = ((rows + tc::kTileM - 1) / tc::kTileM + 1) / 2;
     const int64_t max_pairs6 = num_sms() / 2;
     const int grid6 = 2 * (int)(n_super6 < max_pairs6 ? n_super6 : max_pairs6);
     int ns = 10;
-    while (ns > 2 && tc::smem_bytes6(D, U, L, ns) > 227 * 1024) --ns;
-    const size_t smem6 = tc::smem_bytes6(D, U, L, ns);
+    while (ns > 2 && tc::smem_bytes6(D, U, L, split6, ns) > 227 * 1024) --ns;
+    const size_t smem6 = tc::smem_bytes6(D, U, L, split6, ns);
+    TNF_REQUIRE(ns >= 4, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: only %d weight stages fit (a job needs up to 4)", ns);
     TNF_REQUIRE(smem6 <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem6);
     tc::Args a6{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
                 D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, ns, 2, variant >> 8, nullptr, (long long*)debug};
-    cudaError_t e6 = (cudaError_t)tc::launch_tc6(a6, grid6, ns, smem6, (cudaStream_t)stream);
+    cudaError_t e6 = (cudaError_t)tc::launch_tc6(a6, grid6, split6, smem6, (cudaStream_t)stream);
     if (e6 != cudaSuccess) {
       set_error("tnf_coupling_tc: cudaFuncSetAttribute(%zu B smem): %s", smem6, cudaGetErrorString(e6));
       return (int)e6;

@@ -17,6 +17,10 @@
 // from tensor memory and accumulates into the other region.  The first layer's A operand (the conditioning half of z)
 // comes from hi / lo shared-memory images written by the two I/O warps (double buffered across tiles).
 //
+// The same kernel without the split (kSplit = false: bf16 operands, one MMA per product, tanh.approx) is the bf16
+// path of the D = 256 layer (BASELINE.json configuration 5), whose activation images do not fit shared memory next to
+// two tiles: here they need none.
+//
 // Job sequence per tile and net (t, then s): (0,a) (0,b) (1,a) (1,b) ... (L-1,a) (L-1,b) final.
 // Reference semantics: torch_nf/bijectors.py:145-242 (RealNVP).
 #include <cuda_fp16.h>
@@ -31,19 +35,21 @@ constexpr int kBiasPad6 = 4096;                    // zero block after the resid
 constexpr int kMaxStages6 = 10;                    // weight ring: as many 16 KB stages as fit (no activation images here)
 
 struct Shape6 {
-  int D, U, L, upper, DH, Q, NBF, c_off, t_off;
-  __host__ __device__ Shape6(int D_, int U_, int L_, int upper_) : D(D_), U(U_), L(L_), upper(upper_) {
+  int D, U, L, upper, split, DH, Q, NBF, c_off, t_off;
+  // split != 0: fp16 hi + lo images (fp32 parity); 0: one bf16 image
+  __host__ __device__ Shape6(int D_, int U_, int L_, int upper_, int split_ = 1) : D(D_), U(U_), L(L_), upper(upper_), split(split_) {
     DH = D / 2; Q = U / 4; NBF = DH / 2;
     c_off = upper ? 0 : DH;
     t_off = upper ? DH : 0;
   }
   __host__ __device__ int K_of(int l) const { return l == 0 ? DH : U; }
   __host__ __device__ int NB_of(int l) const { return l < L ? Q : NBF; }          // B rows per CTA of one job
-  __host__ __device__ int KS_of(int l) const {                                     // K rows per 16 KB stage (hi + lo)
-    const int ks = 4096 / NB_of(l);
+  __host__ __device__ int ebytes() const { return split ? 4 : 2; }                  // bytes per weight element in a stage
+  __host__ __device__ int KS_of(int l) const {                                     // K rows per 16 KB stage
+    const int ks = (kStageBytes / ebytes()) / NB_of(l);
     return ks < K_of(l) ? ks : K_of(l);
   }
-  __host__ __device__ int64_t job_bytes(int l) const { return (int64_t)K_of(l) * NB_of(l) * 4; }   // hi + lo, one half
+  __host__ __device__ int64_t job_bytes(int l) const { return (int64_t)K_of(l) * NB_of(l) * ebytes(); }   // one half
   __host__ __device__ int64_t net_bytes() const {
     int64_t b = 0;
     for (int l = 0; l < L; ++l) b += 2 * job_bytes(l);
@@ -64,9 +70,9 @@ struct Shape6 {
 };
 
 bool shape_supported6(int D, int U, int L) {
-  return (D == 64 || D == 128) && (U == 128 || U == 256) && L >= 1 && L <= 5;
+  return (D == 64 || D == 128 || D == 256) && (U == 128 || U == 256) && L >= 1 && L <= 5;
 }
-size_t packed_bytes6(int D, int U, int L) { return (size_t)Shape6(D, U, L, 1).packed_bytes(); }
+size_t packed_bytes6(int D, int U, int L, int split) { return (size_t)Shape6(D, U, L, 1, split).packed_bytes(); }
 
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {   // low half = first (lower K index) element
   uint32_t r;
@@ -112,11 +118,15 @@ __global__ void pack6_kernel(const float* __restrict__ params, unsigned char* __
     const int h = l < sh.L ? j / (2 * sh.Q) : 0;
     const int rank = l < sh.L ? (j / sh.Q) & 1 : j / sh.NBF;
     const int n = j % NB;
-    unsigned char* stage = packed + sh.w_off(rank, net, l, h) + (int64_t)(k / KS) * KS * NB * 4;
-    const __half hi = __float2half_rn(w);
-    const __half lo = __float2half_rn(w - __half2float(hi));
-    *reinterpret_cast<__half*>(stage + img_off(n, k % KS, NB)) = hi;
-    *reinterpret_cast<__half*>(stage + (int64_t)KS * NB * 2 + img_off(n, k % KS, NB)) = lo;
+    unsigned char* stage = packed + sh.w_off(rank, net, l, h) + (int64_t)(k / KS) * KS * NB * sh.ebytes();
+    if (sh.split) {
+      const __half hi = __float2half_rn(w);
+      const __half lo = __float2half_rn(w - __half2float(hi));
+      *reinterpret_cast<__half*>(stage + img_off(n, k % KS, NB)) = hi;
+      *reinterpret_cast<__half*>(stage + (int64_t)KS * NB * 2 + img_off(n, k % KS, NB)) = lo;
+    } else {
+      *reinterpret_cast<__nv_bfloat16*>(stage + img_off(n, k % KS, NB)) = __float2bfloat16_rn(w);
+    }
   }
   int nb = sh.L * sh.U + sh.DH;   // biases per net
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * nb; idx += stride) {
@@ -134,18 +144,26 @@ __global__ void pack6_kernel(const float* __restrict__ params, unsigned char* __
     const int h = l < sh.L ? rem / (2 * sh.Q) : 0;
     const int rank = l < sh.L ? (rem / sh.Q) & 1 : rem / sh.NBF;
     const int n = rem % sh.NB_of(l);
-    __half* blk = reinterpret_cast<__half*>(packed + sh.bias_base(rank) + sh.bias_off(net, l, h) + (int64_t)n * 16);
-    const __half b0 = __float2half_rn(b);
-    const float r1 = b - __half2float(b0);
-    const __half b1 = __float2half_rn(r1);
-    const __half b2 = __float2half_rn(r1 - __half2float(b1));
-    blk[0] = b0; blk[1] = b1; blk[2] = b2;
-    for (int kk = 3; kk < 8; ++kk) blk[kk] = __float2half_rn(0.f);
+    unsigned char* blkp = packed + sh.bias_base(rank) + sh.bias_off(net, l, h) + (int64_t)n * 16;
+    if (sh.split) {
+      __half* blk = reinterpret_cast<__half*>(blkp);
+      const __half b0 = __float2half_rn(b);
+      const float r1 = b - __half2float(b0);
+      const __half b1 = __float2half_rn(r1);
+      const __half b2 = __float2half_rn(r1 - __half2float(b1));
+      blk[0] = b0; blk[1] = b1; blk[2] = b2;
+      for (int kk = 3; kk < 8; ++kk) blk[kk] = __float2half_rn(0.f);
+    } else {
+      __nv_bfloat16* blk = reinterpret_cast<__nv_bfloat16*>(blkp);
+      const __nv_bfloat16 b0 = __float2bfloat16_rn(b);
+      blk[0] = b0; blk[1] = __float2bfloat16_rn(b - __bfloat162float(b0)); blk[2] = __float2bfloat16_rn(0.f);
+      for (int kk = 3; kk < 8; ++kk) blk[kk] = __float2bfloat16_rn(0.f);
+    }
   }
 }
 
-int pack6_launch(const float* params, void* packed, int D, int U, int L, int upper, cudaStream_t st) {
-  Shape6 sh(D, U, L, upper);
+int pack6_launch(const float* params, void* packed, int D, int U, int L, int upper, int split, cudaStream_t st) {
+  Shape6 sh(D, U, L, upper, split);
   pack6_kernel<<<num_sms() * 4, 256, 0, st>>>(params, (unsigned char*)packed, sh);
   return 0;
 }
@@ -167,15 +185,14 @@ struct __align__(16) Ctrl6 {
 // dynamic shared memory:
 //   [ring: S x 16 KB][A1 hi/lo x 2 buffers][ones 4 KB][Ctrl6][pre_scale D][pre_shift D][ld partial 4 x 128]
 //   [resident bias blocks of this rank][4 KB zeros]
-size_t smem_bytes6(int D, int U, int L, int n_stages) {
-  Shape6 sh(D, U, L, 1);
-  return (size_t)n_stages * kStageBytes + 4 * sh.a1_bytes() + kOnesBytes + sizeof(Ctrl6) +
+size_t smem_bytes6(int D, int U, int L, int split, int n_stages) {
+  Shape6 sh(D, U, L, 1, split);
+  return (size_t)n_stages * kStageBytes + (split ? 4 : 2) * sh.a1_bytes() + kOnesBytes + sizeof(Ctrl6) +
          (size_t)(2 * sh.D + 4 * kTileM) * sizeof(float) + (size_t)sh.bias_rank_bytes() + kBiasPad6;
 }
 
-__host__ __device__ inline uint32_t make_idesc6(int N) {   // dense, D = f32, A = B = f16, K-major, M = 256 (pair)
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
+// dense, D = f32, A = B = f16 (split) or bf16, K-major, M = 256 (pair)
+__host__ __device__ inline uint32_t make_idesc6(int N, bool split) { return split ? ((1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24)) : make_idesc2(N); }
 
 // One job of the MMA warp: bias MMA (ones image x resident bias block), then for all K the two CORRECTION products
 // (A_lo, W_hi) (A_hi, W_lo), then for all K the main product (A_hi, W_hi).  Order matters: the tensor core rounds the
@@ -186,18 +203,19 @@ __host__ __device__ inline uint32_t make_idesc6(int N) {   // dense, D = f32, A 
 // kTS: A operand from tensor memory (in-place activations: chunk c = kk/2 holds the hi pairs of its units at columns
 // 32c + 8*(kk%2) .. +8 and the lo pairs 16 columns further); else from the hi / lo shared-memory images (descriptor low
 // words a0 / a1, +256 per K step).
-template <int K, int N, bool kTS>
+template <int K, int N, bool kTS, bool kSplit>
 __device__ __forceinline__ void mma_job6(uint32_t d_tmem, uint32_t a0, uint32_t a1, uint32_t a_dhi, uint32_t ring16,
                                          uint32_t b_hi, uint32_t ones_lo, uint32_t bias_lo, uint32_t wfull0,
                                          uint32_t wpeer0, uint32_t wempty0, uint32_t S, uint32_t& slot, uint32_t& phase,
                                          bool leader, long long* t_w) {
   constexpr int NB = N / 2;
-  constexpr int KS = (4096 / NB) < K ? (4096 / NB) : K;
+  constexpr int KSMAX = (kStageBytes / (kSplit ? 4 : 2)) / NB;
+  constexpr int KS = KSMAX < K ? KSMAX : K;
   constexpr int SPS = KS / 16;                                   // K steps per stage
   constexpr int NST = K / KS;                                    // stages of this job
   constexpr uint32_t kStage16 = kStageBytes >> 4;
   constexpr uint32_t kLo16 = (uint32_t)(KS * NB * 2) >> 4;       // W_lo image inside the stage
-  const uint32_t idesc = make_idesc6(N);
+  const uint32_t idesc = make_idesc6(N, kSplit);
   uint32_t sl[NST];
   {
     const long long c0 = t_w ? clock64() : 0;
@@ -215,7 +233,7 @@ __device__ __forceinline__ void mma_job6(uint32_t d_tmem, uint32_t a0, uint32_t 
   if (leader) {
     umma2_ss2(d_tmem, ones_lo, a_dhi, bias_lo, b_hi, idesc, 0u);
 #pragma unroll
-    for (int kk = 0; kk < K / 16; ++kk) {
+    for (int kk = 0; kk < (kSplit ? K / 16 : 0); ++kk) {
       const uint32_t bw = ring16 + sl[kk / SPS] * kStage16 + (uint32_t)((kk % SPS) * 2 * NB);   // 2 K groups x NB rows x 16 B
       if (kTS) {
         const uint32_t col = (uint32_t)(32 * (kk / 2) + 8 * (kk % 2));
@@ -238,15 +256,16 @@ __device__ __forceinline__ void mma_job6(uint32_t d_tmem, uint32_t a0, uint32_t 
   if (slot >= S) { slot -= S; phase ^= 1u; }
 }
 
-template <bool kInverse, int DH, int U_>
+template <bool kInverse, int DH, int U_, bool kSplit>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupling_tc6_kernel(Args a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const Shape6 sh(a.D, a.U, a.L, a.upper);
+  const Shape6 sh(a.D, a.U, a.L, a.upper, kSplit ? 1 : 0);
+  constexpr int kImgs = kSplit ? 2 : 1;            // A1 images per buffer (hi, lo | bf16)
   const int L = sh.L;
   const uint32_t S = (uint32_t)a.n_stages;
   unsigned char* ring = smem_raw;
   unsigned char* sA1 = ring + (size_t)S * kStageBytes;            // [buffer][hi | lo]
-  unsigned char* sOnes = sA1 + 4 * sh.a1_bytes();
+  unsigned char* sOnes = sA1 + 2 * kImgs * sh.a1_bytes();
   Ctrl6& ct = *reinterpret_cast<Ctrl6*>(sOnes + kOnesBytes);
   float* s_pscale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl6));
   float* s_pshift = s_pscale + sh.D;
@@ -275,7 +294,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
     // ones image: row r, K columns 0, 1, 2 = 1.0 (fp16 0x3c00), everything else 0
     for (int i = threadIdx.x; i < kOnesBytes / 4; i += blockDim.x) {
       uint32_t v = 0u;
-      if (i < kTileM * 4) v = (i & 3) == 0 ? 0x3c003c00u : ((i & 3) == 1 ? 0x00003c00u : 0u);
+      if (i < kTileM * 4) {
+        if (kSplit) v = (i & 3) == 0 ? 0x3c003c00u : ((i & 3) == 1 ? 0x00003c00u : 0u);   // fp16 1.0 in K columns 0, 1, 2
+        else v = (i & 3) == 0 ? 0x3f803f80u : 0u;                                          // bf16 1.0 in K columns 0, 1
+      }
       reinterpret_cast<uint32_t*>(sOnes)[i] = v;
     }
     for (int i = threadIdx.x; i < sh.D; i += blockDim.x) {
@@ -304,7 +326,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
         for (int net = 0; net < 2; ++net) {
           for (int l = 0; l <= L; ++l) {
             const int KS = sh.KS_of(l), NB = sh.NB_of(l);
-            const uint32_t bytes = (uint32_t)(KS * NB * 4);
+            const uint32_t bytes = (uint32_t)(KS * NB * sh.ebytes());
             for (int h = 0; h < (l < L ? 2 : 1); ++h) {
               const unsigned char* src = a.packed + sh.w_off((int)rank, net, l, h);
               for (int st = 0; st < sh.K_of(l) / KS; ++st) {
@@ -371,23 +393,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
           tc_fence_after();
           if (diag) t_dep += clock64() - c0;
           const uint32_t rD = tmem + (uint32_t)((l & 1) * 256), rA = tmem + (uint32_t)(((l + 1) & 1) * 256);
-          const uint32_t a1h = (uint32_t)a1_desc + (2u * buf) * a1_sz16, a1l = a1h + a1_sz16;
+          const uint32_t a1h = (uint32_t)a1_desc + ((uint32_t)kImgs * buf) * a1_sz16, a1l = a1h + a1_sz16;
           if (l < L) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const uint32_t bias_lo = lboH + bias16 + (uint32_t)(sh.bias_off(net, l, h) >> 4);
               if (l == 0)
-                mma_job6<DH, U_ / 2, false>(rD + (uint32_t)(h * (U_ / 2)), a1h, a1l, a_dhi, lboH + ring16, bH_hi, ones_lo, bias_lo,
+                mma_job6<DH, U_ / 2, false, kSplit>(rD + (uint32_t)(h * (U_ / 2)), a1h, a1l, a_dhi, lboH + ring16, bH_hi, ones_lo, bias_lo,
                                             wfull0, wpeer0, wempty0, S, slot, phase, leader, tw);
               else
-                mma_job6<U_, U_ / 2, true>(rD + (uint32_t)(h * (U_ / 2)), rA, 0u, a_dhi, lboH + ring16, bH_hi, ones_lo, bias_lo,
+                mma_job6<U_, U_ / 2, true, kSplit>(rD + (uint32_t)(h * (U_ / 2)), rA, 0u, a_dhi, lboH + ring16, bH_hi, ones_lo, bias_lo,
                                            wfull0, wpeer0, wempty0, S, slot, phase, leader, tw);
               if (leader) tc_commit2_addr(smem_u32(&ct.h_ready[h]));
             }
             if (l == 0 && net == 1 && leader) tc_commit2_addr(smem_u32(&ct.a1_free[buf]));
           } else {
             const uint32_t bias_lo = lboF + bias16 + (uint32_t)(sh.bias_off(net, L, 0) >> 4);
-            mma_job6<U_, DH, true>(rD, rA, 0u, a_dhi, lboF + ring16, bF_hi, ones_lo, bias_lo, wfull0, wpeer0, wempty0, S, slot,
+            mma_job6<U_, DH, true, kSplit>(rD, rA, 0u, a_dhi, lboF + ring16, bF_hi, ones_lo, bias_lo, wfull0, wpeer0, wempty0, S, slot,
                                    phase, leader, tw);
             if (leader) tc_commit2_addr(smem_u32(&ct.f_ready));
             fin_pending = true;
@@ -407,15 +429,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
     uint32_t h_par = 0, f_par = 0;                    // h_par: bit h
     // tanh phase of one accumulator chunk, in place: 32 fp32 columns -> 16 columns of hi pairs + 16 of lo pairs
     auto tanh_chunk = [&](uint32_t col) {
-      uint32_t x[32], o[32];
+      uint32_t x[32];
       tmem_ld32(col, x);
       tc_wait_ld();
+      if (kSplit) {
+        uint32_t o[32];
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float y0 = tanh_f32(__uint_as_float(x[j])), y1 = tanh_f32(__uint_as_float(x[j + 1]));
-        split_f16(y0, y1, o[j >> 1], o[16 + (j >> 1)]);
+        for (int j = 0; j < 32; j += 2) {
+          const float y0 = tanh_f32(__uint_as_float(x[j])), y1 = tanh_f32(__uint_as_float(x[j + 1]));
+          split_f16(y0, y1, o[j >> 1], o[16 + (j >> 1)]);
+        }
+        tmem_st32(col, o);
+      } else {   // bf16 pairs into the first 16 of the chunk's 32 columns
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2)
+          o[j >> 1] = pack_bf16(tanh_fast(__uint_as_float(x[j])), tanh_fast(__uint_as_float(x[j + 1])));
+        tmem_st16(col, o);
       }
-      tmem_st32(col, o);
     };
     for (int64_t k = 0; k < cnt; ++k) {
       const int64_t tile = 2 * (k * P + pair) + rank;
@@ -457,29 +488,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
         mbar_wait(&ct.f_ready, f_par);
         f_par ^= 1u;
         tc_fence_after();
-        uint32_t o[W];
+        constexpr int PW = W < 16 ? W : 16;          // the final accumulator is read in pieces of <= 16 columns
         const uint32_t fcol = tmem + lane_addr + (uint32_t)((L & 1) * 256) + (uint32_t)(cq * W);
-        if (W == 8) tmem_ld8(fcol, reinterpret_cast<uint32_t(&)[8]>(o));
-        else tmem_ld16(fcol, reinterpret_cast<uint32_t(&)[16]>(o));
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(lead_e_fin);   // accumulator read: the next layer-0 job may overwrite it
-        if (net == 0) {
+        float ld_sum = 0.f;
+        float (&y)[W] = zin;
 #pragma unroll
-          for (int j = 0; j < W; ++j) tv[j] = __uint_as_float(o[j]);
-        } else {
-          float ld_sum = 0.f;
-          float (&y)[W] = zin;
-#pragma unroll
-          for (int j = 0; j < W; ++j) {
-            const int col = sh.t_off + cq * W + j;
-            const float zz = fmaf(zin[j], s_pscale[col], s_pshift[col]);
-            const float sv = __uint_as_float(o[j]);
-            ld_sum += sv;
-            // exp to fp32 accuracy (ex2.approx: 2 ulp); the inverse multiplies by exp(-s) = 1 / exp(s)
-            y[j] = kInverse ? (zz - tv[j]) * exp2_fast(-sv * kLog2e) : fmaf(zz, exp2_fast(sv * kLog2e), tv[j]);
+        for (int p0 = 0; p0 < W; p0 += PW) {
+          uint32_t o[PW];
+          if (PW == 8) tmem_ld8(fcol + (uint32_t)p0, reinterpret_cast<uint32_t(&)[8]>(o));
+          else tmem_ld16(fcol + (uint32_t)p0, reinterpret_cast<uint32_t(&)[16]>(o));
+          tc_wait_ld();
+          if (p0 + PW == W) {     // accumulator read: the next layer-0 job may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(lead_e_fin);
           }
+          if (net == 0) {
+#pragma unroll
+            for (int j = 0; j < PW; ++j) tv[p0 + j] = __uint_as_float(o[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < PW; ++j) {
+              const int col = sh.t_off + cq * W + p0 + j;
+              const float zz = fmaf(zin[p0 + j], s_pscale[col], s_pshift[col]);
+              const float sv = __uint_as_float(o[j]);
+              ld_sum += sv;
+              // exp to fp32 accuracy (ex2.approx: 2 ulp); the inverse multiplies by exp(-s) = 1 / exp(s)
+              y[p0 + j] = kInverse ? (zz - tv[p0 + j]) * exp2_fast(-sv * kLog2e) : fmaf(zz, exp2_fast(sv * kLog2e), tv[p0 + j]);
+            }
+          }
+        }
+        if (net == 1) {
           if (valid) {
             float* orow = a.z_out + row * sh.D + sh.t_off + cq * W;
 #pragma unroll
@@ -506,6 +545,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
     constexpr int LPR = DH / 4;
     constexpr int RPI = 32 / LPR;
     constexpr int NI = (kTileM / 2) / RPI;
+    constexpr int kIoBatch = 8;                    // float4 loads in flight per lane (16 spills at 96 registers: measured 1.8x slower)
     const int hc = 4 * (lane % LPR);
     const int col = sh.c_off + hc;
     const int rsub = lane / LPR;
@@ -515,30 +555,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
       const uint32_t buf = (uint32_t)(k & 1);
       if (k >= 2) mbar_wait(&ct.a1_free[buf], (uint32_t)(((k >> 1) - 1) & 1));   // tile k-2's layer-0 jobs are done with it
       const int64_t tile = 2 * (k * P + pair) + rank;
-      unsigned char* a1h = sA1 + (size_t)(2 * buf) * sh.a1_bytes();
+      unsigned char* a1h = sA1 + (size_t)(kImgs * buf) * sh.a1_bytes();
       unsigned char* a1l = a1h + sh.a1_bytes();
 #pragma unroll 1
-      for (int n0 = 0; n0 < NI; n0 += 8) {
-        float4 v[8];
+      for (int n0 = 0; n0 < NI; n0 += kIoBatch) {
+        float4 v[kIoBatch];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kIoBatch; ++u) {
           const int r = row0 + (n0 + u) * RPI + rsub;
           const int64_t grow = tile * kTileM + r;
           v[u] = grow < a.rows ? __ldg(reinterpret_cast<const float4*>(a.z_in + grow * sh.D + col))
                                : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kIoBatch; ++u) {
           const int r = row0 + (n0 + u) * RPI + rsub;
           const int64_t grow = tile * kTileM + r;
           float4 x;
           x.x = fmaf(v[u].x, ps.x, pb.x); x.y = fmaf(v[u].y, ps.y, pb.y);
           x.z = fmaf(v[u].z, ps.z, pb.z); x.w = fmaf(v[u].w, ps.w, pb.w);
-          uint32_t h0, l0, h1, l1;
-          split_f16(x.x, x.y, h0, l0);
-          split_f16(x.z, x.w, h1, l1);
-          *reinterpret_cast<uint2*>(a1h + img_off(r, hc, kTileM)) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(a1l + img_off(r, hc, kTileM)) = make_uint2(l0, l1);
+          if (kSplit) {
+            uint32_t h0, l0, h1, l1;
+            split_f16(x.x, x.y, h0, l0);
+            split_f16(x.z, x.w, h1, l1);
+            *reinterpret_cast<uint2*>(a1h + img_off(r, hc, kTileM)) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(a1l + img_off(r, hc, kTileM)) = make_uint2(l0, l1);
+          } else {
+            *reinterpret_cast<uint2*>(a1h + img_off(r, hc, kTileM)) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+          }
           if (grow < a.rows) *reinterpret_cast<float4*>(a.z_out + grow * sh.D + col) = x;
         }
       }
@@ -554,22 +598,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
   if (warp == kEpiWarps2) tmem_dealloc2(tmem, 512);
 }
 
-int launch_tc6(const Args& a, int grid, int n_stages, size_t smem, cudaStream_t st) {
+int launch_tc6(const Args& a, int grid, int split, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaSuccess;
-  (void)n_stages;
-#define TNF_TC6_LAUNCH(INV, DHV, UV)                                                                              \
+#define TNF_TC6_LAUNCH(INV, DHV, UV, SP)                                                                          \
   do {                                                                                                            \
-    e = cudaFuncSetAttribute(coupling_tc6_kernel<INV, DHV, UV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+    e = cudaFuncSetAttribute(coupling_tc6_kernel<INV, DHV, UV, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                              (int)smem);                                                                          \
-    if (e == cudaSuccess) coupling_tc6_kernel<INV, DHV, UV><<<grid, kThreads6, smem, st>>>(a);                    \
+    if (e == cudaSuccess) coupling_tc6_kernel<INV, DHV, UV, SP><<<grid, kThreads6, smem, st>>>(a);                \
   } while (0)
-#define TNF_TC6_U(INV, DHV)                                  \
-  do {                                                       \
-    if (a.U == 256) TNF_TC6_LAUNCH(INV, DHV, 256);           \
-    else TNF_TC6_LAUNCH(INV, DHV, 128);                      \
+#define TNF_TC6_U(INV, DHV, SP)                                  \
+  do {                                                           \
+    if (a.U == 256) TNF_TC6_LAUNCH(INV, DHV, 256, SP);           \
+    else TNF_TC6_LAUNCH(INV, DHV, 128, SP);                      \
   } while (0)
-  if (a.D == 64) { if (a.inverse) TNF_TC6_U(true, 32); else TNF_TC6_U(false, 32); }
-  else { if (a.inverse) TNF_TC6_U(true, 64); else TNF_TC6_U(false, 64); }
+  if (split) {
+    if (a.D == 64) { if (a.inverse) TNF_TC6_U(true, 32, true); else TNF_TC6_U(false, 32, true); }
+    else if (a.D == 128) { if (a.inverse) TNF_TC6_U(true, 64, true); else TNF_TC6_U(false, 64, true); }
+    else { if (a.inverse) TNF_TC6_U(true, 128, true); else TNF_TC6_U(false, 128, true); }
+  } else {   // bf16: only the D = 256 layer runs here (D <= 128 has the two-tile kernels)
+    if (a.inverse) TNF_TC6_U(true, 128, false); else TNF_TC6_U(false, 128, false);
+  }
 #undef TNF_TC6_U
 #undef TNF_TC6_LAUNCH
   return (int)e;

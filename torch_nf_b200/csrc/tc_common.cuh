@@ -447,10 +447,10 @@ int launch_tc5(const Args& a, int grid, size_t smem, cudaStream_t st);
 size_t smem_bytes5(const Shape& sh, int n_stages);
 // coupling_tc6.cu: fp32-parity mode (fp16 hi / lo operand split, three MMAs per product, activations in TMEM)
 bool shape_supported6(int D, int U, int L);
-size_t packed_bytes6(int D, int U, int L);
-int pack6_launch(const float* params, void* packed, int D, int U, int L, int upper, cudaStream_t st);
-size_t smem_bytes6(int D, int U, int L, int n_stages);
-int launch_tc6(const Args& a, int grid, int n_stages, size_t smem, cudaStream_t st);
+size_t packed_bytes6(int D, int U, int L, int split);
+int pack6_launch(const float* params, void* packed, int D, int U, int L, int upper, int split, cudaStream_t st);
+size_t smem_bytes6(int D, int U, int L, int split, int n_stages);
+int launch_tc6(const Args& a, int grid, int split, size_t smem, cudaStream_t st);
 __host__ __device__ inline bool shape_supported5(int D, int U, int L) {
   return shape_supported2(D, U, L) && U >= 128 && L == 2;
 }
