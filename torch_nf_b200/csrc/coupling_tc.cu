@@ -1659,7 +1659,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   TNF_REQUIRE(smem <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem);
   tc::Args a{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
              D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_groups,
-             (variant >> 8) | ((variant & 15) == 3 ? 0x100 : 0),
+             (variant >> 8) | ((variant & 15) == 3 ? 0x100 : 0),   // tune: bits 0-3 of variant >> 8 = diagnostic knob
              col_stats ? (double*)stats_workspace : nullptr, g_tc_debug};
 #define TNF_TC_LAUNCH(KERNEL, THREADS, INV, DHV)                                                              \
   do {                                                                                                        \
