@@ -54,10 +54,12 @@ def test_small_chain_is_one_launch(D, stages, L, U, N):
     assert ((lp_c.cpu() - lpo).abs() / lpo.abs().clamp(min=1)).max().item() <= 1e-4
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_chain_calls_match_plan_c3(precision):
-    """Tensor-core chains: the C-side executor launches the same kernels as the host-side plan (bit-identical)."""
-    D, stages, L, U, N = 64, 2, 2, 256, 1000
+@pytest.mark.parametrize("precision,D", [("fp32", 64), ("bf16", 64), ("bf16", 128), ("bf16", 256), ("fp32", 256)])
+def test_chain_calls_match_plan_c3(precision, D):
+    """Tensor-core chains: in the sample direction the C-side executor's fused fold launches reproduce the host-side
+    plan bit for bit; log_prob folds every BatchNorm / Affine with ONE launch and takes the base density inside the last
+    executed coupling layer (no z0 store, no base-density pass), so it agrees with the plan to fp32 rounding."""
+    stages, L, U, N = 2, 2, 256, 1000
     nf = de.NormFlow(D, True, "coupling", stages, L, U)
     params = T(synthetic_params(chain_spec(nf.bijectors), D, 1, seed=4)).cuda()
     omega = np.random.RandomState(5).standard_normal((1, N, D))
@@ -66,9 +68,36 @@ def test_chain_calls_match_plan_c3(precision):
         with torch.no_grad():
             ((z_c, lq_c), (z_p, lq_p), n_chain, n_plan) = _both(lambda: nf.forward(params, N, omega=omega))
             assert torch.equal(z_c, z_p) and torch.equal(lq_c, lq_p)
-            (lp_c, lp_p, _, _) = _both(lambda: nf.log_prob(z_c, params))
-            assert torch.equal(lp_c, lp_p)
+            assert n_chain < n_plan
+            (lp_c, lp_p, n_chain, n_plan) = _both(lambda: nf.log_prob(z_c, params))
+            err = ((lp_c - lp_p).abs() / lp_p.abs().clamp(min=1)).max().item()
+            print("fused base density vs plan: rel %.3g, launches %d vs %d" % (err, n_chain, n_plan))
+            assert err <= 2e-6
+            # one fold launch + one launch per coupling layer (+ the base density where the layer's kernel cannot fuse it)
+            assert n_chain == 2 * stages + 1 + (1 if (precision, D) == ("bf16", 128) else 0), n_chain
     finally:
+        tnf.set_conditioner_precision("fp32")
+
+
+@pytest.mark.parametrize("precision,D,U", [("bf16", 64, 256), ("fp32", 64, 256), ("bf16", 256, 256), ("bf16", 128, 128), ("fp32", 128, 128)])
+def test_chain_logprob_ragged_rows(precision, D, U):
+    """Fused base density at row counts that leave partial tiles, single tiles, idle CTAs, and several tiles per CTA
+    (the per-tile hand-off buffers between the I/O and epilogue warps wrap around)."""
+    tnf.set_conditioner_precision(precision)
+    config.set_tc_min_rows(1)
+    try:
+        nf = de.NormFlow(D, True, "coupling", 1, 2, U)
+        params = T(synthetic_params(chain_spec(nf.bijectors), D, 1, seed=8)).cuda()
+        for N in (1, 127, 129, 300, 148 * 128 + 5, 148 * 128 * 5 + 77):
+            omega = np.random.RandomState(9).standard_normal((1, N, D))
+            with torch.no_grad():
+                z, _ = nf.forward(params, N, omega=omega)
+                (lp_c, lp_p, _, _) = _both(lambda: nf.log_prob(z, params))
+            assert lp_c.shape == lp_p.shape == (1, N)
+            err = ((lp_c - lp_p).abs() / lp_p.abs().clamp(min=1)).max().item()
+            assert err <= 2e-6, (N, err)
+    finally:
+        config.set_tc_min_rows(128)
         tnf.set_conditioner_precision("fp32")
 
 

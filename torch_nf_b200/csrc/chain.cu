@@ -205,7 +205,8 @@ size_t tnf_chain_workspace_bytes(int64_t M, int64_t N, int D) {
   const size_t rows = (size_t)(M * N);
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   return 2 * al(rows * (size_t)(D + 1) * 4) + al(rows * 4) + al((size_t)M * 4) + 4 * al((size_t)D * 4) +
-         al((size_t)(2 * D + 1) * 8) + al(tnf_colstats_workspace_bytes(D)) + 3 * al((size_t)D * 4) + 1024;
+         al((size_t)(2 * D + 1) * 8) + al(tnf_colstats_workspace_bytes(D)) + 3 * al((size_t)D * 4) +
+         2 * (size_t)kMaxFoldSteps * al((size_t)D * 4) + 1024;
 }
 
 int tnf_chain_logprob(const tnf_bijector_t* chain, int n_bij, const float* z, const float* params,
@@ -240,6 +241,65 @@ int tnf_chain_logprob(const tnf_bijector_t* chain, int n_bij, const float* z, co
   int nb = 0, np = 0;
   bool have_pend = false;
   auto out_buf = [&]() { float* o = zb[nb]; nb ^= 1; return o; };
+  bool pure = fold && n_bij + 1 <= kMaxFoldSteps;
+  for (int i = 0; i < n_bij && pure; ++i) pure = chain[i].kind != TNF_BIJ_TOINTERVAL;
+  if (pure) {
+    // Tensor-core chain of RealNVP / BatchNorm / Affine: ONE launch composes every BatchNorm / Affine into the per-column
+    // pre-affine of the coupling layer executed after it (the arithmetic, in the order, of the tnf_fold_colaffine /
+    // tnf_accum_bcast launches it replaces), and the last executed layer emits log N(z0) - log-dets itself (no z0
+    // store, no base-density pass).
+    FoldPlan plan;
+    plan.n = 0; plan.D = D;
+    const float* pre[kMaxFoldSteps][2];     // per bijector index: the emitted pre-affine of that coupling layer (or NULL)
+    bool pending = false;
+    int first_cp = -1;
+    for (int i = n_bij - 1; i >= 0; --i) {
+      const tnf_bijector_t& b = chain[i];
+      if (b.kind == TNF_BIJ_BATCHNORM) {
+        TNF_REQUIRE(b.bn_mean && b.bn_alpha && b.bn_log_det, TNF_ERR_ARG, "tnf_chain_logprob: BatchNorm state missing");
+        plan.s[plan.n++] = FoldStep{0, b.bn_mean, b.bn_alpha, b.bn_log_det, nullptr, nullptr};
+        pending = true;
+      } else if (b.kind == TNF_BIJ_AFFINE) {
+        plan.s[plan.n++] = FoldStep{1, params + b.param_offset, params + b.param_offset + D, nullptr, nullptr, nullptr};
+        pending = true;
+      } else {   // RealNVP
+        first_cp = i;
+        pre[i][0] = pre[i][1] = nullptr;
+        if (pending) {
+          float* ps = (float*)ws.take((size_t)D * 4);
+          float* pb = (float*)ws.take((size_t)D * 4);
+          plan.s[plan.n++] = FoldStep{2, nullptr, nullptr, nullptr, ps, pb};
+          pending = false;
+          pre[i][0] = ps; pre[i][1] = pb;
+        }
+      }
+    }
+    float* tail[2] = {nullptr, nullptr};
+    if (pending) {   // BatchNorm / Affine BEFORE the first coupling layer in chain order: applied after the last executed one
+      tail[0] = (float*)ws.take((size_t)D * 4); tail[1] = (float*)ws.take((size_t)D * 4);
+      plan.s[plan.n++] = FoldStep{2, nullptr, nullptr, nullptr, tail[0], tail[1]};
+    }
+    if (plan.n > 0) TNF_TRY(chain_fold_inv_launch(plan, scal, st));
+    for (int i = n_bij - 1; i >= 0; --i) {
+      const tnf_bijector_t& b = chain[i];
+      if (b.kind != TNF_BIJ_REALNVP) continue;
+      const bool fuse_lp = i == first_cp && tail[0] == nullptr && tc_lp_fusable(D, b.num_units, b.num_layers, tc_precision);
+      float* o = fuse_lp ? nullptr : out_buf();
+      if (b.ev_start) cudaEventRecord((cudaEvent_t)b.ev_start, st);
+      TNF_TRY(coupling_tc_impl(cur, o, ld_acc, b.packed, rows, D, b.num_units, b.num_layers, b.transform_upper, TNF_INVERSE,
+                               TNF_LD_ADD, pre[i][0], pre[i][1], nullptr, nullptr, tc_precision, 0, nullptr,
+                               fuse_lp ? log_prob : nullptr, fuse_lp ? scal : nullptr, stream));
+      if (b.ev_stop) cudaEventRecord((cudaEvent_t)b.ev_stop, st);
+      if (fuse_lp) return 0;
+      cur = o;
+    }
+    if (tail[0]) {
+      float* o = out_buf();
+      TNF_TRY(tnf_colaffine(cur, o, tail[0], tail[1], rows, D, stream));
+      cur = o;
+    }
+    return tnf_base_logprob(cur, ld_acc, scal, rows, log_prob, rows, D, TNF_F32, stream);
+  }
   auto flush_pend = [&]() -> int {
     if (!have_pend) return 0;
     float* o = out_buf();
@@ -380,6 +440,26 @@ int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params
       cur = o;
     } else if (b.kind == TNF_BIJ_BATCHNORM) {
       TNF_REQUIRE(b.bn_mean && b.bn_alpha && b.bn_log_det, TNF_ERR_ARG, "tnf_chain_sample: BatchNorm state missing");
+      if (fold) {
+        // one launch: statistics -> mean / alpha / log-det, (z - mean) / alpha folded into the pending map, the Affine
+        // that follows folded too, both log-dets added - the arithmetic of the four launches of the generic branch
+        if (!freeze_bn) {
+          if (have_pend) { TNF_TRY(flush_pend(nullptr)); have_stats = false; }   // statistics are taken on the materialised tensor
+          if (!have_stats) TNF_TRY(tnf_colstats(cur, rows, D, sums, stat_ws, TNF_F32, stream));
+          if (allreduce) {
+            int rc = allreduce(sums, 2 * D + 1, allreduce_user);
+            TNF_REQUIRE(rc == 0, TNF_ERR_ARG, "tnf_chain_sample: the statistics all-reduce callback failed (%d)", rc);
+          }
+        }
+        have_stats = false;
+        const bool aff_next = !last && chain[i + 1].kind == TNF_BIJ_AFFINE;
+        TNF_TRY(bn_fold_fwd_launch(sums, D, b.bn_eps, b.bn_mean, b.bn_alpha, b.bn_log_det, have_pend ? pend[np ^ 1][0] : nullptr,
+                                   have_pend ? pend[np ^ 1][1] : nullptr, aff_next ? params + chain[i + 1].param_offset : nullptr,
+                                   pend[np][0], pend[np][1], scal, freeze_bn ? 0 : 1, st));
+        np ^= 1; have_pend = true;
+        if (aff_next) ++i;
+        continue;
+      }
       if (!freeze_bn) {
         if (have_pend) { TNF_TRY(flush_pend(nullptr)); have_stats = false; }   // statistics are taken on the materialised tensor
         if (!have_stats) TNF_TRY(tnf_colstats(cur, rows, D, sums, stat_ws, TNF_F32, stream));

@@ -14,6 +14,27 @@ int num_sms();
 // sums[2D+1] = column-wise sum of partial[nblocks][2][D] (fixed order) and the row count
 int colstats_reduce_launch(const double* partial, int nblocks, int D, double* sums, double rows, cudaStream_t st);
 
+// fused fold kernels of the chain executor (elementwise.cu)
+struct FoldStep {
+  int kind;                 // 0 BatchNorm (a = mean, b = alpha, ld = log-det), 1 Affine (a = alpha(D), b = shift(D)), 2 emit
+  const float* a; const float* b; const float* ld;
+  float* ps_out; float* pb_out;
+};
+constexpr int kMaxFoldSteps = 96;
+struct FoldPlan { int n, D; FoldStep s[kMaxFoldSteps]; };
+int chain_fold_inv_launch(const FoldPlan& plan, float* scal, cudaStream_t st);
+int bn_fold_fwd_launch(const double* sums, int D, double eps, float* mean, float* alpha, float* log_det, const float* ps_in,
+                       const float* pb_in, const float* aff, float* ps_out, float* pb_out, float* scal, int finalize,
+                       cudaStream_t st);
+
+// tnf_coupling_tc with the fused base density of the chain executor: out_lp != NULL (inverse direction, TNF_LD_ADD) makes
+// the layer emit log N(z_out) - log_det[row] - sum s - lp_scal[0] instead of z_out / log_det (coupling_tc.cu)
+bool tc_lp_fusable(int D, int U, int L, int precision);
+int coupling_tc_impl(const float* z_in, float* z_out, float* log_det, const void* packed, int64_t rows, int D, int U, int L,
+                     int transform_upper, int direction, int accum, const float* pre_scale, const float* pre_shift,
+                     double* col_stats, void* stats_workspace, int precision, int variant, void* debug, float* out_lp,
+                     const float* lp_scal, tnf_stream_t stream);
+
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

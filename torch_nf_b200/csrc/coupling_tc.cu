@@ -1579,6 +1579,30 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
                     int L, int transform_upper, int direction, int accum, const float* pre_scale,
                     const float* pre_shift, double* col_stats, void* stats_workspace, int precision, int variant,
                     void* debug, tnf_stream_t stream) {
+  return tnf::coupling_tc_impl(z_in, z_out, log_det, packed, rows, D, U, L, transform_upper, direction, accum, pre_scale, pre_shift,
+                               col_stats, stats_workspace, precision, variant, debug, nullptr, nullptr, stream);
+}
+
+}  // extern "C"
+
+namespace tnf {
+
+static bool pairs5_default(int D, int U, int L) {
+  return tc::shape_supported2(D, U, L) && tc::shape_supported5(D, U, L) && tc::smem_bytes5(tc::Shape(D, U, L, 1), 4) <= 227 * 1024;
+}
+
+bool tc_lp_fusable(int D, int U, int L, int precision) {
+  if (!tnf_tc_supported(D, U, L, precision)) return false;
+  return precision == TNF_TC_FP32 || bf16_on_tc6(D, U, L) || pairs5_default(D, U, L);
+}
+
+int coupling_tc_impl(const float* z_in, float* z_out, float* log_det, const void* packed, int64_t rows, int D, int U,
+                     int L, int transform_upper, int direction, int accum, const float* pre_scale,
+                     const float* pre_shift, double* col_stats, void* stats_workspace, int precision, int variant,
+                     void* debug, float* out_lp, const float* lp_scal, tnf_stream_t stream) {
+  TNF_REQUIRE(out_lp == nullptr || (direction == TNF_INVERSE && accum == TNF_LD_ADD && (variant & 15) == 0 &&
+                                    tc_lp_fusable(D, U, L, precision)),
+              TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: the fused base density needs the inverse direction, TNF_LD_ADD and the default kernel");
   TNF_REQUIRE(tnf_tc_supported(D, U, L, precision), TNF_ERR_UNSUPPORTED,
               "tnf_coupling_tc: shape D=%d U=%d L=%d not supported at precision %d", D, U, L, precision);
   if (precision == TNF_TC_FP32 || bf16_on_tc6(D, U, L)) {   // TMEM-resident single-tile kernel
@@ -1586,7 +1610,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
     TNF_REQUIRE((variant & 15) == 0, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: this shape / precision has one kernel (variant 0)");
     TNF_REQUIRE(rows >= 0, TNF_ERR_ARG, "tnf_coupling_tc: rows < 0");
     if (rows == 0) return 0;
-    TNF_REQUIRE(z_in && z_out && log_det && packed, TNF_ERR_ARG, "tnf_coupling_tc: null pointer");
+    TNF_REQUIRE(z_in && (z_out || out_lp) && log_det && packed, TNF_ERR_ARG, "tnf_coupling_tc: null pointer");
     TNF_REQUIRE((((uintptr_t)z_in | (uintptr_t)z_out | (uintptr_t)packed) & 15) == 0, TNF_ERR_ALIGN,
                 "tnf_coupling_tc: z and packed weights must be 16-byte aligned");
     TNF_REQUIRE(col_stats == nullptr, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: no fused column statistics in this kernel");
@@ -1599,7 +1623,8 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
     TNF_REQUIRE(ns >= 4, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: only %d weight stages fit (a job needs up to 4)", ns);
     TNF_REQUIRE(smem6 <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem6);
     tc::Args a6{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
-                D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, ns, 2, variant >> 8, nullptr, (long long*)debug};
+                D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, ns, 2, variant >> 8, nullptr, (long long*)debug,
+                out_lp, lp_scal};
     cudaError_t e6 = (cudaError_t)tc::launch_tc6(a6, grid6, split6, smem6, (cudaStream_t)stream);
     if (e6 != cudaSuccess) {
       set_error("tnf_coupling_tc: cudaFuncSetAttribute(%zu B smem): %s", smem6, cudaGetErrorString(e6));
@@ -1611,7 +1636,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   long long* const g_tc_debug = (long long*)debug;
   TNF_REQUIRE(rows >= 0, TNF_ERR_ARG, "tnf_coupling_tc: rows < 0");
   if (rows == 0) return 0;
-  TNF_REQUIRE(z_in && z_out && log_det && packed, TNF_ERR_ARG, "tnf_coupling_tc: null pointer");
+  TNF_REQUIRE(z_in && (z_out || out_lp) && log_det && packed, TNF_ERR_ARG, "tnf_coupling_tc: null pointer");
   TNF_REQUIRE((((uintptr_t)z_in | (uintptr_t)z_out | (uintptr_t)packed) & 15) == 0, TNF_ERR_ALIGN,
               "tnf_coupling_tc: z and packed weights must be 16-byte aligned");
   TNF_REQUIRE(col_stats == nullptr || (D <= 128 && stats_workspace != nullptr), TNF_ERR_UNSUPPORTED,
@@ -1660,7 +1685,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   tc::Args a{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
              D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, n_stages, g_tc_groups,
              (variant >> 8) | ((variant & 15) == 3 ? 0x100 : 0),   // tune: bits 0-3 of variant >> 8 = diagnostic knob
-             col_stats ? (double*)stats_workspace : nullptr, g_tc_debug};
+             col_stats ? (double*)stats_workspace : nullptr, g_tc_debug, out_lp, lp_scal};
 #define TNF_TC_LAUNCH(KERNEL, THREADS, INV, DHV)                                                              \
   do {                                                                                                        \
     e = cudaFuncSetAttribute(tc::KERNEL<INV, DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
@@ -1702,6 +1727,10 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
   if (rc || col_stats == nullptr) return rc;
   return colstats_reduce_launch((const double*)stats_workspace, stat_blocks, D, col_stats, (double)rows, st);
 }
+
+}  // namespace tnf
+
+extern "C" {
 
 int tnf_tc_selftest_gemm(const float* A, const float* W, float* out, int K, int N, int a_in_tmem,
                          tnf_stream_t stream) {

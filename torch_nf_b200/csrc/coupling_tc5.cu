@@ -97,11 +97,11 @@ struct __align__(16) Ctrl5 {
 };
 // dynamic shared memory:
 //   [ring: 4 x 16 KB][A1 g0][A1 g1][Act g0][Act g1][ones 4 KB][Ctrl5][pre_scale D][pre_shift D][ld partial 2 x 128]
-//   [resident bias blocks of this rank][2 KB zeros]
+//   [sum z^2 of the conditioning half: group x tile parity x 128 (fused base density)][resident bias blocks of this rank][2 KB zeros]
 constexpr int kBiasPad5 = 2048;   // zero block after the resident bias region (second K group of the last bias MMA)
 size_t smem_bytes5(const Shape& sh, int n_stages) {
   return (size_t)n_stages * sh.stage_elems() * 2 + 2 * sh.a1_bytes() + 2 * sh.act_bytes() + kOnesBytes + sizeof(Ctrl5) +
-         (size_t)(2 * sh.D + 2 * kTileM) * sizeof(float) + (size_t)sh.bias8_rank_bytes() + kBiasPad5;
+         (size_t)(2 * sh.D + 2 * kTileM + 4 * kTileM) * sizeof(float) + (size_t)sh.bias8_rank_bytes() + kBiasPad5;
 }
 
 // FT: of every 8 activations, FT are evaluated by tanh_poly on the FMA pipe, the rest by MUFU.TANH
@@ -120,7 +120,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
   float* s_pscale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl5));
   float* s_pshift = s_pscale + sh.D;
   float* s_ldp = s_pshift + sh.D;
-  unsigned char* sBias = reinterpret_cast<unsigned char*>(s_ldp + 2 * kTileM);   // resident bias blocks (+ zero pad)
+  float* s_ss = s_ldp + 2 * kTileM;                                               // [group][tile parity][128]
+  unsigned char* sBias = reinterpret_cast<unsigned char*>(s_ss + 4 * kTileM);    // resident bias blocks (+ zero pad)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
@@ -173,6 +174,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
   const uint32_t lead_e_done = mapa_u32(smem_u32(&ct.e_done[0]), 0u), lead_a1_ready = mapa_u32(smem_u32(&ct.a1_ready[0]), 0u);
   const uint32_t lead_w_peer = mapa_u32(smem_u32(&ct.w_peer[0]), 0u);
   const bool want_stats = a.stat_partials != nullptr;
+  const bool lp_mode = kInverse && a.out_lp != nullptr;   // fused base density: this is the chain's last executed layer
   float io_sv1[4] = {0.f, 0.f, 0.f, 0.f}, io_sv2[4] = {0.f, 0.f, 0.f, 0.f};   // I/O warps: sums of columns col..col+3
   // per-warp statistics rows ([2*D] doubles, own columns only) are gathered in the (then dead) activation images
   double* stat_rows = reinterpret_cast<double*>(sAct);
@@ -322,6 +324,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
     unsigned char* myAct = sAct + (size_t)g * sh.act_bytes();
     uint32_t h_par = 0, hb_par = 0;
     float st_y = 0.f, st_y2 = 0.f;            // per-lane column sums of the transformed half (column par*W + lane%W)
+    const float lp_cst = (float)((double)sh.D * 0.91893853320467274178);   // D log sqrt(2 pi)
+    const float lp_scal0 = (lp_mode && a.lp_scal) ? a.lp_scal[0] : 0.f;
 
     int dbg_n = 0;
     const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && q == 0 && par == 0 && lane == 0;
@@ -456,6 +460,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
             y[j] = kInverse ? (zz - tv[j]) * exp2_fast(-sv * kLog2e) : fmaf(zz, exp2_fast(sv * kLog2e), tv[j]);
           }
           TNF_STAMP(601);
+          if (lp_mode) {   // log N(z_out) - log-dets instead of z_out: nothing reads the base sample itself
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < W; ++j) ss = fmaf(y[j], y[j], ss);
+            if (par == 1) s_ldp[g * kTileM + r_tile] = fmaf(0.5f, ss, ld_sum);
+            pair_sync();
+            if (par == 0 && valid) {
+              const float ss_all = ss + s_ss[(g * 2 + (int)(k & 1)) * kTileM + r_tile];
+              a.out_lp[row] = ((-0.5f * ss_all - lp_cst) - ((ld_old + ld_sum) + s_ldp[g * kTileM + r_tile])) - lp_scal0;
+            }
+          } else {
           if (valid) {
             float* orow = a.z_out + row * sh.D + sh.t_off + par * W;
 #pragma unroll
@@ -470,6 +485,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
             if (a.accum == TNF_LD_WRITE) *op = tot;
             else if (a.accum == TNF_LD_ADD) *op = ld_old + tot;
             else *op = ld_old - tot;
+          }
           }
           if (want_stats) {
             float s1[W], s2[W];
@@ -532,7 +548,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
           x.x = fmaf(v[u].x, ps.x, pb.x); x.y = fmaf(v[u].y, ps.y, pb.y);
           x.z = fmaf(v[u].z, ps.z, pb.z); x.w = fmaf(v[u].w, ps.w, pb.w);
           *reinterpret_cast<uint2*>(a1 + img_off(r, hc, kTileM)) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
-          if (grow < a.rows) {
+          if (lp_mode) {   // sum of squares of this row's conditioning half (it passes through unchanged), for the epilogue
+            float ssq = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w)));
+#pragma unroll
+            for (int o = 1; o < LPR; o <<= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+            if (lane % LPR == 0) s_ss[(g * 2 + (int)(k & 1)) * kTileM + r] = ssq;
+          } else if (grow < a.rows) {
             *reinterpret_cast<float4*>(a.z_out + grow * sh.D + col) = x;
             if (want_stats) {
               io_sv1[0] += x.x; io_sv1[1] += x.y; io_sv1[2] += x.z; io_sv1[3] += x.w;
@@ -543,6 +564,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
         }
       }
       fence_async_smem();
+      if (lp_mode) __threadfence_block();   // s_ss before the (relaxed) arrival the epilogue's h_ready chain descends from
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(lead_a1_ready + (uint32_t)g * 8u);
     };

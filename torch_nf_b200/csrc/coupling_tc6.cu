@@ -188,7 +188,7 @@ struct __align__(16) Ctrl6 {
 size_t smem_bytes6(int D, int U, int L, int split, int n_stages) {
   Shape6 sh(D, U, L, 1, split);
   return (size_t)n_stages * kStageBytes + (split ? 4 : 2) * sh.a1_bytes() + kOnesBytes + sizeof(Ctrl6) +
-         (size_t)(2 * sh.D + 4 * kTileM) * sizeof(float) + (size_t)sh.bias_rank_bytes() + kBiasPad6;
+         (size_t)(2 * sh.D + 4 * kTileM + 4 * kTileM) * sizeof(float) + (size_t)sh.bias_rank_bytes() + kBiasPad6;
 }
 
 // dense, D = f32, A = B = f16 (split) or bf16, K-major, M = 256 (pair)
@@ -270,7 +270,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
   float* s_pscale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(Ctrl6));
   float* s_pshift = s_pscale + sh.D;
   float* s_ldp = s_pshift + sh.D;                                  // [3][128] log-det partials of chunk owners 1..3
-  unsigned char* sBias = reinterpret_cast<unsigned char*>(s_ldp + 4 * kTileM);
+  // [tile & 3][128] sum z^2 of the conditioning half (fused base density).  Three tiles are live at once: the I/O warps
+  // load tile k+2 as soon as tile k's layer-0 jobs are done, before tile k's epilogue has consumed its entry
+  float* s_ss = s_ldp + 4 * kTileM;
+  unsigned char* sBias = reinterpret_cast<unsigned char*>(s_ss + 4 * kTileM);
+  const bool lp_mode = kInverse && a.out_lp != nullptr;           // this is the chain's last executed layer: emit log_prob, not z
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
@@ -427,6 +431,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
     constexpr int W = DH / 4;                         // final-layer columns per thread
     const float kLog2e = 1.4426950408889634f;
     uint32_t h_par = 0, f_par = 0;                    // h_par: bit h
+    const float lp_cst = (float)((double)sh.D * 0.91893853320467274178);   // D log sqrt(2 pi)
+    const float lp_scal0 = (lp_mode && a.lp_scal) ? a.lp_scal[0] : 0.f;
     // tanh phase of one accumulator chunk, in place: 32 fp32 columns -> 16 columns of hi pairs + 16 of lo pairs
     auto tanh_chunk = [&](uint32_t col) {
       uint32_t x[32];
@@ -518,7 +524,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
             }
           }
         }
-        if (net == 1) {
+        if (net == 1 && lp_mode) {   // log N(z_out) - log-dets instead of z_out: nothing reads the base sample itself
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < W; ++j) ss = fmaf(y[j], y[j], ss);
+          if (cq != 0) s_ldp[(cq - 1) * kTileM + r_tile] = fmaf(0.5f, ss, ld_sum);
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+          if (cq == 0 && valid) {
+            const float rest = (s_ldp[r_tile] + s_ldp[kTileM + r_tile]) + s_ldp[2 * kTileM + r_tile];
+            const float ss_all = ss + s_ss[(int)(k & 3) * kTileM + r_tile];
+            a.out_lp[row] = ((-0.5f * ss_all - lp_cst) - ((ld_old + ld_sum) + rest)) - lp_scal0;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+        } else if (net == 1) {
           if (valid) {
             float* orow = a.z_out + row * sh.D + sh.t_off + cq * W;
 #pragma unroll
@@ -583,10 +601,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
           } else {
             *reinterpret_cast<uint2*>(a1h + img_off(r, hc, kTileM)) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
           }
-          if (grow < a.rows) *reinterpret_cast<float4*>(a.z_out + grow * sh.D + col) = x;
+          if (lp_mode) {   // sum of squares of this row's conditioning half (it passes through unchanged), for the epilogue
+            float ssq = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w)));
+#pragma unroll
+            for (int o = 1; o < LPR; o <<= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+            if (lane % LPR == 0) s_ss[(int)(k & 3) * kTileM + r] = ssq;
+          } else if (grow < a.rows) *reinterpret_cast<float4*>(a.z_out + grow * sh.D + col) = x;
         }
       }
       fence_async_smem();
+      if (lp_mode) __threadfence_block();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(lead_a1_ready + buf * 8u);
     }

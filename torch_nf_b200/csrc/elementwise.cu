@@ -545,9 +545,11 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   // u1 in (0,1], u2 in [0,1)
   float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);
   float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
-  float r = sqrtf(-2.0f * logf(u1));
+  // hardware lg2 / sqrt / sin / cos (relative error ~2^-22, absolute ~2^-21 for sin / cos on [-pi, pi)): the libm
+  // versions cost ~100 instructions per pair and made the sampler instruction-bound at 4x its HBM time
+  float r = __fsqrt_rn(-1.3862943611198906f * __log2f(u1));       // -2 ln(u1) = -2 ln2 log2(u1)
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  __sincosf(6.283185307179586f * (u2 - 0.5f), &s, &c);          // angle in [-pi, pi): a uniform angle either way
   return make_float2(r * c, r * s);
 }
 
@@ -658,6 +660,19 @@ __global__ void colaffine_kernel(const float* __restrict__ z_in, float* __restri
     z_out[e] = fmaf(z_in[e], scale[d], shift[d]);
   }
 }
+// D % 4 == 0, 16-byte aligned: one float4 per thread and step; a thread's column is fixed when the stride is a
+// multiple of D/4, so its scale / shift stay in registers
+__global__ void colaffine4_kernel(const float4* __restrict__ z_in, float4* __restrict__ z_out,
+                                  const float* __restrict__ scale, const float* __restrict__ shift, int64_t n4, int D4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;       // multiple of D4 (launcher)
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = (int)(e % D4) * 4;
+  const float4 sc = *reinterpret_cast<const float4*>(scale + d), sh = *reinterpret_cast<const float4*>(shift + d);
+  for (; e < n4; e += stride) {
+    const float4 v = __ldcs(z_in + e);
+    __stcs(z_out + e, make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)));
+  }
+}
 
 // launch helper for the row-group kernels
 #define TNF_ROWGROUP(D, ...)                       \
@@ -668,6 +683,107 @@ __global__ void colaffine_kernel(const float* __restrict__ z_in, float* __restri
   } while (0)
 
 static inline int rowgroup_grid(int64_t rows, int G) { return grid_for(rows * G, 256, 16); }
+
+// ---- fused fold kernels of the chain executor (chain.cu): the same arithmetic, in the same order, as the sequences of
+// bn_finalize / fold_colaffine / accum_bcast launches they replace (results are bit-identical to the unfused plan)
+// Inverse direction: every BatchNorm (remembered statistics) and Affine of the chain folded into per-coupling-layer
+// pre-affines with ONE launch.  Steps are in inverse execution order; kind 2 = emit the pending map for the next
+// coupling layer (or the chain's end) and reset it.
+__global__ void chain_fold_inv_kernel(FoldPlan plan, float* __restrict__ scal) {
+  const int D = plan.D, d = threadIdx.x;
+  if (d == 0) {   // scalar log-det: BatchNorm -sum log alpha (remembered), Affine sum alpha (sequential, as fold_colaffine)
+    float acc = scal[0];
+    for (int i = 0; i < plan.n; ++i) {
+      if (plan.s[i].kind == 0) acc += plan.s[i].ld[0];
+      else if (plan.s[i].kind == 1) {
+        float sa = 0.f;
+        for (int k = 0; k < D; ++k) sa += plan.s[i].a[k];
+        acc += sa;
+      }
+    }
+    scal[0] = acc;
+  }
+  if (d >= D) return;
+  float ps = 1.0f, pb = 0.0f;
+  for (int i = 0; i < plan.n; ++i) {
+    const FoldStep& st = plan.s[i];
+    if (st.kind == 2) {
+      st.ps_out[d] = ps; st.pb_out[d] = pb;
+      ps = 1.0f; pb = 0.0f;
+    } else {
+      float s_, t_;
+      if (st.kind == 0) { s_ = st.b[d]; t_ = st.a[d]; }                       // BatchNorm inverse: z * alpha + mean
+      else { s_ = 1.0f / exp_cr(st.a[d]); t_ = -st.b[d] * s_; }               // Affine inverse: (z - shift) / exp(alpha)
+      ps = ps * s_;
+      pb = fmaf(pb, s_, t_);
+    }
+  }
+}
+
+int chain_fold_inv_launch(const FoldPlan& plan, float* scal, cudaStream_t st) {
+  chain_fold_inv_kernel<<<1, plan.D < 32 ? 32 : plan.D, 0, st>>>(plan, scal);
+  return check_launch("chain_fold_inv");
+}
+
+// Sample direction, one launch per BatchNorm: statistics -> mean / alpha / log-det (bn_finalize), fold (z - mean) / alpha
+// into the pending map, scal += log-det, and - when an Affine follows - fold exp(alpha) z + shift and scal += sum alpha.
+__global__ void bn_fold_fwd_kernel(const double* __restrict__ sums, int D, double eps, float* __restrict__ mean,
+                                   float* __restrict__ alpha, float* __restrict__ log_det, const float* __restrict__ ps_in,
+                                   const float* __restrict__ pb_in, const float* __restrict__ aff, float* __restrict__ ps_out,
+                                   float* __restrict__ pb_out, float* __restrict__ scal, int finalize) {
+  __shared__ double red[256];
+  if (finalize) {
+    const double n = sums[2 * D];
+    double acc = 0.0;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      double mu = sums[d] / n;
+      double var = sums[D + d] / n - mu * mu;
+      if (var < 0.0) var = 0.0;
+      float al = (float)sqrt(var + eps);
+      mean[d] = (float)mu;
+      alpha[d] = al;
+      acc += (double)logf(al);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s_ = blockDim.x / 2; s_ > 0; s_ >>= 1) {
+      if ((int)threadIdx.x < s_) red[threadIdx.x] += red[threadIdx.x + s_];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) log_det[0] = (float)(-red[0]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float acc = scal[0] + log_det[0];
+    if (aff != nullptr) {
+      float sa = 0.f;
+      for (int k = 0; k < D; ++k) sa += aff[k];
+      acc += sa;
+    }
+    scal[0] = acc;
+  }
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float ps = ps_in ? ps_in[d] : 1.0f, pb = pb_in ? pb_in[d] : 0.0f;
+    const float a_ = mean[d], b_ = alpha[d];
+    float s_ = 1.0f / b_, t_ = -a_ / b_;
+    ps = ps * s_;
+    pb = fmaf(pb, s_, t_);
+    if (aff != nullptr) {
+      s_ = exp_cr(aff[d]); t_ = aff[D + d];
+      ps = ps * s_;
+      pb = fmaf(pb, s_, t_);
+    }
+    ps_out[d] = ps;
+    pb_out[d] = pb;
+  }
+}
+
+int bn_fold_fwd_launch(const double* sums, int D, double eps, float* mean, float* alpha, float* log_det, const float* ps_in,
+                       const float* pb_in, const float* aff, float* ps_out, float* pb_out, float* scal, int finalize,
+                       cudaStream_t st) {
+  bn_fold_fwd_kernel<<<1, 256, 0, st>>>(sums, D, eps, mean, alpha, log_det, ps_in, pb_in, aff, ps_out, pb_out, scal, finalize);
+  return check_launch("bn_fold_fwd");
+}
 
 int colstats_reduce_launch(const double* partial, int nblocks, int D, double* sums, double rows, cudaStream_t st) {
   colstats_reduce_kernel<<<(2 * D + 1 + 7) / 8, 256, 0, st>>>(partial, nblocks, D, sums, rows);
@@ -810,6 +926,12 @@ int tnf_colaffine(const float* z_in, float* z_out, const float* scale, const flo
                   tnf_stream_t stream) {
   if (rows == 0) return 0;
   TNF_REQUIRE(z_in && z_out && scale && shift, TNF_ERR_ARG, "tnf_colaffine: null pointer");
+  if (D % 4 == 0 && (256 % (D / 4)) == 0 && ((((uintptr_t)z_in | (uintptr_t)z_out | (uintptr_t)scale | (uintptr_t)shift) & 15) == 0)) {
+    const int64_t n4 = rows * (D / 4);
+    int blocks = grid_for(n4, 256 * 4);     // 256 threads per block: a multiple of D/4, so every thread keeps its columns
+    colaffine4_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)z_in, (float4*)z_out, scale, shift, n4, D / 4);
+    return check_launch("tnf_colaffine");
+  }
   colaffine_kernel<<<grid_for(rows * D, 256 * 4), 256, 0, (cudaStream_t)stream>>>(z_in, z_out, scale, shift, rows * D,
                                                                                   D);
   return check_launch("tnf_colaffine");

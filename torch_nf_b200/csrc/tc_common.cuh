@@ -376,6 +376,10 @@ struct Args {
   int tune;   // diagnostic knob of the kernel under development (bits 8.. of `variant`); 0 = shipped configuration
   double* stat_partials;   // [grid*8 warps][2][D] per-warp column sums of the OUTPUT (NULL = off)
   long long* dbg;   // diagnostics: per-phase clock64 stamps of CTA 0 (NULL = off)
+  // fused base density (inverse direction, the chain's LAST executed layer; coupling_tc5 / coupling_tc6 kernels):
+  // out_lp[row] = -1/2 sum_d z_out^2 - D log sqrt(2 pi) - (log_det[row] + sum s) - lp_scal[0]; z_out / log_det are not written
+  float* out_lp;
+  const float* lp_scal;
 };
 
 struct __align__(16) Ctrl {
