@@ -92,6 +92,7 @@ struct __align__(16) Ctrl5 {
   uint64_t e_done[2];     // per group, 8 epilogue warps: accumulator drained (and activation image written)
   uint64_t h_ready[2];    // per group, tcgen05.commit: accumulator of the group's current job complete
   uint64_t h_ready_b[2];  // per group, tcgen05.commit: second N-half of the split job complete
+  uint64_t y_done[2];     // per group, this CTA's 8 epilogue warps: the tile's transformed half is stored (fused statistics)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -147,6 +148,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
       mbar_init(&ct.e_done[g], kEpiWarps2);           // the group's epilogue warps of both CTAs (leader's barrier)
       mbar_init(&ct.h_ready[g], 1);
       mbar_init(&ct.h_ready_b[g], 1);
+      mbar_init(&ct.y_done[g], kEpiWarps2 / 2);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -175,10 +177,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
   const uint32_t lead_w_peer = mapa_u32(smem_u32(&ct.w_peer[0]), 0u);
   const bool want_stats = a.stat_partials != nullptr;
   const bool lp_mode = kInverse && a.out_lp != nullptr;   // fused base density: this is the chain's last executed layer
-  float io_sv1[4] = {0.f, 0.f, 0.f, 0.f}, io_sv2[4] = {0.f, 0.f, 0.f, 0.f};   // I/O warps: sums of columns col..col+3
-  // per-warp statistics rows ([2*D] doubles, own columns only) are gathered in the (then dead) activation images
+  // Column statistics of the OUTPUT are taken by the two I/O warps (a lane owns four columns of each half, sums in
+  // registers): the conditioning half as it passes through, the transformed half read back (L2) once the epilogue warps
+  // have stored a tile - they have a tile of slack, the epilogue warps are the kernel's critical path.
+  float io_sv1[4] = {0.f, 0.f, 0.f, 0.f}, io_sv2[4] = {0.f, 0.f, 0.f, 0.f};   // conditioning half: columns col..col+3
+  float io_tv1[4] = {0.f, 0.f, 0.f, 0.f}, io_tv2[4] = {0.f, 0.f, 0.f, 0.f};   // transformed half: columns t_off+hc..+3
+  // per-I/O-warp statistics rows ([2*D] doubles) are gathered in the (then dead) activation images
   double* stat_rows = reinterpret_cast<double*>(sAct);
-  constexpr int kStatWarps = kEpiWarps2 + 2;
+  constexpr int kStatWarps = 2;
 
   // Static job schedule (L = 2): per tile and group six jobs j = 0..5 = t0 t1 tF s0 s1 sF (net j/3, layer j%3); step
   // n = it*6 + s serves group 0's job s of its tile `it`, then group 1's job (s-2) mod 6 of its tile it (s >= 2) or
@@ -323,7 +329,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
     const uint32_t hcol = tmem + lane_addr + (uint32_t)g * 256u;
     unsigned char* myAct = sAct + (size_t)g * sh.act_bytes();
     uint32_t h_par = 0, hb_par = 0;
-    float st_y = 0.f, st_y2 = 0.f;            // per-lane column sums of the transformed half (column par*W + lane%W)
     const float lp_cst = (float)((double)sh.D * 0.91893853320467274178);   // D log sqrt(2 pi)
     const float lp_scal0 = (lp_mode && a.lp_scal) ? a.lp_scal[0] : 0.f;
 
@@ -477,6 +482,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
             for (int j = 0; j < W; j += 4)
               *reinterpret_cast<float4*>(orow + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           }
+          if (want_stats) {   // release the stored tile half to the I/O warps (statistics)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ct.y_done[g]);
+          }
           if (par == 1) s_ldp[g * kTileM + r_tile] = ld_sum;
           pair_sync();
           if (par == 0 && valid) {
@@ -487,34 +496,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
             else *op = ld_old - tot;
           }
           }
-          if (want_stats) {
-            float s1[W], s2[W];
-#pragma unroll
-            for (int j = 0; j < W; ++j) { s1[j] = valid ? y[j] : 0.f; s2[j] = s1[j] * s1[j]; }
-            if (W == 16) {
-              st_y += warp_transpose_sum16(reinterpret_cast<float(&)[16]>(s1), lane);
-              st_y2 += warp_transpose_sum16(reinterpret_cast<float(&)[16]>(s2), lane);
-            } else {
-              st_y += warp_transpose_sum(reinterpret_cast<float(&)[32]>(s1), lane);
-              st_y2 += warp_transpose_sum(reinterpret_cast<float(&)[32]>(s2), lane);
-            }
-          }
         }
       }
       TNF_STAMP(600);
     }
 #undef TNF_STAMP
-    if (want_stats) {
-      __syncwarp();
-      asm volatile("bar.sync 9, %0;" ::"r"(kEpiWarps2 * 32) : "memory");   // all epilogue warps are past their last phase
-      double* rowp = stat_rows + (size_t)warp * 2 * sh.D;
-      for (int i = lane; i < 2 * sh.D; i += 32) rowp[i] = 0.0;
-      __syncwarp();
-      if (lane < W) {
-        rowp[sh.t_off + par * W + lane] = (double)st_y;
-        rowp[sh.D + sh.t_off + par * W + lane] = (double)st_y2;
-      }
-    }
   } else {
     // =============================== I/O warps: conditioning half, coalesced ===============================
     const int w2 = warp - (kEpiWarps2 + 2);   // warps 18, 19
@@ -568,6 +554,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(lead_a1_ready + (uint32_t)g * 8u);
     };
+    // column sums of the transformed half of the group's tile k, read back (L2) after its epilogue warps stored it
+    auto stats_tile = [&](int g, int64_t k) {
+      mbar_wait(&ct.y_done[g], (uint32_t)(k & 1));
+      const int64_t tile = 2 * ((2 * k + g) * P + pair) + rank;
+      const int tcol = sh.t_off + hc;
+#pragma unroll 1
+      for (int n0 = 0; n0 < NI; n0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int64_t grow = tile * kTileM + row0 + (n0 + u) * RPI + rsub;
+          v[u] = grow < a.rows ? __ldcg(reinterpret_cast<const float4*>(a.z_out + grow * sh.D + tcol))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          io_tv1[0] += v[u].x; io_tv1[1] += v[u].y; io_tv1[2] += v[u].z; io_tv1[3] += v[u].w;
+          io_tv2[0] = fmaf(v[u].x, v[u].x, io_tv2[0]); io_tv2[1] = fmaf(v[u].y, v[u].y, io_tv2[1]);
+          io_tv2[2] = fmaf(v[u].z, v[u].z, io_tv2[2]); io_tv2[3] = fmaf(v[u].w, v[u].w, io_tv2[3]);
+        }
+      }
+    };
     for (int g = 0; g < 2; ++g)
       if (cnt[g] > 0) load_tile(g, 0);
     for (int64_t k = 0; k < cnt[0]; ++k) {
@@ -577,6 +585,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
           load_tile(g, k + 1);
         }
       }
+      if (want_stats)
+        for (int g = 0; g < 2; ++g)
+          if (k < cnt[g]) stats_tile(g, k);
     }
     if (want_stats) {
 #pragma unroll
@@ -585,6 +596,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
         for (int o = LPR; o < 32; o <<= 1) {
           io_sv1[e] += __shfl_xor_sync(0xffffffffu, io_sv1[e], o);
           io_sv2[e] += __shfl_xor_sync(0xffffffffu, io_sv2[e], o);
+          io_tv1[e] += __shfl_xor_sync(0xffffffffu, io_tv1[e], o);
+          io_tv2[e] += __shfl_xor_sync(0xffffffffu, io_tv2[e], o);
         }
       }
     }
@@ -594,17 +607,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads5, 1) coupli
   __syncthreads();
   if (want_stats) {
     // gather: one [2*D] row of doubles per CTA = fixed-order sum over the epilogue warps' rows and the I/O warps' sums
-    if (warp == kEpiWarps2 + 2 || warp == kEpiWarps2 + 3) {   // I/O warps: expand their sums into rows kEpiWarps2 + w2
+    if (warp == kEpiWarps2 + 2 || warp == kEpiWarps2 + 3) {   // I/O warps: expand their sums into rows w2
       const int w2 = warp - (kEpiWarps2 + 2);
       constexpr int LPR = DH / 4;
-      double* rowp = stat_rows + (size_t)(kEpiWarps2 + w2) * 2 * sh.D;
-      for (int i = lane; i < 2 * sh.D; i += 32) rowp[i] = 0.0;
-      __syncwarp();
-      if (lane < LPR) {
+      double* rowp = stat_rows + (size_t)w2 * 2 * sh.D;
+      if (lane < LPR) {   // the two halves cover all D columns
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           rowp[sh.c_off + 4 * lane + e] = (double)io_sv1[e];
           rowp[sh.D + sh.c_off + 4 * lane + e] = (double)io_sv2[e];
+          rowp[sh.t_off + 4 * lane + e] = (double)io_tv1[e];
+          rowp[sh.D + sh.t_off + 4 * lane + e] = (double)io_tv2[e];
         }
       }
     }
