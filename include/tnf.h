@@ -273,6 +273,27 @@ int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params
                      float* z_out, double* log_q, void* workspace, size_t workspace_bytes,
                      tnf_stream_t stream);
 
+/* ---- hyper-network fusion: replaces ConditionalDensityEstimator.log_prob
+ * (conditional_density_estimator.py:101-104: params = param_net(x); density_estimator.log_prob(z, params)) for one
+ * sample per context (N = 1).  The hyper-network's LAST Linear (H -> D_params, :34-37) is evaluated inside the flow
+ * kernel, per sample and in registers, so the (M, D_params) parameter matrix is never written to or read from HBM.
+ *   chain / n_bij   the flow, as for tnf_chain_logprob: STAGES x [RealNVP(upper), BatchNorm, RealNVP(lower), BatchNorm,
+ *                   Affine] (+ ToInterval), what NormFlow(arch_type='coupling') builds (density_estimator.py:260-282);
+ *                   BatchNorm with its remembered statistics (bijectors.py:420-426)
+ *   h (M, H)        output of the hyper-network's last hidden activation (the input of its last Linear), float32
+ *   weight, bias    the last Linear's parameters in torch layout: weight (D_params, H) row-major, bias (D_params)
+ *   packed          tnf_cde_packed_bytes(D_params, H) bytes, written by tnf_cde_pack once per parameter update: the
+ *                   last Linear re-laid in the order the inverse chain consumes the flow parameters (blocks of 32)
+ *   z (M, D)        the samples, log_prob (M) float32 = log N(z0; 0, I) - sum of log-dets
+ * tnf_cde_supported: 1 when the chain has that structure and a compiled shape ((D, U) in {2, 4, 6, 8} x {15} and (8, 16), L = 2,
+ * one stage), else 0 - the caller then materialises params and uses tnf_chain_logprob. */
+int tnf_cde_supported(const tnf_bijector_t* chain, int n_bij, int D, int H);
+size_t tnf_cde_packed_bytes(int64_t D_params, int H);
+int tnf_cde_pack(const tnf_bijector_t* chain, int n_bij, int D, const float* weight, const float* bias, int H,
+                 void* packed, tnf_stream_t stream);
+int tnf_cde_logprob(const tnf_bijector_t* chain, int n_bij, int D, const float* h, int H, const void* packed,
+                    const float* z, int64_t M, float* log_prob, tnf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,12 +56,12 @@ def run(name):
                 "finite": bool(torch.isfinite(out).all())}
     else:   # conditional flows: one parameter row per sample (regime B)
         if name == "c2b":
-            D, Dx, hidden, M, sup = 8, 8, [100], 65536, None
+            D, Dx, hidden, M, sup, U = 8, 8, [100], 65536, None, 15      # notebooks/LFI_gauss.ipynb:93-117
         else:   # c4like: scripts/lfi_mat.py shapes with 'coupling'
-            D, Dx, hidden, M = 6, 2, [64, 64], 1 << 18
+            D, Dx, hidden, M, U = 6, 2, [64, 64], 1 << 18, 15          # scripts/lfi_mat.py:35-46: 2 D clamped up to 15
             sup = ToInterval(D, [-2.0] * D, [2.0] * D)
         tnf.set_conditioner_precision("fp32")
-        nf = de.NormFlow(D, True, "coupling", 1, 2, max(15, 2 * D), sup)
+        nf = de.NormFlow(D, True, "coupling", 1, 2, U, sup)
         torch.manual_seed(0)
         cde = ConditionalDensityEstimator(nf, Dx, hidden).cuda()
         x = torch.randn(M, Dx, device="cuda")
@@ -77,10 +77,26 @@ def run(name):
             return cde.log_prob(z, x)
         ms, launches, out = timed(step_flow)
         ms2, launches2, _ = timed(step_cde)
+        # conditional log_prob alone (the SNPE density evaluation): hyper-network fused into the flow kernel vs params in HBM
+        from torch_nf_b200 import config
+        zz = (torch.rand(M, 1, D, device="cuda") * 3.6 - 1.8) if sup is not None else torch.randn(M, 1, D, device="cuda")
+        config.set_cde_fusion(True)
+        ms_f, launches_f, lp_f = timed(lambda: cde.log_prob(zz, x))
+        config.set_cde_fusion(False)
+        ms_u, launches_u, lp_u = timed(lambda: cde.log_prob(zz, x))
+        config.set_cde_fusion(True)
+        H = cde.param_net[-1].in_features
         pbytes = 2 * nf.D_params * 4            # the parameter row is read once per direction
         line = {"workload": name, "config": "conditional NormFlow D=%d, D_params=%d, M=%d, N=1, fp32 (per-sample weights)" % (D, nf.D_params, M),
                 "value": M / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "kernel_launches_per_step": launches,
                 "with_hyper_network": {"value": M / (ms2 * 1e-3), "ms_per_step": ms2, "note": "param_net (torch Linear/Tanh) evaluated inside the step, twice"},
+                "cde_log_prob": {"fused": {"value": M / (ms_f * 1e-3), "ms": ms_f, "kernel_launches": launches_f,
+                                           "bound": "CUDA-core FMA (last Linear per sample in registers)",
+                                           "fp32_tflops": 2.0 * H * nf.D_params * M / (ms_f * 1e-3) / 1e12,
+                                           "hbm_bytes_per_sample": 4 * (H + D + 1)},
+                                 "unfused": {"value": M / (ms_u * 1e-3), "ms": ms_u, "kernel_launches": launches_u,
+                                             "hbm_bytes_per_sample": 2 * nf.D_params * 4 + 4 * (H + D + 1)},
+                                 "max_rel_diff": float(((lp_f - lp_u).abs() / lp_u.abs().clamp(min=1)).max())},
                 "roofline": {"bound": "hbm (parameter rows)", "bytes_per_sample": pbytes + 2 * (2 * D * 4 + 4),
                              "hbm_frac": (pbytes + 2 * (2 * D * 4 + 4)) * M / (ms * 1e-3) / 1e9 / PEAK["hbm_gbs"]},
                 "finite": bool(torch.isfinite(out).all())}

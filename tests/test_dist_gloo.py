@@ -13,7 +13,7 @@ import torch.distributed as td
 import torch.multiprocessing as mp
 
 from oracle import flow_oracle as O
-from torch_nf_b200 import dist
+from torch_nf_b200 import dist, train
 from torch_nf_b200.synthetic import synthetic_params
 
 
@@ -105,6 +105,21 @@ def _worker(rank, world, port, out):
         res["grad_rel"] = float((g - p2.grad).norm() / p2.grad.norm())
         m = dist.allreduce_mean_scalar(torch.tensor(float(rank + 1)))
         res["mean_scalar"] = float(m)
+        # 5. train.train_step on equally sized shards: the averaged local gradients are the full-batch gradient, the
+        #    replicated optimiser step leaves identical parameters on every rank
+        even = (total // world) * world
+        lo_e, hi_e = dist.shard_range(even)
+        pw = torch.nn.Parameter(params.clone())
+        opt = torch.optim.Adam([pw], lr=1e-3)
+        loss = train.train_step(lambda: -O.normflow_log_prob(chain, D, z_ref[:, lo_e:hi_e], pw, st_ref).mean(), [pw], opt)
+        pf = torch.nn.Parameter(params.clone())
+        optf = torch.optim.Adam([pf], lr=1e-3)
+        optf.zero_grad()
+        loss_f = -O.normflow_log_prob(chain, D, z_ref[:, :even], pf, st_ref).mean()
+        loss_f.backward()
+        optf.step()
+        res["train_loss_err"] = abs(float(loss) - float(loss_f))
+        res["train_param_err"] = float((pw.detach() - pf.detach()).abs().max())
         if rank == 0:
             out.put(res)
     finally:
@@ -128,6 +143,7 @@ def test_world_size_2_gloo():
     assert res["z_err"] < 2e-5 and res["lq_err"] < 1e-4 and res["lp_err"] < 1e-4
     assert res["grad_rel"] < 1e-5
     assert res["mean_scalar"] == 1.5
+    assert res["train_loss_err"] < 1e-4 and res["train_param_err"] < 1e-6
 
 
 def test_single_process_defaults():

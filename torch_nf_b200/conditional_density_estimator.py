@@ -90,5 +90,58 @@ class ConditionalDensityEstimator(torch.nn.Module):
         return self.density_estimator(N=N, params=params, freeze_bn=freeze_bn)
 
     def log_prob(self, z, x):
+        lp = self._log_prob_fused(z, x)
+        if lp is not None:
+            return lp
         params = self.param_net(x)
         return self.density_estimator.log_prob(z, params)
+
+    # ---- hyper-network fusion: the last Linear is evaluated inside the flow kernel ------------------
+    def _log_prob_fused(self, z, x):
+        """log q(z | x) through ``tnf_cde_logprob`` or None when the call needs the unfused path (autograd, several
+        samples per context, dropout, a chain without a compiled shape).  ``h = param_net[:-1](x)`` stays torch (a few
+        small GEMMs); the (M, D_params) matrix the reference builds at conditional_density_estimator.py:102 is never
+        materialised."""
+        from . import _lib, config, ops
+        nf = self.density_estimator
+        last = self.param_net[-1]
+        if (not config.cde_fusion() or self.dropout or not isinstance(last, torch.nn.Linear) or len(self.param_net) < 2
+                or z.dim() != 3 or z.shape[1] != 1 or x.dim() != 2 or x.shape[0] != z.shape[0]
+                or z.dtype != torch.float32 or x.dtype != torch.float32 or not torch.cuda.is_available()):
+            return None
+        if torch.is_grad_enabled() and (z.requires_grad or x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return None
+        M, _, D = z.shape
+        H = last.in_features
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pod = nf._chain_pod(_NoParams(dev, M), de._Rows(M, 0, torch.float32), None, sample=False)
+        if pod is None:
+            return None
+        arr, keep, _ = pod
+        lib = _lib.lib()
+        if not lib.tnf_cde_supported(arr, len(nf.bijectors), D, H):
+            return None
+        home = z.device
+        with torch.no_grad():
+            h = ops.to_device(self.param_net[:-1](x)).contiguous()
+            key = (last.weight, last.weight._version, last.bias, last.bias._version, dev)
+            hit = getattr(self, "_cde_pack", None)
+            if hit is None or any(a is not b if isinstance(a, torch.Tensor) else a != b for a, b in zip(hit[0], key)):
+                w = ops.to_device(last.weight.detach()).contiguous()
+                b = ops.to_device(last.bias.detach()).contiguous()
+                packed = torch.empty(lib.tnf_cde_packed_bytes(nf.D_params, H), dtype=torch.uint8, device=dev)
+                _lib.check(lib.tnf_cde_pack(arr, len(nf.bijectors), D, w.data_ptr(), b.data_ptr(), H, packed.data_ptr(),
+                                            ops._stream()), "tnf_cde_pack")
+                self._cde_pack = hit = (key, packed)
+            zd = ops.to_device(z).contiguous()
+            lp = torch.empty((M, 1), dtype=torch.float32, device=dev)
+            _lib.check(lib.tnf_cde_logprob(arr, len(nf.bijectors), D, h.data_ptr(), H, hit[1].data_ptr(), zd.data_ptr(), M,
+                                           lp.data_ptr(), ops._stream()), "tnf_cde_logprob")
+        return de._to(lp, home)
+
+
+class _NoParams(object):
+    """Stand-in for the parameter matrix in ``NormFlow._chain_pod`` (device and row count are all it reads there)."""
+
+    def __init__(self, device, M):
+        self.device, self.shape = device, (max(2, M), 0)

@@ -95,3 +95,18 @@ def set_chain_abi(on):
 
 def chain_abi():
     return _chain_abi
+
+
+_cde_fusion = os.environ.get("TNF_CDE_FUSION", "1") != "0"
+
+
+def set_cde_fusion(on):
+    """``ConditionalDensityEstimator.log_prob`` without autograd, one sample per context: evaluate the hyper-network's
+    last Linear inside the flow kernel (tnf_cde_logprob; the (M, D_params) parameter matrix never reaches HBM) where
+    the chain has a compiled shape (default), or always materialise ``params`` as the reference does."""
+    global _cde_fusion
+    _cde_fusion = bool(on)
+
+
+def cde_fusion():
+    return _cde_fusion
