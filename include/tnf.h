@@ -285,14 +285,18 @@ int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params
  *   packed          tnf_cde_packed_bytes(D_params, H) bytes, written by tnf_cde_pack once per parameter update: the
  *                   last Linear re-laid in the order the inverse chain consumes the flow parameters (blocks of 32)
  *   z (M, D)        the samples, log_prob (M) float32 = log N(z0; 0, I) - sum of log-dets
+ *   variant         TNF_CDE_TC: the parameter rows h . W + b are produced by tcgen05 MMAs into tensor memory (fp32
+ *                   parity by an fp16 hi / lo operand split, three MMAs per product) and read by the thread that owns
+ *                   the sample's TMEM lane; TNF_CDE_CC: by fp32 FMAs in the consumer threads.  The packed layouts differ.
  * tnf_cde_supported: 1 when the chain has that structure and a compiled shape ((D, U) in {2, 4, 6, 8} x {15} and (8, 16), L = 2,
  * one stage), else 0 - the caller then materialises params and uses tnf_chain_logprob. */
+enum { TNF_CDE_TC = 0, TNF_CDE_CC = 1 };
 int tnf_cde_supported(const tnf_bijector_t* chain, int n_bij, int D, int H);
-size_t tnf_cde_packed_bytes(int64_t D_params, int H);
+size_t tnf_cde_packed_bytes(int64_t D_params, int H, int variant);
 int tnf_cde_pack(const tnf_bijector_t* chain, int n_bij, int D, const float* weight, const float* bias, int H,
-                 void* packed, tnf_stream_t stream);
+                 void* packed, int variant, tnf_stream_t stream);
 int tnf_cde_logprob(const tnf_bijector_t* chain, int n_bij, int D, const float* h, int H, const void* packed,
-                    const float* z, int64_t M, float* log_prob, tnf_stream_t stream);
+                    const float* z, int64_t M, float* log_prob, int variant, tnf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -81,7 +81,13 @@ def run(name):
         from torch_nf_b200 import config
         zz = (torch.rand(M, 1, D, device="cuda") * 3.6 - 1.8) if sup is not None else torch.randn(M, 1, D, device="cuda")
         config.set_cde_fusion(True)
+        config.set_cde_variant("cc")
+        ms_c, launches_c, lp_c = timed(lambda: cde.log_prob(zz, x))
+        config.set_cde_variant("tc")
         ms_f, launches_f, lp_f = timed(lambda: cde.log_prob(zz, x))
+        with torch.no_grad():
+            hh = cde.param_net[:-1](x)
+        ms_h, _, _ = timed(lambda: cde.param_net[:-1](x))
         config.set_cde_fusion(False)
         ms_u, launches_u, lp_u = timed(lambda: cde.log_prob(zz, x))
         config.set_cde_fusion(True)
@@ -91,9 +97,13 @@ def run(name):
                 "value": M / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "kernel_launches_per_step": launches,
                 "with_hyper_network": {"value": M / (ms2 * 1e-3), "ms_per_step": ms2, "note": "param_net (torch Linear/Tanh) evaluated inside the step, twice"},
                 "cde_log_prob": {"fused": {"value": M / (ms_f * 1e-3), "ms": ms_f, "kernel_launches": launches_f,
-                                           "bound": "CUDA-core FMA (last Linear per sample in registers)",
-                                           "fp32_tflops": 2.0 * H * nf.D_params * M / (ms_f * 1e-3) / 1e12,
+                                           "producer": "tcgen05 (fp16 hi/lo split, 3 MMAs per product), parameter rows in tensor memory",
+                                           "hidden_layers_of_param_net_ms": ms_h,
+                                           "algorithmic_tflops": 2.0 * (H + 1) * nf.D_params * M / (ms_f * 1e-3) / 1e12,
                                            "hbm_bytes_per_sample": 4 * (H + D + 1)},
+                                 "fused_cuda_cores": {"value": M / (ms_c * 1e-3), "ms": ms_c, "kernel_launches": launches_c,
+                                                      "fp32_tflops": 2.0 * H * nf.D_params * M / (ms_c * 1e-3) / 1e12,
+                                                      "max_rel_diff_vs_tc": float(((lp_f - lp_c).abs() / lp_c.abs().clamp(min=1)).max())},
                                  "unfused": {"value": M / (ms_u * 1e-3), "ms": ms_u, "kernel_launches": launches_u,
                                              "hbm_bytes_per_sample": 2 * nf.D_params * 4 + 4 * (H + D + 1)},
                                  "max_rel_diff": float(((lp_f - lp_u).abs() / lp_u.abs().clamp(min=1)).max())},

@@ -41,8 +41,17 @@ def _fused_and_unfused(cde, z, x):
     return a, b, n_fused, n_unfused
 
 
+@pytest.fixture(params=["tc", "cc"], autouse=True)
+def _variant(request):
+    """Every test runs with both producers of the parameter rows: tcgen05 (default) and CUDA-core FMA."""
+    config.set_cde_variant(request.param)
+    yield request.param
+    config.set_cde_variant("tc")
+
+
 @pytest.mark.parametrize("D,D_x,hidden,support,M", [(6, 2, [64, 64], True, 1000), (8, 8, [100], False, 4096 + 77),
-                                                    (2, 3, [16], False, 5), (4, 1, [7, 33], True, 129), (6, 2, [64, 64], True, 1)])
+                                                    (2, 3, [16], False, 5), (4, 1, [7, 33], True, 129), (6, 2, [64, 64], True, 1),
+                                                    (6, 2, [64, 64], True, 148 * 128 * 3 + 17), (8, 8, [100], False, 148 * 128 + 1)])
 def test_fused_logprob_matches_unfused_and_oracle(D, D_x, hidden, support, M):
     nf, cde = _cde(D, D_x, hidden, support)
     g = torch.Generator().manual_seed(1)

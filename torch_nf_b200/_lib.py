@@ -72,9 +72,9 @@ PROTOTYPES.update({
     "tnf_chain_logprob": (I, [P, I, P, P, L, L, L, I, I, P, P, Z, P]),
     "tnf_chain_sample": (I, [P, I, P, L, L, L, I, I, P, U64, U64, I, ALLREDUCE_FN, P, P, P, P, P, Z, P]),
     "tnf_cde_supported": (I, [P, I, I, I]),
-    "tnf_cde_packed_bytes": (Z, [L, I]),
-    "tnf_cde_pack": (I, [P, I, I, P, P, I, P, P]),
-    "tnf_cde_logprob": (I, [P, I, I, P, I, P, P, L, P, P]),
+    "tnf_cde_packed_bytes": (Z, [L, I, I]),
+    "tnf_cde_pack": (I, [P, I, I, P, P, I, P, I, P]),
+    "tnf_cde_logprob": (I, [P, I, I, P, I, P, P, L, P, I, P]),
 })
 
 _LIB = None

@@ -124,19 +124,20 @@ class ConditionalDensityEstimator(torch.nn.Module):
         home = z.device
         with torch.no_grad():
             h = ops.to_device(self.param_net[:-1](x)).contiguous()
-            key = (last.weight, last.weight._version, last.bias, last.bias._version, dev)
+            variant = 0 if config.cde_variant() == "tc" else 1
+            key = (last.weight, last.weight._version, last.bias, last.bias._version, dev, variant)
             hit = getattr(self, "_cde_pack", None)
             if hit is None or any(a is not b if isinstance(a, torch.Tensor) else a != b for a, b in zip(hit[0], key)):
                 w = ops.to_device(last.weight.detach()).contiguous()
                 b = ops.to_device(last.bias.detach()).contiguous()
-                packed = torch.empty(lib.tnf_cde_packed_bytes(nf.D_params, H), dtype=torch.uint8, device=dev)
+                packed = torch.empty(lib.tnf_cde_packed_bytes(nf.D_params, H, variant), dtype=torch.uint8, device=dev)
                 _lib.check(lib.tnf_cde_pack(arr, len(nf.bijectors), D, w.data_ptr(), b.data_ptr(), H, packed.data_ptr(),
-                                            ops._stream()), "tnf_cde_pack")
+                                            variant, ops._stream()), "tnf_cde_pack")
                 self._cde_pack = hit = (key, packed)
             zd = ops.to_device(z).contiguous()
             lp = torch.empty((M, 1), dtype=torch.float32, device=dev)
             _lib.check(lib.tnf_cde_logprob(arr, len(nf.bijectors), D, h.data_ptr(), H, hit[1].data_ptr(), zd.data_ptr(), M,
-                                           lp.data_ptr(), ops._stream()), "tnf_cde_logprob")
+                                           lp.data_ptr(), variant, ops._stream()), "tnf_cde_logprob")
         return de._to(lp, home)
 
 

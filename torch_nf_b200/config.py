@@ -98,6 +98,20 @@ def chain_abi():
 
 
 _cde_fusion = os.environ.get("TNF_CDE_FUSION", "1") != "0"
+_cde_variant = os.environ.get("TNF_CDE_VARIANT", "tc")
+
+
+def set_cde_variant(v):
+    """"tc" (default): the fused kernel forms the parameter rows on tcgen05 tensor cores (fp16 hi / lo split, fp32
+    parity); "cc": with fp32 FMAs on CUDA cores."""
+    global _cde_variant
+    if v not in ("tc", "cc"):
+        raise ValueError('cde variant must be "tc" or "cc"')
+    _cde_variant = v
+
+
+def cde_variant():
+    return _cde_variant
 
 
 def set_cde_fusion(on):
