@@ -219,19 +219,25 @@ def test_normflow_bf16_mode_vs_oracle_at_scale(D, stages, N):
 
 
 def test_coupling_tc_fused_column_stats():
-    """The kernel's own [sum | sumsq | rows] of its output equals tnf_colstats on that output."""
+    """The kernel's own [sum | sumsq | rows] of its output equals tnf_colstats on that output: the two-tile bf16 kernels
+    (fp32 partial sums), and the TMEM-resident kernel in both precisions (float64 accumulation: fp32-parity class)."""
     U, L = 256, 2
-    for D, N, upper in ((64, 1000, True), (64, 128 * 148 * 2 + 77, False), (64, 90, True), (128, 128 * 148 + 5, True)):
+    cases = [(64, 1000, True, "bf16"), (64, 128 * 148 * 2 + 77, False, "bf16"), (64, 90, True, "bf16"), (128, 128 * 148 + 5, True, "bf16"),
+             (64, 128 * 148 * 3 + 77, False, "fp32_tc"), (64, 90, True, "fp32_tc"), (128, 128 * 148 + 5, True, "fp32_tc"),
+             (256, 128 * 148 * 2 + 9, True, "bf16"), (256, 300, False, "fp32_tc")]
+    for D, N, upper, prec in cases:
         params = T(synthetic_params([("RealNVP", L, U, upper)], D, 1, seed=21))
         z_in = torch.randn(1, N, D, device="cuda") * 1.5 + 0.3
-        packed = ops.tc_pack(params.cuda()[0], D, U, L, upper)
+        packed = ops.tc_pack(params.cuda()[0], D, U, L, upper, precision=prec)
         ps = (torch.rand(D) + 0.5).cuda(); pb = torch.randn(D).cuda()
         z, ld, sums = ops.coupling_tc(z_in, packed, D, U, L, upper, ops.TNF_FORWARD, pre_scale=ps, pre_shift=pb,
-                                      want_stats=True)
+                                      want_stats=True, precision=prec)
         ref = ops.colstats(z, D)
         assert float(sums[2 * D]) == N == float(ref[2 * D])
-        np.testing.assert_allclose(sums[:2 * D].cpu().numpy(), ref[:2 * D].cpu().numpy(), rtol=2e-5, atol=2e-3 * N ** 0.5)
-        z2, _ = ops.coupling_tc(z_in, packed, D, U, L, upper, ops.TNF_FORWARD, pre_scale=ps, pre_shift=pb)
+        tc6 = prec == "fp32_tc" or D == 256
+        np.testing.assert_allclose(sums[:2 * D].cpu().numpy(), ref[:2 * D].cpu().numpy(), rtol=2e-6 if tc6 else 2e-5,
+                                   atol=(1e-4 if tc6 else 2e-3) * N ** 0.5)
+        z2, _ = ops.coupling_tc(z_in, packed, D, U, L, upper, ops.TNF_FORWARD, pre_scale=ps, pre_shift=pb, precision=prec)
         assert torch.equal(z, z2)
 
 

@@ -424,7 +424,8 @@ int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params
     if (b.kind == TNF_BIJ_REALNVP) {
       float* o = (last && D_out == D) ? z_out : out_buf();
       if (b.packed) {
-        const bool want = !last && chain[i + 1].kind == TNF_BIJ_BATCHNORM && !freeze_bn && D <= 128 && tc_precision == TNF_TC_BF16;
+        const bool want = !last && chain[i + 1].kind == TNF_BIJ_BATCHNORM && !freeze_bn &&
+                          tc_stats_fusable(D, b.num_units, b.num_layers, tc_precision);
         if (b.ev_start) cudaEventRecord((cudaEvent_t)b.ev_start, st);
         TNF_TRY(tnf_coupling_tc(cur, o, ld_acc, b.packed, rows, D, b.num_units, b.num_layers, b.transform_upper, TNF_FORWARD,
                                 TNF_LD_ADD, have_pend ? pend[np ^ 1][0] : nullptr, have_pend ? pend[np ^ 1][1] : nullptr,

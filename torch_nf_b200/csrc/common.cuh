@@ -30,6 +30,8 @@ int bn_fold_fwd_launch(const double* sums, int D, double eps, float* mean, float
 // tnf_coupling_tc with the fused base density of the chain executor: out_lp != NULL (inverse direction, TNF_LD_ADD) makes
 // the layer emit log N(z_out) - log_det[row] - sum s - lp_scal[0] instead of z_out / log_det (coupling_tc.cu)
 bool tc_lp_fusable(int D, int U, int L, int precision);
+// the layer's kernel can emit the column statistics of its output (the next BatchNorm's batch statistics)
+bool tc_stats_fusable(int D, int U, int L, int precision);
 int coupling_tc_impl(const float* z_in, float* z_out, float* log_det, const void* packed, int64_t rows, int D, int U, int L,
                      int transform_upper, int direction, int accum, const float* pre_scale, const float* pre_shift,
                      double* col_stats, void* stats_workspace, int precision, int variant, void* debug, float* out_lp,

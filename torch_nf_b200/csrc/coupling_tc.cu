@@ -1591,6 +1591,11 @@ static bool pairs5_default(int D, int U, int L) {
   return tc::shape_supported2(D, U, L) && tc::shape_supported5(D, U, L) && tc::smem_bytes5(tc::Shape(D, U, L, 1), 4) <= 227 * 1024;
 }
 
+bool tc_stats_fusable(int D, int U, int L, int precision) {
+  if (!tnf_tc_supported(D, U, L, precision)) return false;
+  return precision == TNF_TC_FP32 || bf16_on_tc6(D, U, L) || D <= 128;
+}
+
 bool tc_lp_fusable(int D, int U, int L, int precision) {
   if (!tnf_tc_supported(D, U, L, precision)) return false;
   return precision == TNF_TC_FP32 || bf16_on_tc6(D, U, L) || pairs5_default(D, U, L);
@@ -1613,7 +1618,8 @@ int coupling_tc_impl(const float* z_in, float* z_out, float* log_det, const void
     TNF_REQUIRE(z_in && (z_out || out_lp) && log_det && packed, TNF_ERR_ARG, "tnf_coupling_tc: null pointer");
     TNF_REQUIRE((((uintptr_t)z_in | (uintptr_t)z_out | (uintptr_t)packed) & 15) == 0, TNF_ERR_ALIGN,
                 "tnf_coupling_tc: z and packed weights must be 16-byte aligned");
-    TNF_REQUIRE(col_stats == nullptr, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: no fused column statistics in this kernel");
+    TNF_REQUIRE(col_stats == nullptr || (stats_workspace != nullptr && direction == TNF_FORWARD), TNF_ERR_ARG,
+                "tnf_coupling_tc: this kernel takes fused column statistics in the sample direction, with a workspace");
     const int64_t n_super6 = ((rows + tc::kTileM - 1) / tc::kTileM + 1) / 2;
     const int64_t max_pairs6 = num_sms() / 2;
     const int grid6 = 2 * (int)(n_super6 < max_pairs6 ? n_super6 : max_pairs6);
@@ -1623,14 +1629,16 @@ int coupling_tc_impl(const float* z_in, float* z_out, float* log_det, const void
     TNF_REQUIRE(ns >= 4, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: only %d weight stages fit (a job needs up to 4)", ns);
     TNF_REQUIRE(smem6 <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: shape needs %zu B shared memory", smem6);
     tc::Args a6{z_in, z_out, log_det, (const unsigned char*)packed, pre_scale, pre_shift, rows,
-                D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, ns, 2, variant >> 8, nullptr, (long long*)debug,
-                out_lp, lp_scal};
+                D, U, L, transform_upper != 0, direction == TNF_INVERSE, accum, ns, 2, variant >> 8,
+                col_stats ? (double*)stats_workspace : nullptr, (long long*)debug, out_lp, lp_scal};
     cudaError_t e6 = (cudaError_t)tc::launch_tc6(a6, grid6, split6, smem6, (cudaStream_t)stream);
     if (e6 != cudaSuccess) {
       set_error("tnf_coupling_tc: cudaFuncSetAttribute(%zu B smem): %s", smem6, cudaGetErrorString(e6));
       return (int)e6;
     }
-    return check_launch("tnf_coupling_tc");
+    int rc6 = check_launch("tnf_coupling_tc");
+    if (rc6 || col_stats == nullptr) return rc6;
+    return colstats_reduce_launch((const double*)stats_workspace, grid6, D, col_stats, (double)rows, (cudaStream_t)stream);
   }
   const int g_tc_variant = variant & 15, g_tc_groups = (variant & 16) ? 1 : 2;   // per-call diagnostics, no global state
   long long* const g_tc_debug = (long long*)debug;

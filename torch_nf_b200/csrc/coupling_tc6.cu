@@ -179,6 +179,7 @@ struct __align__(16) Ctrl6 {
   uint64_t e_fin;         // 16 epilogue warps of both CTAs (leader's barrier): the final accumulator has been read
   uint64_t h_ready[2];    // tcgen05.commit: N-half a / b of the current hidden job complete
   uint64_t f_ready;       // tcgen05.commit: final-layer accumulator complete
+  uint64_t y_done;        // this CTA's 16 epilogue warps: the tile's transformed half is stored (fused statistics)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -188,7 +189,8 @@ struct __align__(16) Ctrl6 {
 size_t smem_bytes6(int D, int U, int L, int split, int n_stages) {
   Shape6 sh(D, U, L, 1, split);
   return (size_t)n_stages * kStageBytes + (split ? 4 : 2) * sh.a1_bytes() + kOnesBytes + sizeof(Ctrl6) +
-         (size_t)(2 * sh.D + 4 * kTileM + 4 * kTileM) * sizeof(float) + (size_t)sh.bias_rank_bytes() + kBiasPad6;
+         (size_t)(2 * sh.D + 4 * kTileM + 4 * kTileM) * sizeof(float) + (size_t)(16 * 64) * sizeof(double) +
+         (size_t)sh.bias_rank_bytes() + kBiasPad6;
 }
 
 // dense, D = f32, A = B = f16 (split) or bf16, K-major, M = 256 (pair)
@@ -273,8 +275,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
   // [tile & 3][128] sum z^2 of the conditioning half (fused base density).  Three tiles are live at once: the I/O warps
   // load tile k+2 as soon as tile k's layer-0 jobs are done, before tile k's epilogue has consumed its entry
   float* s_ss = s_ldp + 4 * kTileM;
-  unsigned char* sBias = reinterpret_cast<unsigned char*>(s_ss + 4 * kTileM);
+  double* s_acc = reinterpret_cast<double*>(s_ss + 4 * kTileM);    // [16][64]: the I/O threads' float64 accumulators (fused statistics)
+  // [2 I/O warps][2 * D] column sums, written once after the CTA's last tile: in the A1 images, dead by then (an I/O
+  // warp gets there through y_done of the last tile, which follows every MMA that reads them, in both CTAs of the pair)
+  double* s_stat = reinterpret_cast<double*>(sA1);
+  unsigned char* sBias = reinterpret_cast<unsigned char*>(s_acc + 16 * 64);
   const bool lp_mode = kInverse && a.out_lp != nullptr;           // this is the chain's last executed layer: emit log_prob, not z
+  // Column statistics of the OUTPUT (the next BatchNorm's batch statistics), taken by the two I/O warps in float64: the
+  // conditioning half as it passes through, the transformed half read back (L2) once the epilogue warps stored a tile
+  const bool want_stats = !kInverse && a.stat_partials != nullptr;   // sample direction only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
@@ -291,6 +300,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
     mbar_init(&ct.t_done, 2 * kEpiWarps2);
     mbar_init(&ct.e_fin, 2 * kEpiWarps2);
     mbar_init(&ct.f_ready, 1);
+    mbar_init(&ct.y_done, kEpiWarps2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kEpiWarps2) tmem_alloc2(&ct.tmem_base, 512);
@@ -543,6 +553,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
             for (int j = 0; j < W; j += 4)
               *reinterpret_cast<float4*>(orow + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           }
+          if (want_stats) {   // release the stored tile half to the I/O warps
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ct.y_done);
+          }
           if (cq != 0) s_ldp[(cq - 1) * kTileM + r_tile] = ld_sum;
           asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // the four chunk owners of this lane quadrant
           if (cq == 0 && valid) {
@@ -569,12 +583,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
     const int rsub = lane / LPR;
     const float4 ps = *reinterpret_cast<const float4*>(s_pscale + col);
     const float4 pb = *reinterpret_cast<const float4*>(s_pshift + col);
+    // float64 accumulators of this thread's 4 + 4 columns (sum, sum of squares; conditioning half 0..7, transformed
+    // half 8..15) live in shared memory: 16 doubles in registers for the whole kernel would spill the I/O loop.  Per
+    // tile the (<= 16-row) partial sums are formed in fp32 and added once.
+    double* my_acc = s_acc + (w2 * 32 + lane);   // element i at my_acc[64 * i]
+    if (want_stats)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) my_acc[64 * i] = 0.0;
+    auto stats_tile = [&](int64_t k) {   // column sums of the transformed half of tile k, read back after its epilogue
+      mbar_wait(&ct.y_done, (uint32_t)(k & 1));
+      const int64_t tile = 2 * (k * P + pair) + rank;
+      const int tcol = sh.t_off + hc;
+      float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int n0 = 0; n0 < NI; n0 += kIoBatch) {
+        float4 v[kIoBatch];
+#pragma unroll
+        for (int u = 0; u < kIoBatch; ++u) {
+          const int64_t grow = tile * kTileM + row0 + (n0 + u) * RPI + rsub;
+          v[u] = grow < a.rows ? __ldcg(reinterpret_cast<const float4*>(a.z_out + grow * sh.D + tcol))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kIoBatch; ++u) {
+          p1[0] += v[u].x; p1[1] += v[u].y; p1[2] += v[u].z; p1[3] += v[u].w;
+          p2[0] = fmaf(v[u].x, v[u].x, p2[0]); p2[1] = fmaf(v[u].y, v[u].y, p2[1]);
+          p2[2] = fmaf(v[u].z, v[u].z, p2[2]); p2[3] = fmaf(v[u].w, v[u].w, p2[3]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { my_acc[64 * (8 + e)] += (double)p1[e]; my_acc[64 * (12 + e)] += (double)p2[e]; }
+    };
     for (int64_t k = 0; k < cnt; ++k) {
       const uint32_t buf = (uint32_t)(k & 1);
       if (k >= 2) mbar_wait(&ct.a1_free[buf], (uint32_t)(((k >> 1) - 1) & 1));   // tile k-2's layer-0 jobs are done with it
       const int64_t tile = 2 * (k * P + pair) + rank;
       unsigned char* a1h = sA1 + (size_t)(kImgs * buf) * sh.a1_bytes();
       unsigned char* a1l = a1h + sh.a1_bytes();
+      float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};   // this tile's partial sums, conditioning half
 #pragma unroll 1
       for (int n0 = 0; n0 < NI; n0 += kIoBatch) {
         float4 v[kIoBatch];
@@ -606,18 +652,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
 #pragma unroll
             for (int o = 1; o < LPR; o <<= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
             if (lane % LPR == 0) s_ss[(int)(k & 3) * kTileM + r] = ssq;
-          } else if (grow < a.rows) *reinterpret_cast<float4*>(a.z_out + grow * sh.D + col) = x;
+          } else if (grow < a.rows) {
+            *reinterpret_cast<float4*>(a.z_out + grow * sh.D + col) = x;
+            if (want_stats) {
+              c1[0] += x.x; c1[1] += x.y; c1[2] += x.z; c1[3] += x.w;
+              c2[0] = fmaf(x.x, x.x, c2[0]); c2[1] = fmaf(x.y, x.y, c2[1]);
+              c2[2] = fmaf(x.z, x.z, c2[2]); c2[3] = fmaf(x.w, x.w, c2[3]);
+            }
+          }
         }
       }
       fence_async_smem();
       if (lp_mode) __threadfence_block();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(lead_a1_ready + buf * 8u);
+      if (want_stats) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { my_acc[64 * e] += (double)c1[e]; my_acc[64 * (4 + e)] += (double)c2[e]; }
+        if (k >= 1) stats_tile(k - 1);   // a tile behind: its epilogue ends about when this load does
+      }
+    }
+    if (want_stats) {
+      if (cnt > 0) stats_tile(cnt - 1);
+      double* rowp = s_stat + (size_t)w2 * 2 * sh.D;   // this warp's [2 * D] row: the two halves cover all D columns
+#pragma unroll 1
+      for (int i = 0; i < 16; ++i) {                   // lanes with the same lane % LPR own the same columns
+        double v = my_acc[64 * i];
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int e = i & 3, half_off = i < 8 ? sh.c_off : sh.t_off, sq = (i >> 2) & 1;
+        if (lane < LPR) rowp[sq * sh.D + half_off + 4 * lane + e] = v;
+      }
     }
   }
   // ---- teardown
   tc_fence_before();
   __syncthreads();
+  if (want_stats) {   // one [2 * D] row of doubles per CTA: the sum of the two I/O warps' rows
+    for (int i = threadIdx.x; i < 2 * sh.D; i += blockDim.x)
+      a.stat_partials[(size_t)blockIdx.x * 2 * sh.D + i] = s_stat[i] + s_stat[2 * sh.D + i];
+  }
   cluster_sync_all();
   if (warp == kEpiWarps2) tmem_dealloc2(tmem, 512);
 }

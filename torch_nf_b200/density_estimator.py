@@ -417,7 +417,7 @@ class NormFlow(DensityEstimator):
                 if self._use_tc(b, pd, z):
                     nxt = slices[i + 1][0].name if i + 1 < len(slices) else None
                     mode = config.tc_precision()
-                    fuse_stats = (nxt == "BatchNorm" and not freeze_bn and D <= 128 and mode == "bf16")
+                    fuse_stats = nxt == "BatchNorm" and not freeze_bn      # every tensor-core kernel emits them
                     res = ops.coupling_tc(z, self._packed(b, idx, n, pd, src), b.D, b.num_units, b.num_layers,
                                           b.transform_upper, TNF_FORWARD, ld=ld_acc, accum=TNF_LD_ADD,
                                           pre_scale=pend[0] if pend else None, pre_shift=pend[1] if pend else None,
