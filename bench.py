@@ -262,6 +262,10 @@ def main():
     if world > 1:
         td.init_process_group("nccl", device_id=dev)
         dist.enable()
+        # BatchNorm statistics across ranks: inside the fold kernels over NVLink peer memory (falls back to one NCCL
+        # all-reduce per BatchNorm when symmetric memory is unavailable; TNF_PEER_EXCHANGE=0 forces the fallback)
+        if os.environ.get("TNF_PEER_EXCHANGE", "1") != "0":
+            dist.enable_peer_exchange()
     tnf.set_conditioner_precision(args.precision)
     _lib.lib()
 
@@ -401,7 +405,10 @@ def main():
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "l2": "inputs_larger_than_l2 (z = 268 MB per pass)",
                        "parallelism": "dp%d over sample rows" % world, "weights": "fan-in scaled synthetic, seed 0",
-                       "noise": "device Philox4x32-10"},
+                       "noise": "device Philox4x32-10",
+                       "bn_statistics_exchange": ("none (1 rank)" if world == 1 else
+                                                  ("in-kernel over NVLink peer memory" if dist.peer_struct(0) is not None
+                                                   else "NCCL all-reduce per BatchNorm (%s)" % (dist.peer_error or "peer exchange off")))},
             "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
             "clocks": clock_info,
             "checks": {"finite": finite, "max_abs_logq_minus_logprob": consistency},

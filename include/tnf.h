@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define TNF_ABI_VERSION 2
+#define TNF_ABI_VERSION 3
 
 enum { TNF_F32 = 0, TNF_F64 = 1 };
 enum { TNF_FORWARD = 0, TNF_INVERSE = 1 };
@@ -245,7 +245,9 @@ int tnf_finish_logq(double* log_q, const void* ld_acc, const void* scal, int64_t
  *   (M, N, D) float32) injects the base noise, NULL draws it on the device (Philox stream seed / offset).
  *   `allreduce` (or NULL): data-parallel hook, called on the host after each BatchNorm's statistics kernel has been
  *   enqueued; it must enqueue, on the same stream, an in-place sum over ranks of the 2*D+1 doubles in `stats_buf`
- *   (caller-allocated device buffer, required with the hook) and return 0.
+ *   (caller-allocated device buffer, required with the hook) and return 0.  `peer` (or NULL): exchange them over
+ *   NVLink peer memory instead (tnf_peer_t below) wherever the BatchNorm is folded into a tensor-core coupling layer;
+ *   the hook stays the path of every other chain.
  * `workspace`: tnf_chain_workspace_bytes(M, N, D) bytes of device memory, caller-owned. */
 enum { TNF_BIJ_REALNVP = 0, TNF_BIJ_BATCHNORM = 1, TNF_BIJ_AFFINE = 2, TNF_BIJ_TOINTERVAL = 3, TNF_BIJ_TOSIMPLEX = 4 };
 typedef struct tnf_bijector {
@@ -262,6 +264,24 @@ typedef struct tnf_bijector {
   void* ev_stop;  /* (profiling: per-kernel device time inside a chain call); NULL = off */
 } tnf_bijector_t;
 typedef int (*tnf_allreduce_fn)(double* stats_buf, int count, void* user);
+/* Data-parallel BatchNorm statistics over NVLink peer memory (one process per GPU of one node; replaces the all-reduce
+ * hook for chains whose BatchNorms are folded into tensor-core coupling layers): every rank holds a SYMMETRIC buffer
+ * pair that all ranks can address,
+ *   stats[r]  rank r's buffer of 2 x world x TNF_PEER_SLOT doubles ([sequence parity][source rank][sum | sumsq | rows])
+ *   flags[r]  rank r's world sequence counters (unsigned 64-bit, zero before the first exchange)
+ * The fold kernel of a BatchNorm stores this rank's 2 D + 1 sums into slot [seq & 1][rank] of EVERY rank's buffer
+ * (peer stores), publishes `seq` in flags[r][rank] with a system-scope release, waits until its own counters all reached
+ * `seq`, and adds the world's contributions in rank order - bit-identical on every rank, no host round trip, no
+ * collective launch.  `seq` is the number of the call's first exchange: the caller keeps a counter that starts at 1
+ * and advances by the number of BatchNorms per call, identically on every rank. */
+#define TNF_PEER_MAX 8
+#define TNF_PEER_SLOT 520
+typedef struct tnf_peer {
+  int rank, world;
+  double* stats[TNF_PEER_MAX];
+  unsigned long long* flags[TNF_PEER_MAX];
+  unsigned long long seq;
+} tnf_peer_t;
 size_t tnf_chain_workspace_bytes(int64_t M, int64_t N, int D);
 int tnf_chain_logprob(const tnf_bijector_t* chain, int n_bij, const float* z, const float* params,
                       int64_t param_row_stride, int64_t M, int64_t N, int D, int tc_precision,
@@ -269,7 +289,7 @@ int tnf_chain_logprob(const tnf_bijector_t* chain, int n_bij, const float* z, co
 int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params,
                      int64_t param_row_stride, int64_t M, int64_t N, int D, int tc_precision,
                      const float* omega, uint64_t seed, uint64_t offset, int freeze_bn,
-                     tnf_allreduce_fn allreduce, void* allreduce_user, double* stats_buf,
+                     tnf_allreduce_fn allreduce, void* allreduce_user, double* stats_buf, const tnf_peer_t* peer,
                      float* z_out, double* log_q, void* workspace, size_t workspace_bytes,
                      tnf_stream_t stream);
 

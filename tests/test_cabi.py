@@ -17,7 +17,7 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(handle, name), "missing C-ABI symbol %s" % name
     assert set(declared) == set(_lib.PROTOTYPES), "ctypes prototypes out of sync with include/tnf.h"
     handle.tnf_abi_version.restype = ctypes.c_int
-    assert handle.tnf_abi_version() == 2
+    assert handle.tnf_abi_version() == 3
 
 
 def test_no_torch_types_in_abi():

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, precision, q):
+def _worker(rank, world, port, precision, peer, q):
     import torch.distributed as td
     import torch_nf_b200 as tnf
     import torch_nf_b200.density_estimator as de
@@ -32,6 +32,7 @@ def _worker(rank, world, port, precision, q):
     td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         dist.enable()
+        peer_on = dist.enable_peer_exchange() if peer else False
         tnf.set_conditioner_precision(precision)
         config.set_tc_min_rows(1)
         g = np.load(os.path.join(GOLDEN, "flow_c3.npz"))
@@ -45,14 +46,21 @@ def _worker(rank, world, port, precision, q):
             z, lq = nf.forward(params, hi - lo, omega=omega[:, lo:hi])
             lp = nf.log_prob(torch.tensor(g["z"][:, lo:hi]).cuda(), params)
         bn = [b for b in nf.bijectors if b.name == "BatchNorm"]
+        if peer_on:      # a second call: the sequence counters and the slot parity carry over
+            with torch.no_grad():
+                z2, lq2 = nf.forward(params, hi - lo, omega=omega[:, lo:hi])
+            assert torch.equal(z, z2) and torch.equal(lq, lq2)
         q.put((rank, lo, hi, z.cpu().numpy(), lq.cpu().numpy(), lp.cpu().numpy(),
-               [b.get_last_mean().cpu().numpy() for b in bn], [b.get_last_alpha().cpu().numpy() for b in bn]))
+               [b.get_last_mean().cpu().numpy() for b in bn], [b.get_last_alpha().cpu().numpy() for b in bn],
+               peer_on, dist.peer_error))
     finally:
         td.destroy_process_group()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_two_nccl_ranks_reproduce_the_single_process_golden(precision):
+@pytest.mark.parametrize("precision,peer", [("fp32", False), ("bf16", False), ("fp32", True), ("bf16", True)])
+def test_two_nccl_ranks_reproduce_the_single_process_golden(precision, peer):
+    """peer = True: the statistics cross the ranks inside the fold kernel over NVLink peer memory (tnf_peer_t) instead
+    of one NCCL all-reduce per BatchNorm; both ranks must then hold bit-identical statistics."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -60,13 +68,18 @@ def test_two_nccl_ranks_reproduce_the_single_process_golden(precision):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, precision, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, precision, peer, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in procs])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    if peer:
+        if not all(r[8] for r in res):
+            pytest.skip("symmetric memory unavailable: %s" % res[0][9])
+        for i in range(len(res[0][6])):     # summed in rank order on every rank: identical bits
+            assert np.array_equal(res[0][6][i], res[1][6][i]) and np.array_equal(res[0][7][i], res[1][7][i])
     g = np.load(os.path.join(GOLDEN, "flow_c3.npz"))
     z = np.concatenate([r[3] for r in res], axis=1)
     lq = np.concatenate([r[4] for r in res], axis=1)

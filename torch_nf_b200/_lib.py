@@ -67,10 +67,18 @@ class Bijector(ctypes.Structure):
 
 TNF_BIJ_REALNVP, TNF_BIJ_BATCHNORM, TNF_BIJ_AFFINE, TNF_BIJ_TOINTERVAL, TNF_BIJ_TOSIMPLEX = 0, 1, 2, 3, 4
 ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_void_p)
+TNF_PEER_MAX, TNF_PEER_SLOT = 8, 520
+
+
+class Peer(ctypes.Structure):
+    """tnf_peer_t (include/tnf.h): BatchNorm statistics exchanged over NVLink peer memory."""
+    _fields_ = [("rank", c_int), ("world", c_int), ("stats", c_void_p * TNF_PEER_MAX), ("flags", c_void_p * TNF_PEER_MAX),
+                ("seq", ctypes.c_ulonglong)]
+
 PROTOTYPES.update({
     "tnf_chain_workspace_bytes": (Z, [L, L, I]),
     "tnf_chain_logprob": (I, [P, I, P, P, L, L, L, I, I, P, P, Z, P]),
-    "tnf_chain_sample": (I, [P, I, P, L, L, L, I, I, P, U64, U64, I, ALLREDUCE_FN, P, P, P, P, P, Z, P]),
+    "tnf_chain_sample": (I, [P, I, P, L, L, L, I, I, P, U64, U64, I, ALLREDUCE_FN, P, P, P, P, P, P, Z, P]),
     "tnf_cde_supported": (I, [P, I, I, I]),
     "tnf_cde_packed_bytes": (Z, [L, I, I]),
     "tnf_cde_pack": (I, [P, I, I, P, P, I, P, I, P]),
@@ -106,7 +114,7 @@ def lib():
         fn = getattr(handle, name)   # AttributeError = missing symbol: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if handle.tnf_abi_version() != 2:
+    if handle.tnf_abi_version() != 3:
         raise RuntimeError("torch_nf_b200: ABI version mismatch")
     _LIB = handle
     return _LIB

@@ -362,8 +362,8 @@ int tnf_chain_logprob(const tnf_bijector_t* chain, int n_bij, const float* z, co
 
 int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params, int64_t param_row_stride, int64_t M,
                      int64_t N, int D, int tc_precision, const float* omega, uint64_t seed, uint64_t offset, int freeze_bn,
-                     tnf_allreduce_fn allreduce, void* allreduce_user, double* stats_buf, float* z_out, double* log_q,
-                     void* workspace, size_t workspace_bytes, tnf_stream_t stream) {
+                     tnf_allreduce_fn allreduce, void* allreduce_user, double* stats_buf, const tnf_peer_t* peer, float* z_out,
+                     double* log_q, void* workspace, size_t workspace_bytes, tnf_stream_t stream) {
   TNF_REQUIRE(chain && n_bij >= 1 && M >= 0 && N >= 0 && D >= 2, TNF_ERR_ARG, "tnf_chain_sample: bad argument");
   const int64_t rows = M * N;
   if (rows == 0) return 0;
@@ -404,6 +404,10 @@ int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params
   cudaMemsetAsync(ld_acc, 0, (size_t)rows * 4, st);
   cudaMemsetAsync(scal, 0, (size_t)Mp * 4, st);
   const bool fold = all_tc(chain, n_bij) && Mp == 1;
+  // BatchNorm statistics across ranks: inside the fold kernel over NVLink peer memory when the caller set it up and the
+  // chain folds; otherwise through the all-reduce hook
+  const bool use_peer = fold && peer != nullptr && peer->world > 1 && !freeze_bn;
+  int n_exchanged = 0;
   const int64_t Mk = Mp == 1 ? 1 : M, Nk = Mp == 1 ? rows : N;
   const float* cur = z0;
   int nb = 1, np = 0;
@@ -447,7 +451,7 @@ int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params
         if (!freeze_bn) {
           if (have_pend) { TNF_TRY(flush_pend(nullptr)); have_stats = false; }   // statistics are taken on the materialised tensor
           if (!have_stats) TNF_TRY(tnf_colstats(cur, rows, D, sums, stat_ws, TNF_F32, stream));
-          if (allreduce) {
+          if (allreduce && !use_peer) {
             int rc = allreduce(sums, 2 * D + 1, allreduce_user);
             TNF_REQUIRE(rc == 0, TNF_ERR_ARG, "tnf_chain_sample: the statistics all-reduce callback failed (%d)", rc);
           }
@@ -456,7 +460,8 @@ int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params
         const bool aff_next = !last && chain[i + 1].kind == TNF_BIJ_AFFINE;
         TNF_TRY(bn_fold_fwd_launch(sums, D, b.bn_eps, b.bn_mean, b.bn_alpha, b.bn_log_det, have_pend ? pend[np ^ 1][0] : nullptr,
                                    have_pend ? pend[np ^ 1][1] : nullptr, aff_next ? params + chain[i + 1].param_offset : nullptr,
-                                   pend[np][0], pend[np][1], scal, freeze_bn ? 0 : 1, st));
+                                   pend[np][0], pend[np][1], scal, freeze_bn ? 0 : 1, use_peer ? peer : nullptr,
+                                   use_peer ? peer->seq + (unsigned long long)(n_exchanged++) : 0ull, st));
         np ^= 1; have_pend = true;
         if (aff_next) ++i;
         continue;

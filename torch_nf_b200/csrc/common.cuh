@@ -23,9 +23,11 @@ struct FoldStep {
 constexpr int kMaxFoldSteps = 96;
 struct FoldPlan { int n, D; FoldStep s[kMaxFoldSteps]; };
 int chain_fold_inv_launch(const FoldPlan& plan, float* scal, cudaStream_t st);
-int bn_fold_fwd_launch(const double* sums, int D, double eps, float* mean, float* alpha, float* log_det, const float* ps_in,
+// peer != NULL (world > 1, finalize): the statistics are first exchanged over NVLink peer memory inside the kernel
+// (tnf_peer_t, include/tnf.h) with sequence number `seq`; `sums` then holds the world's totals
+int bn_fold_fwd_launch(double* sums, int D, double eps, float* mean, float* alpha, float* log_det, const float* ps_in,
                        const float* pb_in, const float* aff, float* ps_out, float* pb_out, float* scal, int finalize,
-                       cudaStream_t st);
+                       const tnf_peer_t* peer, unsigned long long seq, cudaStream_t st);
 
 // tnf_coupling_tc with the fused base density of the chain executor: out_lp != NULL (inverse direction, TNF_LD_ADD) makes
 // the layer emit log N(z_out) - log_det[row] - sum s - lp_scal[0] instead of z_out / log_det (coupling_tc.cu)

@@ -727,11 +727,48 @@ int chain_fold_inv_launch(const FoldPlan& plan, float* scal, cudaStream_t st) {
 
 // Sample direction, one launch per BatchNorm: statistics -> mean / alpha / log-det (bn_finalize), fold (z - mean) / alpha
 // into the pending map, scal += log-det, and - when an Affine follows - fold exp(alpha) z + shift and scal += sum alpha.
-__global__ void bn_fold_fwd_kernel(const double* __restrict__ sums, int D, double eps, float* __restrict__ mean,
+// The cross-rank exchange of the statistics (tnf_peer_t): peer stores of this rank's sums into every rank's symmetric
+// buffer, a system-scope release of the sequence number, an acquire spin on this rank's own counters, and the sum of
+// the world's contributions in rank order.  One CTA; ~2 NVLink round trips instead of a collective launch.
+struct PeerX {
+  int rank, world;
+  double* stats[TNF_PEER_MAX];
+  unsigned long long* flags[TNF_PEER_MAX];
+  unsigned long long seq;
+};
+__device__ __forceinline__ void peer_exchange(const PeerX& px, double* sums, int n) {
+  const int par = (int)(px.seq & 1ull);
+  for (int r = 0; r < px.world; ++r) {
+    double* dst = px.stats[r] + ((size_t)par * px.world + px.rank) * TNF_PEER_SLOT;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = sums[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < px.world) {
+    unsigned long long* f = px.flags[threadIdx.x] + px.rank;            // my counter in rank threadIdx.x's flag array
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(px.seq) : "memory");
+    const unsigned long long* mine = px.flags[px.rank] + threadIdx.x;   // rank threadIdx.x's counter in my array
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    } while (v < px.seq);
+  }
+  __syncthreads();
+  const double* src = px.stats[px.rank] + (size_t)par * px.world * TNF_PEER_SLOT;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double t = 0.0;
+    for (int r = 0; r < px.world; ++r) t += src[(size_t)r * TNF_PEER_SLOT + i];
+    sums[i] = t;
+  }
+  __syncthreads();
+}
+
+__global__ void bn_fold_fwd_kernel(double* __restrict__ sums, int D, double eps, float* __restrict__ mean,
                                    float* __restrict__ alpha, float* __restrict__ log_det, const float* __restrict__ ps_in,
                                    const float* __restrict__ pb_in, const float* __restrict__ aff, float* __restrict__ ps_out,
-                                   float* __restrict__ pb_out, float* __restrict__ scal, int finalize) {
+                                   float* __restrict__ pb_out, float* __restrict__ scal, int finalize, PeerX px) {
   __shared__ double red[256];
+  if (finalize && px.world > 1) peer_exchange(px, sums, 2 * D + 1);
   if (finalize) {
     const double n = sums[2 * D];
     double acc = 0.0;
@@ -778,10 +815,21 @@ __global__ void bn_fold_fwd_kernel(const double* __restrict__ sums, int D, doubl
   }
 }
 
-int bn_fold_fwd_launch(const double* sums, int D, double eps, float* mean, float* alpha, float* log_det, const float* ps_in,
+int bn_fold_fwd_launch(double* sums, int D, double eps, float* mean, float* alpha, float* log_det, const float* ps_in,
                        const float* pb_in, const float* aff, float* ps_out, float* pb_out, float* scal, int finalize,
-                       cudaStream_t st) {
-  bn_fold_fwd_kernel<<<1, 256, 0, st>>>(sums, D, eps, mean, alpha, log_det, ps_in, pb_in, aff, ps_out, pb_out, scal, finalize);
+                       const tnf_peer_t* peer, unsigned long long seq, cudaStream_t st) {
+  PeerX px{};
+  px.world = 1;
+  if (peer != nullptr && peer->world > 1 && finalize) {
+    TNF_REQUIRE(peer->world <= TNF_PEER_MAX && peer->rank >= 0 && peer->rank < peer->world && 2 * D + 1 <= TNF_PEER_SLOT && seq >= 1,
+                TNF_ERR_ARG, "bn_fold_fwd: bad peer description (world %d, rank %d, D %d)", peer->world, peer->rank, D);
+    px.rank = peer->rank; px.world = peer->world; px.seq = seq;
+    for (int r = 0; r < peer->world; ++r) {
+      TNF_REQUIRE(peer->stats[r] && peer->flags[r], TNF_ERR_ARG, "bn_fold_fwd: peer buffer of rank %d missing", r);
+      px.stats[r] = peer->stats[r]; px.flags[r] = peer->flags[r];
+    }
+  }
+  bn_fold_fwd_kernel<<<1, 256, 0, st>>>(sums, D, eps, mean, alpha, log_det, ps_in, pb_in, aff, ps_out, pb_out, scal, finalize, px);
   return check_launch("bn_fold_fwd");
 }
 

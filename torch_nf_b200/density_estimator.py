@@ -394,9 +394,14 @@ class NormFlow(DensityEstimator):
                     return 1
             cb = _lib.ALLREDUCE_FN(_hook)
         prec = ops.TC_PRECISION.get(config.tc_precision(), 0)
+        peer = None
+        if stats is not None:      # statistics over NVLink peer memory inside the fold kernels, when set up (dist.py)
+            peer = dist.peer_struct(sum(1 for b in self.bijectors if b.name == "BatchNorm"))
+        import ctypes
         rc = _lib.lib().tnf_chain_sample(arr, len(self.bijectors), pd.data_ptr(), pd.stride(0) if Mp > 1 else 0, M, N, D,
                                          prec, om_ptr, seed & (2 ** 64 - 1), 0, int(bool(freeze_bn)), cb, None,
-                                         stats.data_ptr() if stats is not None else None, z.data_ptr(), log_q.data_ptr(),
+                                         stats.data_ptr() if stats is not None else None,
+                                         ctypes.byref(peer) if peer is not None else None, z.data_ptr(), log_q.data_ptr(),
                                          ws.data_ptr(), nbytes, ops._stream())
         _lib.check(rc, "tnf_chain_sample")
         for (b, mean, alpha, ld) in bn_new:

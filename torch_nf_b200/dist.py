@@ -27,8 +27,63 @@ def enable(group=None):
 
 
 def disable():
-    global _group, _enabled
-    _group, _enabled = None, False
+    global _group, _enabled, _peer
+    _group, _enabled, _peer = None, False, None
+
+
+# ---- BatchNorm statistics over NVLink peer memory (tnf_peer_t, include/tnf.h) --------------------------------------
+_peer = None          # dict(stats, flags, stats_ptrs, flag_ptrs, seq) once enable_peer_exchange() succeeded
+peer_error = None     # why it did not (the NCCL all-reduce hook is used then)
+
+
+def enable_peer_exchange():
+    """Exchange the BatchNorm statistics of folded tensor-core chains inside the fold kernel, over NVLink peer memory,
+    instead of one NCCL all-reduce per BatchNorm: every rank allocates a symmetric buffer pair (torch symmetric memory
+    is the plumbing that maps the peers' buffers), and the kernel stores / flags / sums across ranks itself.  Returns
+    True when the buffers are mapped; False (reason in ``peer_error``) leaves the all-reduce hook in place."""
+    global _peer, peer_error
+    if not _enabled or world_size() == 1:
+        return False
+    from . import _lib
+    try:
+        import torch.distributed as td
+        import torch.distributed._symmetric_memory as sm
+        w = world_size()
+        if w > _lib.TNF_PEER_MAX:
+            raise RuntimeError("more than %d ranks" % _lib.TNF_PEER_MAX)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        grp = _group if _group is not None else td.group.WORLD
+        stats = sm.empty(2 * w * _lib.TNF_PEER_SLOT, dtype=torch.float64, device=dev)
+        flags = sm.empty(w, dtype=torch.int64, device=dev)
+        stats.zero_()
+        flags.zero_()
+        hs = sm.rendezvous(stats, grp)
+        hf = sm.rendezvous(flags, grp)
+        torch.cuda.synchronize()
+        td.barrier(group=_group)          # every rank's counters are zero before anyone can signal
+        _peer = dict(stats=stats, flags=flags, stats_ptrs=[int(p) for p in hs.buffer_ptrs],
+                     flag_ptrs=[int(p) for p in hf.buffer_ptrs], seq=1, handles=(hs, hf))
+        peer_error = None
+        return True
+    except Exception as exc:          # no symmetric memory on this build / topology: keep the NCCL hook
+        _peer, peer_error = None, "%s: %s" % (type(exc).__name__, exc)
+        return False
+
+
+def peer_struct(n_exchanges):
+    """ctypes ``tnf_peer_t`` for a call that may perform ``n_exchanges`` statistics exchanges (None when peer exchange
+    is off).  The sequence counter advances identically on every rank."""
+    if _peer is None:
+        return None
+    from . import _lib
+    p = _lib.Peer()
+    p.rank, p.world = rank(), world_size()
+    for r in range(p.world):
+        p.stats[r] = _peer["stats_ptrs"][r]
+        p.flags[r] = _peer["flag_ptrs"][r]
+    p.seq = _peer["seq"]
+    _peer["seq"] += max(1, int(n_exchanges))
+    return p
 
 
 def is_enabled():
