@@ -238,7 +238,20 @@ def main():
                     help="weak: --batch rows per GPU (default); strong: --batch rows in total, split over the ranks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-parity measurement of the same step")
+    ap.add_argument("--config", default="c3", choices=["c3", "c5"],
+                    help="c3 (default): the configuration the metric is quoted on; c5: BASELINE.json config 5 "
+                         "(D=256, 16 coupling layers, bf16 conditioner; quoted at batch 2^20 over 8 GPUs: --scaling strong)")
     args = ap.parse_args()
+    if args.config == "c5":
+        global D, STAGES, N_LAYERS, FLOP_PER_SAMPLE_LAYER, BYTES_PER_SAMPLE_LAYER, METRIC, WORKLOAD
+        D, STAGES = 256, 8
+        N_LAYERS = 2 * STAGES
+        FLOP_PER_SAMPLE_LAYER = 4 * (128 * U + (L - 1) * U * U + U * 128)      # 524 288
+        BYTES_PER_SAMPLE_LAYER = 2 * D * 4 + 8                                  # 2 056
+        METRIC = "flow log_prob+sample samples/sec at D=256,L=16 (BASELINE config 5)"
+        WORKLOAD = "C5: NormFlow(256,False,'coupling',8,2,256) sample(N)+log_prob, bf16 conditioner / fp32 log-det"
+        args.no_fp32 = True
+        args.no_cpu_baseline = True
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
@@ -335,7 +348,7 @@ def main():
         achieved = FLOP_PER_SAMPLE_LAYER * B / (avg * 1e-3) / 1e12
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "tc_traffic.json")
-        if os.path.exists(tpath):       # dram__bytes_read+write per launch from the committed `ncu --set full` capture,
+        if os.path.exists(tpath) and args.config == "c3":       # dram__bytes_read+write per launch from the committed `ncu --set full` capture,
             with open(tpath) as fh:     # valid only for the kernel source it was taken on (digest checked here)
                 tj = json.load(fh)
             ent = tj.get(kernel)
@@ -356,10 +369,11 @@ def main():
                 "kernel_share_of_step": sum(kern_ms) / (step_ms * steps),
                 "chain_roofline_frac": (world * B * steps / (step_ms * steps * 1e-3)) / world / (
                     1.0 / (2 * N_LAYERS * FLOP_PER_SAMPLE_LAYER / (pk["tflops_burst"] * 1e12))),
-                "hbm_gbs_at_algorithmic_bytes": BYTES_PER_SAMPLE_LAYER * B / (avg * 1e-3) / 1e9}
+                "hbm_gbs_at_algorithmic_bytes": BYTES_PER_SAMPLE_LAYER * B / (avg * 1e-3) / 1e9,
+                "hbm_frac_at_algorithmic_bytes": BYTES_PER_SAMPLE_LAYER * B / (avg * 1e-3) / 1e9 / pk["hbm_gbs"]}
 
     roofline = roofline_of(kern_ms, ms / args.steps, args.steps,
-                           "coupling_tc5_kernel" if args.precision == "bf16" else "coupling_tc6_kernel",
+                           "coupling_tc5_kernel" if (args.precision == "bf16" and args.config == "c3") else "coupling_tc6_kernel",
                            1 if args.precision == "bf16" else 3)
 
     # the same step at the reference's precision (fp32 parity mode), device resident, a few steps
@@ -403,7 +417,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * B, "l2": "inputs_larger_than_l2 (z = 268 MB per pass)",
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "l2": "inputs_larger_than_l2 (z = %d MB per pass)" % (B * D * 4 // 1000000), "rows_per_gpu": B,
                        "parallelism": "dp%d over sample rows" % world, "weights": "fan-in scaled synthetic, seed 0",
                        "noise": "device Philox4x32-10",
                        "bn_statistics_exchange": ("none (1 rank)" if world == 1 else
