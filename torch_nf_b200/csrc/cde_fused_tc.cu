@@ -15,6 +15,10 @@
 //     first, the main product last), tcgen05.commit -> "block ready";
 //   * warp 5 (one lane): streams the packed W blocks (both images of a block contiguous) L2 -> shared-memory ring with
 //     cp.async.bulk.
+// Measured and rejected: clusters of four CTAs consuming the W stream in lockstep, each fetching a quarter of a block
+// and multicasting it (cp.async.bulk ... .multicast::cluster, ring slots released by multicast tcgen05.commit): a
+// quarter of the L2 -> SM traffic, but 0.46 instead of 0.26 ms at C4 - the 10 KB copies and the four-way lockstep cost
+// more than the traffic saved, so the stream is latency-, not bandwidth-bound (ncu: tensor pipe 30 % of elapsed).
 // HBM traffic per sample: H + D + 1 floats.  The tensor pipe does 3 x 2 (H + 1) D_params FLOP per sample (C4: 0.55
 // MFLOP, 0.14 TFLOP per 2^18 batch); the kernel is bound by the consumer threads' instruction issue (~4 instructions
 // per parameter: tcgen05.ld share, FMA, tanh / exp of the small nets).
