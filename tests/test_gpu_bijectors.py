@@ -20,7 +20,7 @@ def close(a, b, rtol, atol):
 
 def test_native_library_loaded():
     from torch_nf_b200 import _lib
-    assert _lib.lib().tnf_abi_version() == 2
+    assert _lib.lib().tnf_abi_version() == 3
     before = _lib.launch_count()
     Affine(4).forward_and_log_det(torch.zeros(1, 2, 4), torch.zeros(1, 8))
     assert _lib.launch_count() > before
