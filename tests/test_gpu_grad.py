@@ -50,7 +50,7 @@ def test_affine_backward(dtype, tol):
     g = torch.Generator().manual_seed(1)
     D = 5
     a = bij.Affine(D)
-    for M, N in ((4, 9), (1, 300), (40, 1)):
+    for M, N in ((4, 9), (1, 300), (40, 1), (5000, 1), (4100, 3)):      # the last two: thread-per-(m, d) kernel
         params = (torch.randn(M, 2 * D, generator=g, dtype=torch.float64) * 0.5).to(dtype)
         z = torch.randn(M, N, D, generator=g, dtype=torch.float64).to(dtype)
         wz = torch.randn(M, N, D, generator=g, dtype=torch.float64).to(dtype)
@@ -156,3 +156,33 @@ def test_conditional_training_step():
         opt.step()
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("conditioner_rows", [1, 37])
+def test_chain_logprob_autograd_node(conditioner_rows):
+    """log_prob as ONE autograd node (_ChainLogProbFn): gradients w.r.t. the parameters (shared row and one row per
+    context) AND w.r.t. the samples, against oracle autograd; the per-bijector path gives the same numbers."""
+    D, N = 6, 5
+    M = conditioner_rows if conditioner_rows > 1 else 3
+    lb, ub = -2.0 * np.ones(D), 2.0 * np.ones(D)
+    nf = de.NormFlow(D, True, "coupling", 2, 2, 15, bij.ToInterval(D, lb, ub))
+    chain = O.build_chain(D, "coupling", 2, 2, 15, ("ToInterval", lb, ub))
+    rs = np.random.RandomState(1)
+    params0 = torch.tensor(synthetic_params(chain_spec(nf.bijectors), D, conditioner_rows, seed=5))
+    z0 = torch.tensor(rs.uniform(-1.8, 1.8, (M, N, D)).astype(np.float32))
+    w = torch.tensor(rs.standard_normal((M, N)).astype(np.float32))
+    with torch.no_grad():      # non-trivial remembered BatchNorm statistics
+        nf.forward(params0, 64)
+    st = [(b.get_last_mean().float().cpu(), b.get_last_alpha().float().cpu()) if b.name == "BatchNorm" else None for b in nf.bijectors]
+    p1, z1 = params0.clone().requires_grad_(True), z0.clone().requires_grad_(True)
+    assert nf._chain_grad_ok()
+    (nf.log_prob(z1, p1) * w).sum().backward()
+    p2, z2 = params0.clone().requires_grad_(True), z0.clone().requires_grad_(True)
+    (O.normflow_log_prob(chain, D, z2, p2, st) * w).sum().backward()
+    assert ((p1.grad - p2.grad).norm() / p2.grad.norm()).item() < 1e-4
+    assert ((z1.grad - z2.grad).norm() / z2.grad.norm()).item() < 1e-4
+    # the bijector-by-bijector autograd path
+    p3 = params0.clone().requires_grad_(True)
+    nf._chain_grad_ok = lambda: False
+    (nf.log_prob(z0, p3) * w).sum().backward()
+    assert ((p3.grad - p1.grad).norm() / p1.grad.norm()).item() < 1e-5

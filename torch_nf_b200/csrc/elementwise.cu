@@ -177,6 +177,42 @@ __global__ void affine_bwd_kernel(const T* __restrict__ z_in, const T* __restric
   }
 }
 
+// one sample (or a few) per parameter row - the conditional regime (N = 1): a block per m with two barriers per row is
+// ~1 ms at M = 2^18; here a thread owns (m, d) and walks its N samples, no shared memory, no barriers
+template <typename T>
+__global__ void affine_bwd_flat_kernel(const T* __restrict__ z_in, const T* __restrict__ params, int64_t pstride,
+                                       const T* __restrict__ g_y, const T* __restrict__ g_ld, T* __restrict__ g_z,
+                                       T* __restrict__ g_params, int64_t gstride, int64_t M, int64_t N, int D, int inverse) {
+  const int64_t total = M * D, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t m = e / D;
+    const int d = (int)(e - m * D);
+    const T* p = params + m * pstride;
+    const T sc = exp_cr(p[d]), sh = p[D + d];
+    const T gl = g_ld ? g_ld[m] : T(0);
+    double ga = 0.0, gb = 0.0;
+    for (int64_t n = 0; n < N; ++n) {
+      const int64_t i = (m * N + n) * D + d;
+      const T gy = g_y ? g_y[i] : T(0);
+      const T z = z_in[i];
+      if (!inverse) {
+        g_z[i] = gy * sc;
+        ga += (double)(gy * z * sc);
+        gb += (double)gy;
+      } else {
+        const T y = (z - sh) / sc;
+        const T gz = gy / sc;
+        g_z[i] = gz;
+        ga -= (double)(gy * y);
+        gb -= (double)gz;
+      }
+    }
+    T* gp = g_params + m * gstride;
+    gp[d] += (T)(ga + (double)gl);
+    gp[D + d] += (T)gb;
+  }
+}
+
 // ---------------------------------------------------------------- column statistics
 constexpr int kStatThreads = 256;
 constexpr int kStatMaxBlocks = 1184;  // 8 x 148
@@ -887,6 +923,14 @@ int tnf_affine_bwd(const void* z_in, const void* params, int64_t pstride, const 
   if (M == 0 || N == 0) return 0;
   TNF_REQUIRE(z_in && params && g_z_in && g_params, TNF_ERR_ARG, "tnf_affine_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (gstride != 0 && N <= 32 && M >= 4096) {   // many parameter rows with few samples each
+    TNF_DISPATCH(dtype, {
+      affine_bwd_flat_kernel<T><<<grid_for(M * D, 256), 256, 0, st>>>(
+          (const T*)z_in, (const T*)params, pstride, (const T*)g_z_out, (const T*)g_log_det, (T*)g_z_in, (T*)g_params,
+          gstride, M, N, D, direction == TNF_INVERSE);
+    });
+    return check_launch("tnf_affine_bwd");
+  }
   int nt = 256;
   int grid = (int)(M < (int64_t)num_sms() * 8 ? M : (int64_t)num_sms() * 8);
   TNF_DISPATCH(dtype, {
