@@ -18,6 +18,7 @@ so every rank normalises with the global batch).  Prints ONE JSON line.
           measured in the same run and reported in the `fp32` object.
 `e2e`     the same step through the public API with HOST tensors (pinned):
           parameters and samples cross PCIe inside the timed region.
+`--workload train`  BASELINE config 4 (conditional-flow training step), `--config c5`  BASELINE config 5.
 `--impl reference`  times the reference's CPU algorithm (the oracle port, torch
           CPU ops on all host cores) on a bounded sample of the same workload.
 """
@@ -241,7 +242,15 @@ def main():
     ap.add_argument("--config", default="c3", choices=["c3", "c5"],
                     help="c3 (default): the configuration the metric is quoted on; c5: BASELINE.json config 5 "
                          "(D=256, 16 coupling layers, bf16 conditioner; quoted at batch 2^20 over 8 GPUs: --scaling strong)")
+    ap.add_argument("--workload", default="sample_logprob", choices=["sample_logprob", "train"],
+                    help="train: BASELINE.json config 4, the conditional-flow training step (forward + backward + gradient "
+                         "all-reduce + Adam) of profiles/scripts/bench_train.py; prints that script's JSON line")
     args = ap.parse_args()
+    if args.workload == "train":
+        import runpy
+        sys.argv = [os.path.join(ROOT, "profiles", "scripts", "bench_train.py"), "--steps", str(args.steps), "--warmup", str(max(args.warmup, 3))]
+        runpy.run_path(sys.argv[0], run_name="__main__")
+        return
     if args.config == "c5":
         global D, STAGES, N_LAYERS, FLOP_PER_SAMPLE_LAYER, BYTES_PER_SAMPLE_LAYER, METRIC, WORKLOAD
         D, STAGES = 256, 8

@@ -1,0 +1,96 @@
+"""Out-of-bounds WRITE check without compute-sanitizer (closed on this GPU pool): every output of the tensor-core
+coupling kernels, the chain executor and the fused conditional kernel is a view inside a larger NaN-poisoned buffer;
+after the call the guard bands on both sides must be untouched.  Ragged row counts (partial tiles, idle CTAs)."""
+import numpy as np
+import pytest
+import torch
+
+import torch_nf_b200.density_estimator as de
+from torch_nf_b200 import _lib, ops
+from torch_nf_b200.bijectors import ToInterval
+from torch_nf_b200.conditional_density_estimator import ConditionalDensityEstimator, _NoParams
+from torch_nf_b200.synthetic import chain_spec, synthetic_params
+
+pytestmark = pytest.mark.gpu
+GUARD = 4096   # elements on each side
+
+
+def _guarded(n, dtype=torch.float32):
+    buf = torch.full((n + 2 * GUARD,), float("nan"), dtype=dtype, device="cuda")
+    return buf, buf[GUARD:GUARD + n]
+
+
+def _intact(buf, n):
+    return bool(torch.isnan(buf[:GUARD]).all()) and bool(torch.isnan(buf[GUARD + n:]).all())
+
+
+@pytest.mark.parametrize("precision,D", [("bf16", 64), ("fp32_tc", 64), ("bf16", 256), ("bf16", 128)])
+@pytest.mark.parametrize("N", [1, 129, 148 * 128 * 2 + 77])
+def test_coupling_tc_writes_stay_inside(precision, D, N):
+    U, L = 256, 2
+    params = torch.tensor(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=1)).cuda()
+    packed = ops.tc_pack(params[0], D, U, L, True, precision=precision)
+    z = torch.randn(1, N, D, device="cuda")
+    for direction, stats in ((ops.TNF_FORWARD, True), (ops.TNF_FORWARD, False), (ops.TNF_INVERSE, False)):
+        zbuf, zout = _guarded(N * D)
+        lbuf, ld = _guarded(N)
+        ld.zero_()
+        res = ops.coupling_tc(z, packed, D, U, L, True, direction, ld=ld, accum=ops.TNF_LD_ADD, out=zout.view(N, D),
+                              want_stats=stats, precision=precision)
+        torch.cuda.synchronize()
+        assert _intact(zbuf, N * D) and _intact(lbuf, N)
+        assert torch.isfinite(zout).all() and torch.isfinite(ld).all()
+        if stats:
+            assert float(res[2][2 * D]) == N
+
+
+def test_chain_and_fused_conditional_writes_stay_inside():
+    lib = _lib.lib()
+    # tensor-core chain log_prob with the fused base density: log_prob buffer and workspace guarded
+    D, stages, L, U, N = 64, 2, 2, 256, 148 * 128 + 33
+    nf = de.NormFlow(D, True, "coupling", stages, L, U)
+    pd = torch.tensor(synthetic_params(chain_spec(nf.bijectors), D, 1, seed=2)).cuda()
+    import torch_nf_b200 as tnf
+    tnf.set_conditioner_precision("bf16")
+    try:
+        z = torch.randn(1, N, D, device="cuda")
+        arr, keep, _ = nf._chain_pod(pd, z, None, sample=False)
+        nbytes = lib.tnf_chain_workspace_bytes(1, N, D)
+        wfull = torch.full((nbytes + 2 * GUARD,), 0x7F, dtype=torch.uint8, device="cuda")
+        ws = wfull[GUARD:GUARD + nbytes]
+        lbuf, lp = _guarded(N)
+        off = (-ws.data_ptr()) % 256      # the executor carves 256-byte aligned pieces
+        rc = lib.tnf_chain_logprob(arr, len(nf.bijectors), z.data_ptr(), pd.data_ptr(), 0, 1, N, D, ops.TC_PRECISION["bf16"],
+                                   lp.data_ptr(), ws.data_ptr() + off, nbytes - off, ops._stream())
+        if rc != 0:      # the shifted workspace is a few bytes short of the documented size: retry unshifted
+            _lib.check(lib.tnf_chain_logprob(arr, len(nf.bijectors), z.data_ptr(), pd.data_ptr(), 0, 1, N, D,
+                                             ops.TC_PRECISION["bf16"], lp.data_ptr(), ws.data_ptr(), nbytes, ops._stream()), "chain")
+        torch.cuda.synchronize()
+        assert _intact(lbuf, N) and torch.isfinite(lp).all()
+        assert bool((wfull[:GUARD] == 0x7F).all()) and bool((wfull[GUARD + nbytes:] == 0x7F).all())
+    finally:
+        tnf.set_conditioner_precision("fp32")
+    # fused conditional log-density, both producers, ragged M
+    Dc, M = 6, 148 * 128 + 5
+    nfc = de.NormFlow(Dc, True, "coupling", 1, 2, 15, ToInterval(Dc, [-2.0] * Dc, [2.0] * Dc))
+    cde = ConditionalDensityEstimator(nfc, 2, [64, 64]).cuda()
+    x = torch.randn(M, 2, device="cuda")
+    zc = torch.rand(M, 1, Dc, device="cuda") * 3.6 - 1.8
+    arr, keep, _ = nfc._chain_pod(_NoParams(x.device, M), de._Rows(M, 0, torch.float32), None, sample=False)
+    last = cde.param_net[-1]
+    H = last.in_features
+    with torch.no_grad():
+        h = cde.param_net[:-1](x).contiguous()
+    for variant in (0, 1):
+        pbytes = lib.tnf_cde_packed_bytes(nfc.D_params, H, variant)
+        pfull = torch.full((pbytes + 2 * GUARD,), 0x7F, dtype=torch.uint8, device="cuda")
+        packed = pfull[GUARD:GUARD + pbytes]
+        assert packed.data_ptr() % 16 == 0
+        _lib.check(lib.tnf_cde_pack(arr, len(nfc.bijectors), Dc, last.weight.data_ptr(), last.bias.data_ptr(), H,
+                                    packed.data_ptr(), variant, ops._stream()), "pack")
+        lbuf, lp = _guarded(M)
+        _lib.check(lib.tnf_cde_logprob(arr, len(nfc.bijectors), Dc, h.data_ptr(), H, packed.data_ptr(), zc.data_ptr(), M,
+                                       lp.data_ptr(), variant, ops._stream()), "lp")
+        torch.cuda.synchronize()
+        assert _intact(lbuf, M) and torch.isfinite(lp).all()
+        assert bool((pfull[:GUARD] == 0x7F).all()) and bool((pfull[GUARD + pbytes:] == 0x7F).all())
