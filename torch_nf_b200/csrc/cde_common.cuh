@@ -208,7 +208,7 @@ bool shape_ok(int D, int U, int L, int stages);
 size_t tc_packed_bytes(int64_t D_params, int H);
 int tc_pack(const ChainDesc& c, int D, int U, const float* weight, const float* bias, int H, void* packed, cudaStream_t st);
 int tc_logprob(const ChainDesc& c, int D, int U, const float* h, int H, const void* packed, const float* z, int64_t M,
-               float* log_prob, cudaStream_t st);
+               float* log_prob, int dbgbits, cudaStream_t st);
 
 }  // namespace cde
 }  // namespace tnf

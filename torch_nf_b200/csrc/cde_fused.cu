@@ -195,7 +195,7 @@ int tnf_cde_logprob(const tnf_bijector_t* chain, int n_bij, int D, const float* 
     TNF_REQUIRE(chain[i].kind != TNF_BIJ_BATCHNORM || (chain[i].bn_mean && chain[i].bn_alpha && chain[i].bn_log_det), TNF_ERR_ARG,
                 "tnf_cde_logprob: BatchNorm state missing");
   TNF_REQUIRE(!sup || c.ti_consts, TNF_ERR_ARG, "tnf_cde_logprob: ToInterval constants missing");
-  if (variant == TNF_CDE_TC) return cde::tc_logprob(c, D, U, h, H, packed, z, M, log_prob, (cudaStream_t)stream);
+  if ((variant & 15) == TNF_CDE_TC) return cde::tc_logprob(c, D, U, h, H, packed, z, M, log_prob, variant >> 8, (cudaStream_t)stream);
   const size_t smem = ((size_t)cde::kRing * (H + 1) * cde::kBlockP + (size_t)H * (cde::kThreads + 1)) * sizeof(float);
   TNF_REQUIRE(smem <= 227 * 1024, TNF_ERR_UNSUPPORTED, "tnf_cde_logprob: H = %d needs %zu B shared memory", H, smem);
   const int64_t n_tiles = (M + cde::kThreads - 1) / cde::kThreads;
