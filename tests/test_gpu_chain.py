@@ -40,7 +40,16 @@ def test_small_chain_is_one_launch(D, stages, L, U, N):
     params = T(synthetic_params(chain_spec(nf.bijectors), D, 1, seed=2)).cuda()
     omega = np.random.RandomState(3).standard_normal((1, N, D))
     with torch.no_grad():
-        z, lq = nf.forward(params, N, omega=omega)           # sets the BatchNorm statistics
+        # sampling with LIVE BatchNorm statistics: base density + ONE cooperative launch (grid barrier per BatchNorm)
+        ((z, lq), (z_p, lq_p), n_chain, n_plan) = _both(lambda: nf.forward(params, N, omega=omega))
+        assert n_chain == 2 and n_plan > 4, (n_chain, n_plan)
+        assert ((z - z_p).abs() / z_p.abs().clamp(min=1)).max().item() <= 1e-5
+        assert (lq - lq_p).abs().max().item() <= 2e-5 * max(1.0, float(lq_p.abs().max()))
+        bn = [b for b in nf.bijectors if b.name == "BatchNorm"]
+        m_plan = [b.get_last_mean().clone() for b in bn]
+        z, lq = nf.forward(params, N, omega=omega)           # (the chain call again: it sets the BatchNorm statistics)
+        for b, mp in zip(bn, m_plan):
+            assert (b.get_last_mean() - mp).abs().max().item() <= 1e-6
         (lp_c, lp_p, n_chain, n_plan) = _both(lambda: nf.log_prob(z, params))
         assert n_chain == 1 and n_plan > 4, (n_chain, n_plan)
         assert (lp_c - lp_p).abs().max().item() <= 2e-5 * max(1.0, float(lp_p.abs().max()))
@@ -50,6 +59,8 @@ def test_small_chain_is_one_launch(D, stages, L, U, N):
         assert (lq_c - lq_p).abs().max().item() <= 2e-5 * max(1.0, float(lq_p.abs().max()))
     chain = O.build_chain(D, "coupling", stages, L, U)
     zo, lqo, st = O.normflow_forward(chain, D, params.cpu(), omega)
+    assert ((z.cpu() - zo).abs() / zo.abs().clamp(min=1)).max().item() <= 1e-5
+    assert ((lq.cpu() - lqo).abs() / lqo.abs().clamp(min=1)).max().item() <= 1e-4
     lpo = O.normflow_log_prob(chain, D, z.cpu(), params.cpu(), st)
     assert ((lp_c.cpu() - lpo).abs() / lpo.abs().clamp(min=1)).max().item() <= 1e-4
 

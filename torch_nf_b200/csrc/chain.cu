@@ -29,6 +29,7 @@ struct SmallBij {
   const float* a;         // BatchNorm: remembered mean (D)
   const float* b;         // BatchNorm: remembered alpha (D)
   const float* ld;        // BatchNorm: remembered log-det (1)
+  float eps;              // BatchNorm (live statistics)
 };
 struct SmallChain {
   int n, D, n_params, inverse;
@@ -121,6 +122,115 @@ __global__ void __launch_bounds__(128) chain_small_kernel(SmallChain c, const fl
   }
 }
 
+// ---- the same chain in the SAMPLE direction with LIVE BatchNorm statistics (bijectors.py:401-415): one cooperative
+// launch, thread = sample (all CTAs co-resident), z in registers for the whole chain.  Each BatchNorm: per-CTA column
+// sums in float64 -> global partials -> grid barrier -> every CTA adds the partials in CTA order (identical bits
+// everywhere) and finalises mean / alpha / log-det with the arithmetic of bn_finalize_kernel; CTA 0 stores the state.
+constexpr int kLiveMaxBn = 16;
+constexpr int kLiveMaxGrid = 2400;
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) chain_small_live_kernel(SmallChain c, const float* __restrict__ z_in,
+                                                               const float* __restrict__ params, int64_t rows,
+                                                               float* __restrict__ z_out, double* __restrict__ log_q,
+                                                               double* __restrict__ partial, unsigned int* __restrict__ counter) {
+  extern __shared__ float sp[];
+  __shared__ double s_red[4][2 * kSmallMaxD];
+  __shared__ double s_part[128];
+  __shared__ float s_mean[kSmallMaxD], s_alpha[kSmallMaxD], s_ld;
+  for (int i = threadIdx.x; i < c.n_params; i += blockDim.x) sp[i] = params[i];
+  __syncthreads();
+  const int D = c.D, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = r < rows;
+  float z[kSmallMaxD];
+  float ht[kSmallMaxU], hs[kSmallMaxU], gt[kSmallMaxU], gs[kSmallMaxU], t[kSmallMaxD], s[kSmallMaxD];
+  for (int d = 0; d < D; ++d) z[d] = valid ? z_in[r * D + d] : 0.f;
+  float ld = 0.f;
+  int n_bn = 0;
+  for (int ii = 0; ii < c.n; ++ii) {
+    const SmallBij& b = c.b[ii];
+    if (b.kind == TNF_BIJ_REALNVP) {
+      const int h = D / 2;
+      const int d_in = b.upper ? h : D - h, d_out = D - d_in;
+      const int c_off = b.upper ? 0 : h, t_off = b.upper ? h : 0;
+      small_conditioner(sp + b.poff, z + c_off, d_in, d_out, b.U, b.L, ht, hs, gt, gs, t, s);
+      for (int j = 0; j < d_out; ++j) {
+        z[t_off + j] = t[j] + z[t_off + j] * expf(s[j]);
+        ld += s[j];
+      }
+    } else if (b.kind == TNF_BIJ_BATCHNORM) {
+      for (int d = 0; d < D; ++d) {   // per-CTA column sums, float64
+        const double v = valid ? (double)z[d] : 0.0;
+        const double s1 = warp_sum(v), s2 = warp_sum(v * v);
+        if (lane == 0) { s_red[warp][d] = s1; s_red[warp][D + d] = s2; }
+      }
+      __syncthreads();
+      double* mine = partial + ((size_t)n_bn * gridDim.x + blockIdx.x) * 2 * D;
+      if ((int)threadIdx.x < 2 * D) mine[threadIdx.x] = ((s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + s_red[2][threadIdx.x]) + s_red[3][threadIdx.x];
+      grid_barrier(counter, (unsigned int)(n_bn + 1) * gridDim.x);
+      {   // all 128 threads add the CTAs' partials: thread = (slice, column), slices combined in slice order below
+        const int C2 = 2 * D, S = 128 / C2;
+        const double* all = partial + (size_t)n_bn * gridDim.x * C2;
+        if ((int)threadIdx.x < S * C2) {
+          const int col = threadIdx.x % C2, sl = threadIdx.x / C2;
+          double acc = 0.0;
+          for (unsigned int k = sl; k < gridDim.x; k += S) acc += __ldcg(all + (size_t)k * C2 + col);
+          s_part[threadIdx.x] = acc;
+        }
+        __syncthreads();
+      }
+      if ((int)threadIdx.x < D) {
+        const int C2 = 2 * D, S = 128 / C2;
+        double a1 = 0.0, a2 = 0.0;
+        for (int sl = 0; sl < S; ++sl) { a1 += s_part[sl * C2 + threadIdx.x]; a2 += s_part[sl * C2 + D + threadIdx.x]; }
+        const double n = (double)rows, mu = a1 / n;
+        double var = a2 / n - mu * mu;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mu;
+        s_alpha[threadIdx.x] = (float)sqrt(var + (double)b.eps);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int d = 0; d < D; ++d) acc += (double)logf(s_alpha[d]);
+        s_ld = (float)(-acc);
+      }
+      __syncthreads();
+      if (blockIdx.x == 0) {   // the remembered statistics (bijectors.py:412-415)
+        if ((int)threadIdx.x < D) { const_cast<float*>(b.a)[threadIdx.x] = s_mean[threadIdx.x]; const_cast<float*>(b.b)[threadIdx.x] = s_alpha[threadIdx.x]; }
+        if (threadIdx.x == 0) const_cast<float*>(b.ld)[0] = s_ld;
+      }
+      for (int d = 0; d < D; ++d) z[d] = (z[d] - s_mean[d]) / s_alpha[d];
+      ld += s_ld;
+      ++n_bn;
+      __syncthreads();   // s_red / s_mean are reused by the next BatchNorm
+    } else {   // Affine: [alpha(D), shift(D)]
+      const float* al = sp + b.poff;
+      for (int d = 0; d < D; ++d) {
+        z[d] = fmaf(z[d], expf(al[d]), al[D + d]);
+        ld += al[d];
+      }
+    }
+  }
+  if (valid) {
+    log_q[r] -= (double)ld;
+    for (int d = 0; d < D; ++d) z_out[r * D + d] = z[d];
+  }
+}
+
 // ---------------------------------------------------------------- executor helpers
 static bool small_chain_ok(const tnf_bijector_t* ch, int n, int D, int64_t Mp, int frozen_or_inverse) {
   if (Mp != 1 || D > kSmallMaxD || n > kSmallMaxBij || !frozen_or_inverse) return false;
@@ -151,7 +261,7 @@ static int launch_small(const tnf_bijector_t* ch, int n, int D, int inverse, con
     const tnf_bijector_t& b = ch[i];
     c.b[i].kind = b.kind; c.b[i].L = b.num_layers; c.b[i].U = b.num_units; c.b[i].upper = b.transform_upper;
     c.b[i].poff = (int)b.param_offset;
-    c.b[i].a = b.bn_mean; c.b[i].b = b.bn_alpha; c.b[i].ld = b.bn_log_det;
+    c.b[i].a = b.bn_mean; c.b[i].b = b.bn_alpha; c.b[i].ld = b.bn_log_det; c.b[i].eps = (float)b.bn_eps;
     int64_t end = b.param_offset;
     if (b.kind == TNF_BIJ_REALNVP) {
       const int h = D / 2, d_in = b.transform_upper ? h : D - h, d_out = D - d_in, U = b.num_units, L = b.num_layers;
@@ -171,6 +281,45 @@ static int launch_small(const tnf_bijector_t* ch, int n, int D, int inverse, con
   if (blocks > cap) blocks = cap;
   chain_small_kernel<<<(int)blocks, 128, smem, st>>>(c, z_in, params, rows, z_out, out_lp, log_q);
   return check_launch("tnf_chain (fused small-chain kernel)");
+}
+
+// cooperative launch of chain_small_live_kernel, or 1 when the batch does not fit one co-resident grid
+static int launch_small_live(const tnf_bijector_t* ch, int n, int D, const float* z_in, const float* params, int64_t rows,
+                             float* z_out, double* log_q, double* partial, unsigned int* counter, cudaStream_t st) {
+  int n_bn = 0;
+  for (int i = 0; i < n; ++i) n_bn += ch[i].kind == TNF_BIJ_BATCHNORM;
+  const int64_t grid = (rows + 127) / 128;
+  if (n_bn > kLiveMaxBn || grid > kLiveMaxGrid) return 1;
+  SmallChain c;
+  c.n = n; c.D = D; c.inverse = 0; c.n_params = 0;
+  for (int i = 0; i < n; ++i) {
+    const tnf_bijector_t& b = ch[i];
+    c.b[i].kind = b.kind; c.b[i].L = b.num_layers; c.b[i].U = b.num_units; c.b[i].upper = b.transform_upper;
+    c.b[i].poff = (int)b.param_offset;
+    c.b[i].a = b.bn_mean; c.b[i].b = b.bn_alpha; c.b[i].ld = b.bn_log_det; c.b[i].eps = (float)b.bn_eps;
+    int64_t end = b.param_offset;
+    if (b.kind == TNF_BIJ_REALNVP) {
+      const int h = D / 2, d_in = b.transform_upper ? h : D - h, d_out = D - d_in, U = b.num_units, L = b.num_layers;
+      end += 2 * ((int64_t)d_in * U + (int64_t)d_out * U + d_out + U + (int64_t)(L - 1) * (U + 1) * U);
+    } else if (b.kind == TNF_BIJ_AFFINE) {
+      end += 2 * D;
+    }
+    if (end > c.n_params) c.n_params = (int)end;
+  }
+  const size_t smem = (size_t)c.n_params * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(chain_small_live_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("tnf_chain: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_small_live_kernel, 128, smem) != cudaSuccess ||
+      grid > (int64_t)per_sm * num_sms())
+    return 1;
+  cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+  void* args[] = {(void*)&c, (void*)&z_in, (void*)&params, (void*)&rows, (void*)&z_out, (void*)&log_q, (void*)&partial, (void*)&counter};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)chain_small_live_kernel, dim3((unsigned)grid), dim3(128), args, smem, st);
+  if (e != cudaSuccess) { cudaGetLastError(); return 1; }   // not launchable cooperatively: the per-bijector path
+  return check_launch("tnf_chain (fused small-chain kernel, live statistics)");
 }
 
 struct Ws {   // carve the caller's workspace
@@ -206,7 +355,8 @@ size_t tnf_chain_workspace_bytes(int64_t M, int64_t N, int D) {
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   return 2 * al(rows * (size_t)(D + 1) * 4) + al(rows * 4) + al((size_t)M * 4) + 4 * al((size_t)D * 4) +
          al((size_t)(2 * D + 1) * 8) + al(tnf_colstats_workspace_bytes(D)) + 3 * al((size_t)D * 4) +
-         2 * (size_t)kMaxFoldSteps * al((size_t)D * 4) + 1024;
+         2 * (size_t)kMaxFoldSteps * al((size_t)D * 4) +
+         (D <= kSmallMaxD ? al((size_t)kLiveMaxBn * kLiveMaxGrid * 2 * (size_t)D * 8) + 256 : 0) + 1024;
 }
 
 int tnf_chain_logprob(const tnf_bijector_t* chain, int n_bij, const float* z, const float* params,
@@ -400,6 +550,15 @@ int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params
   }
   if (small_chain_ok(chain, n_bij, D, Mp, freeze_bn))
     return launch_small(chain, n_bij, D, 0, z0, params, rows, z_out, nullptr, log_q, st);
+  if (!freeze_bn && allreduce == nullptr && (peer == nullptr || peer->world <= 1) && small_chain_ok(chain, n_bij, D, Mp, 1)) {
+    // live BatchNorm statistics, one rank: ONE cooperative launch when the batch fits a co-resident grid
+    double* partial = (double*)ws.take((size_t)kLiveMaxBn * kLiveMaxGrid * 2 * (size_t)D * 8);
+    unsigned int* counter = (unsigned int*)ws.take(256);
+    if (partial && counter) {
+      int rc = launch_small_live(chain, n_bij, D, z0, params, rows, z_out, log_q, partial, counter, st);
+      if (rc != 1) return rc;
+    }
+  }
 
   cudaMemsetAsync(ld_acc, 0, (size_t)rows * 4, st);
   cudaMemsetAsync(scal, 0, (size_t)Mp * 4, st);
