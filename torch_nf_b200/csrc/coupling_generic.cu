@@ -36,6 +36,14 @@ struct CouplingShape {
   }
 };
 
+// 4- / 8-byte asynchronous global -> shared copies: the whole parameter row of a context is requested at once (one
+// memory latency) instead of ~K dependent loads per layer and thread
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* smem, const T* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "n"((int)sizeof(T)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <typename T>
 struct CouplingArgs {
   const T* z_in; T* z_out; T* log_det; const T* params;
@@ -43,6 +51,8 @@ struct CouplingArgs {
   int D, U, L, upper, inverse, accum, RB;
   const float* mask;   // MAF: flat 0/1 mask in the parameter-row layout (NULL = RealNVP)
   int passes;          // MAF forward: D-1 fixed-point passes (reference bijectors.py:751-756); else 1
+  int stage_params;    // > 0: per-row weights (regime B), one CTA per row: the row's `stage_params` parameters are copied to
+                       // shared memory with cp.async first (one latency for the whole row)
 };
 
 // y[r][j] = act(sum_k in[r][k] W[k][j] + b[j]) for both nets; rows 0..RB-1 (RB % RT == 0)
@@ -89,12 +99,18 @@ __global__ void coupling_generic_kernel(CouplingArgs<T> a) {
   T* bufB = bufA + (size_t)2 * RB * sh.W;      // [2][RB][W]
   T* zt = bufB + (size_t)2 * RB * sh.W;        // [RB][D]
   T* ut = zt + (size_t)RB * D;                 // [RB][D]  MAF forward: the fixed input u
+  T* prow = ut + (size_t)RB * D;               // [stage_params]  this row's parameters (regime B)
 
   const int64_t tiles_per_m = (a.N + RB - 1) / RB;
   const int64_t m = blockIdx.x / tiles_per_m;
   const int64_t n0 = (blockIdx.x % tiles_per_m) * RB;
   const int rows = (int)((a.N - n0) < RB ? (a.N - n0) : RB);
   const T* p0 = a.params + m * a.pstride;
+  if (a.stage_params > 0) {
+    for (int i = threadIdx.x; i < a.stage_params; i += blockDim.x) cp_async_elem(prow + i, p0 + i);
+    cp_async_wait_all();
+    p0 = prow;      // visible to the other threads after the barrier that follows the z tile load
+  }
   const T* zin = a.z_in + (m * a.N + n0) * D;
   T* zout = a.z_out + (m * a.N + n0) * D;
 
@@ -372,9 +388,13 @@ static int launch_fwd(const void* z_in, void* z_out, void* log_det, const void* 
   int RB = pick_rb<T>(N, per_row, 0, budget);
   TNF_REQUIRE(per_row * RB <= budget, TNF_ERR_UNSUPPORTED, "tnf_coupling: shape needs %zu B smem", per_row * RB);
   size_t smem = per_row * RB;
+  // regime B with one CTA per parameter row and a small net: stage the row in shared memory
+  const int64_t np = sh.num_params();
+  const int stage = (pstride != 0 && M > 1 && mask == nullptr && (N + RB - 1) / RB == 1 && np * (int64_t)sizeof(T) <= 6 * 1024) ? (int)np : 0;
+  smem += (size_t)stage * sizeof(T);
   CouplingArgs<T> a{(const T*)z_in, (T*)z_out, (T*)log_det, (const T*)params, pstride, M, N,
                     D, U, L, upper, direction == TNF_INVERSE, accum, RB, mask,
-                    (mask != nullptr && direction != TNF_INVERSE) ? (D - 1 > 0 ? D - 1 : 1) : 1};
+                    (mask != nullptr && direction != TNF_INVERSE) ? (D - 1 > 0 ? D - 1 : 1) : 1, stage};
   int64_t tiles = M * ((N + RB - 1) / RB);
   TNF_REQUIRE(tiles < (int64_t)1 << 31, TNF_ERR_UNSUPPORTED, "tnf_coupling: too many tiles");
   int nt = 2 * sh.W;
@@ -404,6 +424,8 @@ static int launch_bwd(const void* z_in, const void* params, int64_t pstride, con
   size_t smem = per_row * RB;
   int64_t tiles_per_m = (N + RB - 1) / RB;
   int atomic_params = (gstride == 0 && M * tiles_per_m > 1) || tiles_per_m > 1;
+  // (staging the parameter and gradient rows in shared memory, as the forward does, was measured slower here: 12.96
+  // against 12.33 ms per C4 training step)
   CouplingBwdArgs<T> a{(const T*)z_in, (const T*)params, (const T*)g_y, (const T*)g_ld, (T*)g_z, (T*)g_params,
                        pstride, gstride, M, N, D, U, L, upper, direction == TNF_INVERSE, RB, atomic_params, mask};
   int64_t tiles = M * tiles_per_m;
