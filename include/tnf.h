@@ -72,6 +72,15 @@ int tnf_coupling_bwd(const void* z_in, const void* params, int64_t param_row_str
                      int64_t g_param_row_stride, int64_t M, int64_t N, int D, int U, int L,
                      int transform_upper, int direction, int dtype, tnf_stream_t stream);
 
+/* The same backward for the conditional regime (one parameter row per m, N <= 32 samples per row): every element of the
+ * row's slice of g_params is WRITTEN exactly once instead of accumulated - the caller need not zero-fill the (M,
+ * D_params) gradient matrix and the kernel does not read it.  TNF_ERR_UNSUPPORTED when rows share parameters or a row
+ * spans several tiles (the caller then zero-fills and uses tnf_coupling_bwd). */
+int tnf_coupling_bwd_overwrite(const void* z_in, const void* params, int64_t param_row_stride,
+                               const void* g_z_out, const void* g_log_det, void* g_z_in, void* g_params,
+                               int64_t g_param_row_stride, int64_t M, int64_t N, int D, int U, int L,
+                               int transform_upper, int direction, int dtype, tnf_stream_t stream);
+
 /* ---- MAF: replaces MAF.forward_and_log_det / inverse_and_log_det (bijectors.py:742-796).
  * params row = per layer [W_mu (K*J), W_alpha (K*J)], no biases (:698-738); `mask` = the binary masks
  * Ms (:663-696) flattened in the same layout (each layer's mask twice), D_params floats, shared by all m.

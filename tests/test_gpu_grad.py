@@ -169,6 +169,8 @@ def test_chain_logprob_autograd_node(conditioner_rows):
     chain = O.build_chain(D, "coupling", 2, 2, 15, ("ToInterval", lb, ub))
     rs = np.random.RandomState(1)
     params0 = torch.tensor(synthetic_params(chain_spec(nf.bijectors), D, conditioner_rows, seed=5))
+    if conditioner_rows > 1:      # trailing extra columns are legal and ignored (tests/test_bijectors.py:89-93): zero gradient
+        params0 = torch.cat([params0, torch.tensor(rs.standard_normal((conditioner_rows, 3)).astype(np.float32))], dim=1)
     z0 = torch.tensor(rs.uniform(-1.8, 1.8, (M, N, D)).astype(np.float32))
     w = torch.tensor(rs.standard_normal((M, N)).astype(np.float32))
     with torch.no_grad():      # non-trivial remembered BatchNorm statistics
@@ -181,6 +183,8 @@ def test_chain_logprob_autograd_node(conditioner_rows):
     (O.normflow_log_prob(chain, D, z2, p2, st) * w).sum().backward()
     assert ((p1.grad - p2.grad).norm() / p2.grad.norm()).item() < 1e-4
     assert ((z1.grad - z2.grad).norm() / z2.grad.norm()).item() < 1e-4
+    if conditioner_rows > 1:
+        assert float(p1.grad[:, nf.D_params:].abs().max()) == 0.0 and torch.isfinite(p1.grad).all()
     # the bijector-by-bijector autograd path
     p3 = params0.clone().requires_grad_(True)
     nf._chain_grad_ok = lambda: False

@@ -26,6 +26,7 @@ PROTOTYPES = {
     "tnf_launch_count": (L, []),
     "tnf_coupling": (I, [P, P, P, P, L, L, L, I, I, I, I, I, I, I, P]),
     "tnf_coupling_bwd": (I, [P, P, L, P, P, P, P, L, L, L, I, I, I, I, I, I, P]),
+    "tnf_coupling_bwd_overwrite": (I, [P, P, L, P, P, P, P, L, L, L, I, I, I, I, I, I, P]),
     "tnf_maf": (I, [P, P, P, P, L, P, L, L, I, I, I, I, I, I, P]),
     "tnf_maf_bwd": (I, [P, P, L, P, P, P, P, P, L, L, L, I, I, I, I, I, P]),
     "tnf_tc_supported": (I, [I, I, I, I]),

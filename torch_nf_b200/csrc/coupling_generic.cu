@@ -181,9 +181,12 @@ struct CouplingBwdArgs {
   const float* mask;   // MAF (inverse direction only); NULL = RealNVP
 };
 
+// mode 0: accumulate (read-modify-write), 1: atomic accumulate (several CTAs share the row), 2: plain store (this CTA
+// is the only writer of the row and writes every element exactly once: no zero-fill by the caller, no load)
 template <typename T>
-__device__ __forceinline__ void grad_add(T* addr, T v, int use_atomic) {
-  if (use_atomic) atomicAdd(addr, v);
+__device__ __forceinline__ void grad_add(T* addr, T v, int mode) {
+  if (mode == 1) atomicAdd(addr, v);
+  else if (mode == 2) *addr = v;
   else *addr += v;
 }
 
@@ -415,7 +418,7 @@ static int launch_fwd(const void* z_in, void* z_out, void* log_det, const void* 
 template <typename T>
 static int launch_bwd(const void* z_in, const void* params, int64_t pstride, const void* g_y, const void* g_ld,
                       void* g_z, void* g_params, int64_t gstride, int64_t M, int64_t N, int D, int U, int L,
-                      int upper, int direction, cudaStream_t st, const float* mask = nullptr) {
+                      int upper, int direction, cudaStream_t st, const float* mask = nullptr, bool overwrite = false) {
   CouplingShape sh(D, U, L, upper, mask != nullptr);
   const size_t budget = 200 * 1024;
   size_t per_row = ((size_t)2 * D + (size_t)2 * L * U + (size_t)4 * sh.W + sh.d_in) * sizeof(T);
@@ -424,6 +427,11 @@ static int launch_bwd(const void* z_in, const void* params, int64_t pstride, con
   size_t smem = per_row * RB;
   int64_t tiles_per_m = (N + RB - 1) / RB;
   int atomic_params = (gstride == 0 && M * tiles_per_m > 1) || tiles_per_m > 1;
+  if (overwrite) {
+    TNF_REQUIRE(!atomic_params && gstride != 0, TNF_ERR_UNSUPPORTED,
+                "tnf_coupling_bwd_overwrite: needs one parameter row per m and one tile per row (N <= 32)");
+    atomic_params = 2;
+  }
   // (staging the parameter and gradient rows in shared memory, as the forward does, was measured slower here: 12.96
   // against 12.33 ms per C4 training step)
   CouplingBwdArgs<T> a{(const T*)z_in, (const T*)params, (const T*)g_y, (const T*)g_ld, (T*)g_z, (T*)g_params,
@@ -472,6 +480,18 @@ int tnf_coupling_bwd(const void* z_in, const void* params, int64_t pstride, cons
   TNF_REQUIRE(z_in && params && g_z_in && g_params, TNF_ERR_ARG, "tnf_coupling_bwd: null pointer");
   TNF_DISPATCH(dtype, return launch_bwd<T>(z_in, params, pstride, g_z_out, g_log_det, g_z_in, g_params, gstride, M, N,
                                            D, U, L, transform_upper != 0, direction, (cudaStream_t)stream));
+  return 0;
+}
+
+int tnf_coupling_bwd_overwrite(const void* z_in, const void* params, int64_t pstride, const void* g_z_out,
+                               const void* g_log_det, void* g_z_in, void* g_params, int64_t gstride, int64_t M, int64_t N,
+                               int D, int U, int L, int transform_upper, int direction, int dtype, tnf_stream_t stream) {
+  int rc = validate("tnf_coupling_bwd_overwrite", M, N, D, U, L);
+  if (rc) return rc;
+  if (M == 0 || N == 0) return 0;
+  TNF_REQUIRE(z_in && params && g_z_in && g_params, TNF_ERR_ARG, "tnf_coupling_bwd_overwrite: null pointer");
+  TNF_DISPATCH(dtype, return launch_bwd<T>(z_in, params, pstride, g_z_out, g_log_det, g_z_in, g_params, gstride, M, N,
+                                           D, U, L, transform_upper != 0, direction, (cudaStream_t)stream, nullptr, true));
   return 0;
 }
 

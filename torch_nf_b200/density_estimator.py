@@ -703,7 +703,12 @@ class _ChainLogProbFn(torch.autograd.Function):
         Mp = pd.shape[0]
         g_lp = g_lp.contiguous()
         pdd = pd.detach()
-        g_params = torch.zeros(pd.shape, dtype=pd.dtype, device=pd.device)
+        # one row per context: the coupling backward WRITES its columns (no zero-fill, no read-modify-write of the
+        # (M, D_params) matrix); otherwise a zero-filled buffer that the kernels accumulate into
+        ow = Mp == M and M > 1 and N <= 32
+        g_params = (torch.empty if ow else torch.zeros)(pd.shape, dtype=pd.dtype, device=pd.device)
+        if ow and pd.shape[1] > nf.D_params:
+            g_params[:, nf.D_params:].zero_()            # trailing extra columns (legal, ignored) get a zero gradient
         g_z = ops.base_logprob_bwd(z0, g_lp)               # d log N(z0) / d z0 = -z0
         g_ld = -g_lp                                       # log_prob = log N(z0) - sum of log-dets
         g_ld_rows = g_ld.sum(dim=1) if Mp == M and M > 1 else g_ld.sum().reshape(1)     # Affine: log-det per parameter row
@@ -712,11 +717,13 @@ class _ChainLogProbFn(torch.autograd.Function):
             z_in = ins[len(slices) - 1 - k]
             if b.name == "RealNVP":
                 g_z = ops.coupling_bwd(z_in, pdd[:, idx:idx + n], g_z, g_ld, g_params[:, idx:idx + n], b.D, b.num_units,
-                                       b.num_layers, b.transform_upper, TNF_INVERSE)
+                                       b.num_layers, b.transform_upper, TNF_INVERSE, overwrite=ow)
             elif b.name == "BatchNorm":                    # remembered statistics are constants: z alpha + mean
                 _, alpha = b._state_on(z0.device, z0.dtype)
                 g_z = ops.bn_apply(g_z, torch.zeros_like(alpha), alpha, D, TNF_INVERSE)
             elif b.name == "Affine":
+                if ow:
+                    g_params[:, idx:idx + n].zero_()       # 2 D columns: the Affine backward accumulates
                 g_z = ops.affine_bwd(z_in, pdd[:, idx:idx + n], g_z, g_ld_rows, g_params[:, idx:idx + n], D, TNF_INVERSE)
             else:
                 g_z = ops.tointerval_bwd(z_in, b._consts(z0.device), g_z, g_ld, D, TNF_INVERSE)

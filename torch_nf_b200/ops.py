@@ -124,8 +124,10 @@ def coupling(z, params, D, U, L, upper, direction, ld=None, accum=TNF_LD_WRITE):
     return z_out, ld
 
 
-def coupling_bwd(z_in, params, g_z_out, g_ld, g_params, D, U, L, upper, direction):
-    """Accumulates into ``g_params`` (same row layout as ``params``); returns g_z_in."""
+def coupling_bwd(z_in, params, g_z_out, g_ld, g_params, D, U, L, upper, direction, overwrite=False):
+    """Accumulates into ``g_params`` (same row layout as ``params``); returns g_z_in.  ``overwrite``: the slice is
+    WRITTEN instead (conditional regime: one row per m, few samples per row; needs no zero-filled buffer); when the
+    shape does not allow it the slice is zeroed here and accumulated into."""
     z_in = _check3(z_in)
     M, N, _ = z_in.shape
     params, pstride = param_view(params, coupling_num_params(D, U, L, upper))
@@ -136,9 +138,13 @@ def coupling_bwd(z_in, params, g_z_out, g_ld, g_params, D, U, L, upper, directio
     g_ld = None if g_ld is None else g_ld.contiguous()
     g_z = torch.empty_like(z_in)
     Mk, Nk = (1, M * N) if Mp == 1 else (M, N)
-    rc = _lib.lib().tnf_coupling_bwd(z_in.data_ptr(), params.data_ptr(), pstride, _ptr(g_z_out), _ptr(g_ld),
-                                     g_z.data_ptr(), g_params.data_ptr(), gstride, Mk, Nk, D, U, L, int(upper),
-                                     direction, _dt(z_in), _stream())
+    args = (z_in.data_ptr(), params.data_ptr(), pstride, _ptr(g_z_out), _ptr(g_ld), g_z.data_ptr(), g_params.data_ptr(),
+            gstride, Mk, Nk, D, U, L, int(upper), direction, _dt(z_in), _stream())
+    if overwrite:
+        if Mp > 1 and Nk <= 32 and _lib.lib().tnf_coupling_bwd_overwrite(*args) == 0:
+            return g_z
+        g_params.zero_()
+    rc = _lib.lib().tnf_coupling_bwd(*args)
     _lib.check(rc, "tnf_coupling_bwd")
     return g_z
 
