@@ -179,6 +179,7 @@ struct CouplingBwdArgs {
   int64_t pstride, gstride, M, N;
   int D, U, L, upper, inverse, RB, atomic_params;
   const float* mask;   // MAF (inverse direction only); NULL = RealNVP
+  int stage_params;    // > 0 (regime B, one CTA per row): the row's parameters are copied to shared memory with cp.async
 };
 
 // mode 0: accumulate (read-modify-write), 1: atomic accumulate (several CTAs share the row), 2: plain store (this CTA
@@ -205,6 +206,7 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
   T* dl = act + (size_t)2 * L * RB * U;
   T* gz1 = dl + (size_t)4 * RB * W;  // [RB][d_in]
   T* gdir = gz1 + (size_t)RB * sh.d_in;  // [RB][D]  MAF: direct part of g_z (zt must stay intact: it is the layer-0 input)
+  T* prow = gdir + (size_t)RB * D;       // [stage_params] this row's parameters (regime B)
   auto ACT = [&](int net, int l) { return act + ((size_t)(net * L + l) * RB) * U; };  // output of layer l
   auto DL = [&](int buf, int net) { return dl + ((size_t)(buf * 2 + net) * RB) * W; };
 
@@ -214,6 +216,11 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
   const int rows = (int)((a.N - n0) < RB ? (a.N - n0) : RB);
   const T* p0 = a.params + m * a.pstride;
   T* gp0 = a.g_params + (a.gstride ? m * a.gstride : 0);
+  if (a.stage_params > 0) {   // read twice below (recompute, input deltas): one asynchronous copy of the whole row
+    for (int i = threadIdx.x; i < a.stage_params; i += blockDim.x) cp_async_elem(prow + i, p0 + i);
+    cp_async_wait_all();
+    p0 = prow;                // visible to the other threads after the barrier that follows the z tile load
+  }
   const T* zin = a.z_in + (m * a.N + n0) * D;
   const T* gy = a.g_y ? a.g_y + (m * a.N + n0) * D : nullptr;
   const T* gld = a.g_ld ? a.g_ld + m * a.N + n0 : nullptr;
@@ -432,10 +439,12 @@ static int launch_bwd(const void* z_in, const void* params, int64_t pstride, con
                 "tnf_coupling_bwd_overwrite: needs one parameter row per m and one tile per row (N <= 32)");
     atomic_params = 2;
   }
-  // (staging the parameter and gradient rows in shared memory, as the forward does, was measured slower here: 12.96
-  // against 12.33 ms per C4 training step)
+  // the parameter row staged in shared memory as in the forward (staging the GRADIENT row too was measured slower)
+  const int64_t np = sh.num_params();
+  const int stage = (pstride != 0 && M > 1 && tiles_per_m == 1 && mask == nullptr && np * (int64_t)sizeof(T) <= 6 * 1024) ? (int)np : 0;
+  smem += (size_t)stage * sizeof(T);
   CouplingBwdArgs<T> a{(const T*)z_in, (const T*)params, (const T*)g_y, (const T*)g_ld, (T*)g_z, (T*)g_params,
-                       pstride, gstride, M, N, D, U, L, upper, direction == TNF_INVERSE, RB, atomic_params, mask};
+                       pstride, gstride, M, N, D, U, L, upper, direction == TNF_INVERSE, RB, atomic_params, mask, stage};
   int64_t tiles = M * tiles_per_m;
   TNF_REQUIRE(tiles < (int64_t)1 << 31, TNF_ERR_UNSUPPORTED, "tnf_coupling_bwd: too many tiles");
   int nt = 2 * sh.W;
