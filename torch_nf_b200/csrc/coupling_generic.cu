@@ -53,6 +53,8 @@ struct CouplingArgs {
   int passes;          // MAF forward: D-1 fixed-point passes (reference bijectors.py:751-756); else 1
   int stage_params;    // > 0: per-row weights (regime B), one CTA per row: the row's `stage_params` parameters are copied to
                        // shared memory with cp.async first (one latency for the whole row)
+  int64_t n_vblocks;   // tiles in total; with WPB warps per CTA the last CTA may have idle warps
+  int vblock_smem;     // shared-memory bytes of one tile
 };
 
 // y[r][j] = act(sum_k in[r][k] W[k][j] + b[j]) for both nets; rows 0..RB-1 (RB % RT == 0)
@@ -60,9 +62,9 @@ template <typename T, int RT>
 __device__ __forceinline__ void mlp_layer(const T* __restrict__ in_t, const T* __restrict__ in_s, int in_stride,
                                           int K, int J, const T* __restrict__ Wt, const T* __restrict__ Ws,
                                           const T* __restrict__ bt, const T* __restrict__ bs, T* __restrict__ out_t,
-                                          T* __restrict__ out_s, int out_stride, int RB, bool act,
+                                          T* __restrict__ out_s, int out_stride, int RB, bool act, int vt, int vn,
                                           const float* __restrict__ mk = nullptr) {
-  for (int c = threadIdx.x; c < 2 * J; c += blockDim.x) {
+  for (int c = vt; c < 2 * J; c += vn) {
     const int net = c >= J;
     const int j = c - net * J;
     const T* W = net ? Ws : Wt;
@@ -90,9 +92,17 @@ __device__ __forceinline__ void mlp_layer(const T* __restrict__ in_t, const T* _
   }
 }
 
-template <typename T, int RT>
+// WPB > 1 (single-warp tiles, the conditional regime): WPB independent tiles per CTA, one per warp, synchronised with
+// __syncwarp - a CTA per 32-thread tile caps the SM at 32 resident warps, and this kernel lives on latency hiding
+template <typename T, int RT, int WPB>
 __global__ void coupling_generic_kernel(CouplingArgs<T> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_base[];
+  const int vt = WPB > 1 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  const int vn = WPB > 1 ? 32 : (int)blockDim.x;
+  const int64_t vb = WPB > 1 ? (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5) : (int64_t)blockIdx.x;
+  if (WPB > 1 && vb >= a.n_vblocks) return;      // whole warp: nothing below synchronises across warps
+  unsigned char* smem_raw = smem_base + (WPB > 1 ? (size_t)(threadIdx.x >> 5) * a.vblock_smem : 0);
+  auto vsync = [&]() { if (WPB > 1) __syncwarp(); else __syncthreads(); };
   const CouplingShape sh(a.D, a.U, a.L, a.upper, a.mask != nullptr);
   const int RB = a.RB, D = a.D, U = a.U;
   T* bufA = reinterpret_cast<T*>(smem_raw);    // [2][RB][W]
@@ -102,24 +112,24 @@ __global__ void coupling_generic_kernel(CouplingArgs<T> a) {
   T* prow = ut + (size_t)RB * D;               // [stage_params]  this row's parameters (regime B)
 
   const int64_t tiles_per_m = (a.N + RB - 1) / RB;
-  const int64_t m = blockIdx.x / tiles_per_m;
-  const int64_t n0 = (blockIdx.x % tiles_per_m) * RB;
+  const int64_t m = vb / tiles_per_m;
+  const int64_t n0 = (vb % tiles_per_m) * RB;
   const int rows = (int)((a.N - n0) < RB ? (a.N - n0) : RB);
   const T* p0 = a.params + m * a.pstride;
   if (a.stage_params > 0) {
-    for (int i = threadIdx.x; i < a.stage_params; i += blockDim.x) cp_async_elem(prow + i, p0 + i);
+    for (int i = vt; i < a.stage_params; i += vn) cp_async_elem(prow + i, p0 + i);
     cp_async_wait_all();
     p0 = prow;      // visible to the other threads after the barrier that follows the z tile load
   }
   const T* zin = a.z_in + (m * a.N + n0) * D;
   T* zout = a.z_out + (m * a.N + n0) * D;
 
-  for (int e = threadIdx.x; e < RB * D; e += blockDim.x) {
+  for (int e = vt; e < RB * D; e += vn) {
     const T v = e < rows * D ? zin[e] : T(0);
     zt[e] = v;
     if (sh.maf) ut[e] = v;
   }
-  __syncthreads();
+  vsync();
 
   const T* tt = nullptr;
   const T* ss = nullptr;
@@ -139,8 +149,8 @@ __global__ void coupling_generic_kernel(CouplingArgs<T> a) {
       const T* bt = sh.maf ? nullptr : Ws + (size_t)K * J;
       const T* bs = sh.maf ? nullptr : bt + J;
       mlp_layer<T, RT>(src_t, src_s, src_stride, K, J, Wt, Ws, bt, bs, cur, cur + (size_t)RB * sh.W, sh.W, RB,
-                       l < a.L, mk);
-      __syncthreads();
+                       l < a.L, vt, vn, mk);
+      vsync();
       p = sh.maf ? Ws + (size_t)K * J : bs + J;
       if (mk) mk += (size_t)2 * K * J;
       src_t = cur;
@@ -152,16 +162,16 @@ __global__ void coupling_generic_kernel(CouplingArgs<T> a) {
     // src_t / src_s now hold t and s ([RB][W], first d_out columns)
     tt = src_t;
     ss = src_s;
-    for (int e = threadIdx.x; e < rows * sh.d_out; e += blockDim.x) {
+    for (int e = vt; e < rows * sh.d_out; e += vn) {
       const int r = e / sh.d_out, j = e - r * sh.d_out;
       const T t = tt[(size_t)r * sh.W + j], sv = ss[(size_t)r * sh.W + j];
       T* zp = &zt[r * D + sh.t_off + j];
       const T z2 = (sh.maf && !a.inverse) ? ut[r * D + j] : *zp;
       *zp = a.inverse ? (z2 - t) / t_exp<T>(sv) : t + z2 * t_exp<T>(sv);
     }
-    __syncthreads();
+    vsync();
   }
-  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+  for (int r = vt; r < rows; r += vn) {
     T ld = T(0);
     for (int j = 0; j < sh.d_out; ++j) ld += ss[(size_t)r * sh.W + j];
     T* o = a.log_det + m * a.N + n0 + r;
@@ -169,7 +179,7 @@ __global__ void coupling_generic_kernel(CouplingArgs<T> a) {
     else if (a.accum == TNF_LD_ADD) *o += ld;
     else *o -= ld;
   }
-  for (int e = threadIdx.x; e < rows * D; e += blockDim.x) zout[e] = zt[e];
+  for (int e = vt; e < rows * D; e += vn) zout[e] = zt[e];
 }
 
 // ------------------------------------------------------------------ backward
@@ -180,6 +190,8 @@ struct CouplingBwdArgs {
   int D, U, L, upper, inverse, RB, atomic_params;
   const float* mask;   // MAF (inverse direction only); NULL = RealNVP
   int stage_params;    // > 0 (regime B, one CTA per row): the row's parameters are copied to shared memory with cp.async
+  int64_t n_vblocks;   // tiles in total
+  int vblock_smem;     // shared-memory bytes of one tile
 };
 
 // mode 0: accumulate (read-modify-write), 1: atomic accumulate (several CTAs share the row), 2: plain store (this CTA
@@ -195,9 +207,15 @@ __device__ __forceinline__ void grad_add(T* addr, T v, int mode) {
 //   zt   [RB][D]            layer input tile (later reused to assemble g_z)
 //   act  [2][L][RB][U]      post-tanh activations of every hidden layer, both nets
 //   dl   [2][2][RB][W]      delta ping-pong, both nets
-template <typename T, int RT>
+template <typename T, int RT, int WPB>
 __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_base[];
+  const int vt = WPB > 1 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  const int vn = WPB > 1 ? 32 : (int)blockDim.x;
+  const int64_t vb = WPB > 1 ? (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5) : (int64_t)blockIdx.x;
+  if (WPB > 1 && vb >= a.n_vblocks) return;
+  unsigned char* smem_raw = smem_base + (WPB > 1 ? (size_t)(threadIdx.x >> 5) * a.vblock_smem : 0);
+  auto vsync = [&]() { if (WPB > 1) __syncwarp(); else __syncthreads(); };
   const CouplingShape sh(a.D, a.U, a.L, a.upper, a.mask != nullptr);
   const int RB = a.RB, D = a.D, U = a.U, L = a.L, W = sh.W;
   const int nbias = sh.maf ? 0 : 1;   // MAF nets have no biases
@@ -211,13 +229,13 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
   auto DL = [&](int buf, int net) { return dl + ((size_t)(buf * 2 + net) * RB) * W; };
 
   const int64_t tiles_per_m = (a.N + RB - 1) / RB;
-  const int64_t m = blockIdx.x / tiles_per_m;
-  const int64_t n0 = (blockIdx.x % tiles_per_m) * RB;
+  const int64_t m = vb / tiles_per_m;
+  const int64_t n0 = (vb % tiles_per_m) * RB;
   const int rows = (int)((a.N - n0) < RB ? (a.N - n0) : RB);
   const T* p0 = a.params + m * a.pstride;
   T* gp0 = a.g_params + (a.gstride ? m * a.gstride : 0);
   if (a.stage_params > 0) {   // read twice below (recompute, input deltas): one asynchronous copy of the whole row
-    for (int i = threadIdx.x; i < a.stage_params; i += blockDim.x) cp_async_elem(prow + i, p0 + i);
+    for (int i = vt; i < a.stage_params; i += vn) cp_async_elem(prow + i, p0 + i);
     cp_async_wait_all();
     p0 = prow;                // visible to the other threads after the barrier that follows the z tile load
   }
@@ -226,8 +244,8 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
   const T* gld = a.g_ld ? a.g_ld + m * a.N + n0 : nullptr;
   T* gz = a.g_z + (m * a.N + n0) * D;
 
-  for (int e = threadIdx.x; e < RB * D; e += blockDim.x) zt[e] = e < rows * D ? zin[e] : T(0);
-  __syncthreads();
+  for (int e = vt; e < RB * D; e += vn) zt[e] = e < rows * D ? zin[e] : T(0);
+  vsync();
 
   // ---- recompute the conditioner, keeping every hidden activation
   {
@@ -239,22 +257,22 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
     for (int l = 0; l < L; ++l) {
       const T* Wt = p; const T* Ws = p + (size_t)K * U;
       const T* bt = nbias ? Ws + (size_t)K * U : nullptr; const T* bs = nbias ? bt + U : nullptr;
-      mlp_layer<T, RT>(src_t, src_s, src_stride, K, U, Wt, Ws, bt, bs, ACT(0, l), ACT(1, l), U, RB, true, mk);
-      __syncthreads();
+      mlp_layer<T, RT>(src_t, src_s, src_stride, K, U, Wt, Ws, bt, bs, ACT(0, l), ACT(1, l), U, RB, true, vt, vn, mk);
+      vsync();
       p = Ws + (size_t)K * U + (size_t)nbias * 2 * U;
       if (mk) mk += (size_t)2 * K * U;
       src_t = ACT(0, l); src_s = ACT(1, l); src_stride = U; K = U;
     }
     const T* Wt = p; const T* Ws = p + (size_t)K * sh.d_out;
     const T* bt = nbias ? Ws + (size_t)K * sh.d_out : nullptr; const T* bs = nbias ? bt + sh.d_out : nullptr;
-    mlp_layer<T, RT>(src_t, src_s, src_stride, K, sh.d_out, Wt, Ws, bt, bs, DL(1, 0), DL(1, 1), W, RB, false, mk);
-    __syncthreads();
+    mlp_layer<T, RT>(src_t, src_s, src_stride, K, sh.d_out, Wt, Ws, bt, bs, DL(1, 0), DL(1, 1), W, RB, false, vt, vn, mk);
+    vsync();
   }
   // ---- output deltas: DL(0,net) <- d loss / d (t, s); g_z2 into zt
   {
     const T* tt = DL(1, 0); const T* ss = DL(1, 1);
     T* dt = DL(0, 0); T* ds = DL(0, 1);
-    for (int e = threadIdx.x; e < RB * sh.d_out; e += blockDim.x) {
+    for (int e = vt; e < RB * sh.d_out; e += vn) {
       const int r = e / sh.d_out, j = e - r * sh.d_out;
       T g_t = T(0), g_s = T(0);
       if (r < rows) {
@@ -276,7 +294,7 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
       dt[(size_t)r * W + j] = g_t;
       ds[(size_t)r * W + j] = g_s;
     }
-    __syncthreads();
+    vsync();
   }
   // ---- walk the layers backwards
   int cur = 0;
@@ -296,7 +314,7 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
     const int in_stride = (l == 0) ? D : U;
     const T* dt = DL(cur, 0); const T* ds = DL(cur, 1);
     // weight / bias gradients: thread per (k, j), j fastest (coalesced)
-    for (int64_t e = threadIdx.x; e < (int64_t)2 * K * J; e += blockDim.x) {
+    for (int64_t e = vt; e < (int64_t)2 * K * J; e += vn) {
       const int net = e >= (int64_t)K * J;
       const int64_t kj = e - (int64_t)net * K * J;
       const int k = (int)(kj / J), j = (int)(kj - (int64_t)k * J);
@@ -308,7 +326,7 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
       grad_add<T>((net ? gWs : gWt) + kj, sacc, a.atomic_params);
     }
     if (nbias) {
-      for (int c = threadIdx.x; c < 2 * J; c += blockDim.x) {
+      for (int c = vt; c < 2 * J; c += vn) {
         const int net = c >= J; const int j = c - net * J;
         const T* dd = net ? ds : dt;
         T sacc = T(0);
@@ -319,7 +337,7 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
     // input deltas
     if (l > 0) {
       T* nt_ = DL(cur ^ 1, 0); T* ns_ = DL(cur ^ 1, 1);
-      for (int c = threadIdx.x; c < 2 * K; c += blockDim.x) {
+      for (int c = vt; c < 2 * K; c += vn) {
         const int net = c >= K; const int k = c - net * K;
         const T* Wn = net ? Ws : Wt; const T* dd = net ? ds : dt;
         const T* ain = net ? in_s : in_t;
@@ -342,7 +360,7 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
         }
       }
     } else {
-      for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      for (int k = vt; k < K; k += vn) {
         for (int r0 = 0; r0 < RB; r0 += RT) {
           T acc[RT];
 #pragma unroll
@@ -359,11 +377,11 @@ __global__ void coupling_generic_bwd_kernel(CouplingBwdArgs<T> a) {
         }
       }
     }
-    __syncthreads();
+    vsync();
     cur ^= 1;
   }
   // ---- assemble g_z: conditioning half = g_y1 + MLP input gradient; transformed half is in zt
-  for (int e = threadIdx.x; e < rows * D; e += blockDim.x) {
+  for (int e = vt; e < rows * D; e += vn) {
     const int r = e / D, d = e - r * D;
     T v;
     if (sh.maf) v = gdir[e] + gz1[(size_t)r * sh.d_in + d];     // every column is transformed AND conditions
@@ -404,16 +422,23 @@ static int launch_fwd(const void* z_in, void* z_out, void* log_det, const void* 
   smem += (size_t)stage * sizeof(T);
   CouplingArgs<T> a{(const T*)z_in, (T*)z_out, (T*)log_det, (const T*)params, pstride, M, N,
                     D, U, L, upper, direction == TNF_INVERSE, accum, RB, mask,
-                    (mask != nullptr && direction != TNF_INVERSE) ? (D - 1 > 0 ? D - 1 : 1) : 1, stage};
+                    (mask != nullptr && direction != TNF_INVERSE) ? (D - 1 > 0 ? D - 1 : 1) : 1, stage, 0, 0};
   int64_t tiles = M * ((N + RB - 1) / RB);
   TNF_REQUIRE(tiles < (int64_t)1 << 31, TNF_ERR_UNSUPPORTED, "tnf_coupling: too many tiles");
   int nt = 2 * sh.W;
   nt = nt < 32 ? 32 : (nt > 256 ? 256 : (nt + 31) / 32 * 32);
+  smem = (smem + 15) & ~(size_t)15;
+  a.n_vblocks = tiles; a.vblock_smem = (int)smem;
 #define TNF_LAUNCH_FWD(RT)                                                                                    \
   do {                                                                                                        \
-    cudaFuncSetAttribute(coupling_generic_kernel<T, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    coupling_generic_kernel<T, RT><<<(unsigned)tiles, nt, smem, st>>>(a);                                     \
+    cudaFuncSetAttribute(coupling_generic_kernel<T, RT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    coupling_generic_kernel<T, RT, 1><<<(unsigned)tiles, nt, smem, st>>>(a);                                  \
   } while (0)
+  if (nt == 32 && RB == 1 && tiles >= 4096 && 2 * smem <= 64 * 1024) {   // single-warp tiles: two per CTA (64 resident warps per SM)
+    cudaFuncSetAttribute(coupling_generic_kernel<T, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));
+    coupling_generic_kernel<T, 1, 2><<<(unsigned)((tiles + 1) / 2), 64, 2 * smem, st>>>(a);
+    return check_launch("tnf_coupling");
+  }
   if (RB >= 8) TNF_LAUNCH_FWD(8);
   else if (RB == 4) TNF_LAUNCH_FWD(4);
   else if (RB == 2) TNF_LAUNCH_FWD(2);
@@ -444,16 +469,23 @@ static int launch_bwd(const void* z_in, const void* params, int64_t pstride, con
   const int stage = (pstride != 0 && M > 1 && tiles_per_m == 1 && mask == nullptr && np * (int64_t)sizeof(T) <= 6 * 1024) ? (int)np : 0;
   smem += (size_t)stage * sizeof(T);
   CouplingBwdArgs<T> a{(const T*)z_in, (const T*)params, (const T*)g_y, (const T*)g_ld, (T*)g_z, (T*)g_params,
-                       pstride, gstride, M, N, D, U, L, upper, direction == TNF_INVERSE, RB, atomic_params, mask, stage};
+                       pstride, gstride, M, N, D, U, L, upper, direction == TNF_INVERSE, RB, atomic_params, mask, stage, 0, 0};
   int64_t tiles = M * tiles_per_m;
   TNF_REQUIRE(tiles < (int64_t)1 << 31, TNF_ERR_UNSUPPORTED, "tnf_coupling_bwd: too many tiles");
   int nt = 2 * sh.W;
   nt = nt < 32 ? 32 : (nt > 256 ? 256 : (nt + 31) / 32 * 32);
+  smem = (smem + 15) & ~(size_t)15;
+  a.n_vblocks = tiles; a.vblock_smem = (int)smem;
 #define TNF_LAUNCH_BWD(RT)                                                                                        \
   do {                                                                                                            \
-    cudaFuncSetAttribute(coupling_generic_bwd_kernel<T, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    coupling_generic_bwd_kernel<T, RT><<<(unsigned)tiles, nt, smem, st>>>(a);                                     \
+    cudaFuncSetAttribute(coupling_generic_bwd_kernel<T, RT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    coupling_generic_bwd_kernel<T, RT, 1><<<(unsigned)tiles, nt, smem, st>>>(a);                                  \
   } while (0)
+  if (nt == 32 && RB == 1 && tiles >= 4096 && 2 * smem <= 64 * 1024) {   // single-warp tiles: two per CTA
+    cudaFuncSetAttribute(coupling_generic_bwd_kernel<T, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));
+    coupling_generic_bwd_kernel<T, 1, 2><<<(unsigned)((tiles + 1) / 2), 64, 2 * smem, st>>>(a);
+    return check_launch("tnf_coupling_bwd");
+  }
   if (RB >= 8) TNF_LAUNCH_BWD(8);
   else if (RB == 4) TNF_LAUNCH_BWD(4);
   else if (RB == 2) TNF_LAUNCH_BWD(2);
