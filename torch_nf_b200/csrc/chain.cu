@@ -590,10 +590,11 @@ int tnf_chain_sample(const tnf_bijector_t* chain, int n_bij, const float* params
         const bool want = !last && chain[i + 1].kind == TNF_BIJ_BATCHNORM && !freeze_bn &&
                           tc_stats_fusable(D, b.num_units, b.num_layers, tc_precision);
         if (b.ev_start) cudaEventRecord((cudaEvent_t)b.ev_start, st);
-        TNF_TRY(tnf_coupling_tc(cur, o, ld_acc, b.packed, rows, D, b.num_units, b.num_layers, b.transform_upper, TNF_FORWARD,
-                                TNF_LD_ADD, have_pend ? pend[np ^ 1][0] : nullptr, have_pend ? pend[np ^ 1][1] : nullptr,
-                                want ? sums : nullptr, want ? stat_ws : nullptr, tc_precision, 0, nullptr, stream));
-        if (b.ev_stop) cudaEventRecord((cudaEvent_t)b.ev_stop, st);
+        // (the profiling stop event is recorded right after the coupling kernel, before the statistics reduce launch)
+        TNF_TRY(coupling_tc_impl(cur, o, ld_acc, b.packed, rows, D, b.num_units, b.num_layers, b.transform_upper, TNF_FORWARD,
+                                 TNF_LD_ADD, have_pend ? pend[np ^ 1][0] : nullptr, have_pend ? pend[np ^ 1][1] : nullptr,
+                                 want ? sums : nullptr, want ? stat_ws : nullptr, tc_precision, 0, nullptr, nullptr, nullptr, stream,
+                                 b.ev_stop));
         have_pend = false; have_stats = want;
       } else {
         TNF_TRY(flush_pend(nullptr));

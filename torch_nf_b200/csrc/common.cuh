@@ -37,7 +37,7 @@ bool tc_stats_fusable(int D, int U, int L, int precision);
 int coupling_tc_impl(const float* z_in, float* z_out, float* log_det, const void* packed, int64_t rows, int D, int U, int L,
                      int transform_upper, int direction, int accum, const float* pre_scale, const float* pre_shift,
                      double* col_stats, void* stats_workspace, int precision, int variant, void* debug, float* out_lp,
-                     const float* lp_scal, tnf_stream_t stream);
+                     const float* lp_scal, tnf_stream_t stream, void* ev_after_kernel = nullptr);
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

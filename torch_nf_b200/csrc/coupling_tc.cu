@@ -1580,7 +1580,7 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
                     const float* pre_shift, double* col_stats, void* stats_workspace, int precision, int variant,
                     void* debug, tnf_stream_t stream) {
   return tnf::coupling_tc_impl(z_in, z_out, log_det, packed, rows, D, U, L, transform_upper, direction, accum, pre_scale, pre_shift,
-                               col_stats, stats_workspace, precision, variant, debug, nullptr, nullptr, stream);
+                               col_stats, stats_workspace, precision, variant, debug, nullptr, nullptr, stream, nullptr);
 }
 
 }  // extern "C"
@@ -1604,7 +1604,7 @@ bool tc_lp_fusable(int D, int U, int L, int precision) {
 int coupling_tc_impl(const float* z_in, float* z_out, float* log_det, const void* packed, int64_t rows, int D, int U,
                      int L, int transform_upper, int direction, int accum, const float* pre_scale,
                      const float* pre_shift, double* col_stats, void* stats_workspace, int precision, int variant,
-                     void* debug, float* out_lp, const float* lp_scal, tnf_stream_t stream) {
+                     void* debug, float* out_lp, const float* lp_scal, tnf_stream_t stream, void* ev_after_kernel) {
   TNF_REQUIRE(out_lp == nullptr || (direction == TNF_INVERSE && accum == TNF_LD_ADD && (variant & 15) == 0 &&
                                     tc_lp_fusable(D, U, L, precision)),
               TNF_ERR_UNSUPPORTED, "tnf_coupling_tc: the fused base density needs the inverse direction, TNF_LD_ADD and the default kernel");
@@ -1637,6 +1637,7 @@ int coupling_tc_impl(const float* z_in, float* z_out, float* log_det, const void
       return (int)e6;
     }
     int rc6 = check_launch("tnf_coupling_tc");
+    if (ev_after_kernel) cudaEventRecord((cudaEvent_t)ev_after_kernel, (cudaStream_t)stream);
     if (rc6 || col_stats == nullptr) return rc6;
     return colstats_reduce_launch((const double*)stats_workspace, grid6, D, col_stats, (double)rows, (cudaStream_t)stream);
   }
@@ -1732,6 +1733,7 @@ int coupling_tc_impl(const float* z_in, float* z_out, float* log_det, const void
     return (int)e;
   }
   int rc = check_launch("tnf_coupling_tc");
+  if (ev_after_kernel) cudaEventRecord((cudaEvent_t)ev_after_kernel, st);   // the coupling kernel alone, not the statistics reduce
   if (rc || col_stats == nullptr) return rc;
   return colstats_reduce_launch((const double*)stats_workspace, stat_blocks, D, col_stats, (double)rows, st);
 }
