@@ -151,3 +151,18 @@ def test_single_process_defaults():
     assert dist.shard_range(10) == (0, 10)
     s = torch.arange(5, dtype=torch.float64)
     assert dist.allreduce_stats(s) is s
+
+
+def test_peer_struct_sequence_numbers():
+    """tnf_peer_t as the host builds it: every call gets the current sequence number and advances the counter by the
+    number of exchanges it may perform, so all ranks (which make the same calls) stay in step."""
+    from torch_nf_b200 import _lib
+    assert dist.peer_struct(3) is None                      # peer exchange not set up
+    dist._peer = dict(stats_ptrs=[0x1000, 0x2000], flag_ptrs=[0x3000, 0x4000], seq=1)
+    try:
+        p = dist.peer_struct(8)
+        assert isinstance(p, _lib.Peer) and p.seq == 1 and p.world == 1 and p.rank == 0     # no process group here
+        assert p.stats[0] == 0x1000 and p.flags[0] == 0x3000
+        assert dist.peer_struct(8).seq == 9 and dist.peer_struct(0).seq == 17 and dist.peer_struct(2).seq == 18
+    finally:
+        dist._peer = None
