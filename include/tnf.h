@@ -134,6 +134,26 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
                     double* col_stats, void* stats_workspace, int precision, int variant, void* debug,
                     tnf_stream_t stream);
 
+/* ---- backward of the tensor-core coupling layer (shared weights, bf16 conditioner, TNF_TC_BF16) ----
+ * autograd through RealNVP.forward / inverse_and_log_det (bijectors.py:145-242) for D in {64,128}, U in {128,256},
+ * L = 2 (tnf_tc_bwd_supported).  tnf_tc_bwd_pack re-lays one fp32 parameter row as the forward AND transposed bf16
+ * UMMA operand images (+ fp32 biases) the kernel streams; tnf_coupling_tc_bwd recomputes the conditioner of every
+ * 128-row tile from z_in on tcgen05, turns g_z_out (rows, D) and g_log_det (rows; gradient w.r.t. the plain sum s;
+ * either may be NULL = zero) into g_z_in (rows, D), and stores the bf16 matrices the weight gradients are made of
+ * into `workspace` (tnf_tc_bwd_workspace_bytes): per net n in {t, s}, in this order,
+ *     h1, h2 (tanh outputs), d1, d2 (gradients of the hidden pre-activations): [n][4][rows][U]
+ *     d3 (gradient of the net's output):                                      [n][rows][D/2]  after the 8 matrices.
+ * The weight gradients are then GEMMs over the batch (dW_l = a_{l-1}^T d_l, db_l = column sums of d_l, a_0 = the
+ * conditioning half of z_in), left to the caller: a plain reduction with K = rows. */
+int tnf_tc_bwd_supported(int D, int U, int L);
+size_t tnf_tc_bwd_packed_bytes(int D, int U, int L);
+size_t tnf_tc_bwd_workspace_bytes(int64_t rows, int D, int U, int L);
+int tnf_tc_bwd_pack(const float* params, void* packed, int D, int U, int L, int transform_upper,
+                    tnf_stream_t stream);
+int tnf_coupling_tc_bwd(const float* z_in, const void* packed, const float* g_z_out, const float* g_log_det,
+                        float* g_z_in, void* workspace, int64_t rows, int D, int U, int L, int transform_upper,
+                        int direction, tnf_stream_t stream);
+
 /* ---- Affine: replaces Affine.forward_and_log_det / inverse_and_log_det
  * (bijectors.py:277-315).  params row = [alpha(D), shift(D)].
  * log_det (M) = sum alpha, written when non-NULL. */

@@ -1,0 +1,111 @@
+"""Tensor-core backward of the shared-weight coupling layer (tnf_coupling_tc_bwd) against torch autograd through the
+CPU oracle, and the bf16-mode training path of a C3-like chain built on it.
+
+Stated tolerance (SURVEY 8d, bf16 conditioner): rel-L2 <= 1e-2 on the parameter gradient; the same bound is asserted
+for the sample gradient.  The oracle differentiates the fp32 reference arithmetic (oracle/flow_oracle.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow_oracle as O
+import torch_nf_b200.density_estimator as de
+from torch_nf_b200 import config, ops
+from torch_nf_b200._lib import TNF_FORWARD, TNF_INVERSE
+from torch_nf_b200.synthetic import chain_spec, synthetic_params
+
+pytestmark = pytest.mark.gpu
+
+GRAD_TOL = 1e-2
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+@pytest.mark.parametrize("D,U,upper,rows", [(64, 256, True, 1024), (64, 256, False, 1000), (64, 128, True, 300),
+                                           (128, 256, False, 640), (128, 128, True, 129)])
+@pytest.mark.parametrize("direction", [TNF_INVERSE, TNF_FORWARD])
+def test_tc_backward_layer(D, U, upper, rows, direction):
+    L = 2
+    assert ops.tc_bwd_supported(D, U, L)
+    spec = [("RealNVP", L, U, upper)]
+    params = torch.tensor(synthetic_params(spec, D, 1, seed=D + U))
+    g = torch.Generator().manual_seed(7)
+    z = torch.randn(1, rows, D, generator=g)
+    wz = torch.randn(1, rows, D, generator=g)
+    wl = torch.randn(1, rows, generator=g)
+    # oracle autograd (fp32 reference arithmetic)
+    zo, po = z.clone().requires_grad_(True), params.clone().requires_grad_(True)
+    fn = O.coupling_inverse if direction == TNF_INVERSE else O.coupling_forward
+    zz, ld = fn(zo, po, D, L, U, upper)
+    ((zz * wz).sum() + (ld * wl).sum()).backward()
+    # the kernel
+    dev = torch.device("cuda")
+    pd = params.to(dev)
+    packed = ops.tc_bwd_pack(pd[0], D, U, L, upper)
+    g_params = torch.zeros_like(pd)
+    g_z = ops.coupling_tc_bwd(z.to(dev).contiguous(), packed, wz.to(dev), wl.to(dev), g_params[0], D, U, L, upper, direction)
+    torch.cuda.synchronize()
+    rz, rp = _rel(g_z.cpu(), zo.grad), _rel(g_params.cpu(), po.grad)
+    print("D=%d U=%d upper=%d rows=%d dir=%d: rel-L2 g_z %.2e g_params %.2e" % (D, U, upper, rows, direction, rz, rp))
+    assert torch.isfinite(g_z).all() and torch.isfinite(g_params).all()
+    assert rz < GRAD_TOL and rp < GRAD_TOL, (rz, rp)
+    # per-piece check of the parameter gradient: every weight / bias block of both nets
+    off = 0
+    h = D // 2
+    for (K, J) in ((h, U), (U, U), (U, h)):
+        for n_el in (K * J, K * J, J, J):
+            a, b = g_params[0, off:off + n_el].cpu(), po.grad[0, off:off + n_el]
+            assert _rel(a, b) < 3 * GRAD_TOL, (K, J, n_el, _rel(a, b))
+            off += n_el
+
+
+def test_tc_backward_null_gradients():
+    """g_z_out = NULL and g_log_det = NULL are zeros."""
+    D, U, L, rows = 64, 256, 2, 256
+    params = torch.tensor(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=3)).cuda()
+    z = torch.randn(1, rows, D, device="cuda")
+    packed = ops.tc_bwd_pack(params[0], D, U, L, True)
+    wl = torch.randn(rows, device="cuda")
+    ga, gb = torch.zeros_like(params), torch.zeros_like(params)
+    z1 = ops.coupling_tc_bwd(z, packed, None, wl, ga[0], D, U, L, True, TNF_INVERSE)
+    z2 = ops.coupling_tc_bwd(z, packed, torch.zeros_like(z), wl, gb[0], D, U, L, True, TNF_INVERSE)
+    assert torch.equal(z1, z2) and torch.equal(ga, gb)
+    gc = torch.zeros_like(params)
+    z3 = ops.coupling_tc_bwd(z, packed, None, None, gc[0], D, U, L, True, TNF_INVERSE)
+    assert float(z3.abs().max()) == 0.0 and float(gc.abs().max()) == 0.0
+
+
+def test_c3_training_gradients_bf16():
+    """-mean log_prob of a C3-shaped flow (2 stages here) in the bf16-conditioner mode: forward and backward of every
+    coupling layer on tensor cores, against oracle autograd; several tiles per CTA and a ragged last tile."""
+    D, stages, U, N = 64, 2, 256, 148 * 128 * 2 + 77
+    old = config.conditioner_precision()
+    config.set_conditioner_precision("bf16")
+    try:
+        nf = de.NormFlow(D, False, "coupling", stages, 2, U)
+        chain = O.build_chain(D, "coupling", stages, 2, U)
+        params0 = torch.tensor(synthetic_params(chain_spec(nf.bijectors), D, 1, seed=0))
+        with torch.no_grad():
+            z, _ = nf.forward(params0, N, omega=np.random.RandomState(1).standard_normal((1, N, D)))
+        st = [(b.get_last_mean().float().cpu(), b.get_last_alpha().float().cpu()) if b.name == "BatchNorm" else None
+              for b in nf.bijectors]
+        # "data" that is NOT distributed as the model: on the model's own samples the expected score is zero, the true
+        # gradient is pure sampling noise and a relative error says nothing (measured there: 2.6e-2)
+        z = (z.detach() * 1.25 + 0.1).contiguous()
+        p1, z1 = params0.clone().requires_grad_(True), z.clone().requires_grad_(True)
+        assert all(nf._tc_train(b, p1, z1) for b in nf.bijectors if b.name == "RealNVP")
+        launches0 = de.ops._lib.launch_count()
+        nf.params = p1                      # conditioner=False: log_prob uses the flow's own parameter leaf
+        loss = -nf.log_prob(z1).mean()
+        loss.backward()
+        assert de.ops._lib.launch_count() > launches0
+        p2, z2 = params0.clone().requires_grad_(True), z.clone().requires_grad_(True)
+        loss_o = -O.normflow_log_prob(chain, D, z2, p2, st).mean()
+        loss_o.backward()
+        rp, rz = _rel(p1.grad, p2.grad), _rel(z1.grad, z2.grad)
+        print("C3-like bf16 training: loss %.5f vs %.5f, rel-L2 g_params %.2e g_z %.2e" % (loss.item(), loss_o.item(), rp, rz))
+        assert abs(loss.item() - loss_o.item()) < config.BF16_TOL_LOGP * max(1.0, abs(loss_o.item()))
+        assert rp < GRAD_TOL and rz < GRAD_TOL, (rp, rz)
+    finally:
+        config.set_conditioner_precision(old)

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "_C.so")
 STAMP = os.path.join(HERE, "_C.so.stamp")
-SOURCES = ["elementwise.cu", "coupling_generic.cu", "coupling_tc.cu", "coupling_tc4.cu", "coupling_tc5.cu", "coupling_tc6.cu", "chain.cu", "cde_fused.cu", "cde_fused_tc.cu"]
+SOURCES = ["elementwise.cu", "coupling_generic.cu", "coupling_tc.cu", "coupling_tc4.cu", "coupling_tc5.cu", "coupling_tc6.cu", "coupling_tcb.cu", "chain.cu", "cde_fused.cu", "cde_fused_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--cudart", "static",

@@ -34,6 +34,11 @@ PROTOTYPES = {
     "tnf_tc_packed_bytes": (Z, [I, I, I, I]),
     "tnf_tc_pack": (I, [P, P, I, I, I, I, I, P]),
     "tnf_coupling_tc": (I, [P, P, P, P, L, I, I, I, I, I, I, P, P, P, P, I, I, P, P]),
+    "tnf_tc_bwd_supported": (I, [I, I, I]),
+    "tnf_tc_bwd_packed_bytes": (Z, [I, I, I]),
+    "tnf_tc_bwd_workspace_bytes": (Z, [L, I, I, I]),
+    "tnf_tc_bwd_pack": (I, [P, P, I, I, I, I, P]),
+    "tnf_coupling_tc_bwd": (I, [P, P, P, P, P, P, L, I, I, I, I, I, P]),
     "tnf_affine": (I, [P, P, P, P, L, L, L, I, I, I, P]),
     "tnf_affine_bwd": (I, [P, P, L, P, P, P, P, L, L, L, I, I, I, P]),
     "tnf_colstats_workspace_bytes": (Z, [I]),

@@ -932,6 +932,26 @@ int tnf_affine_bwd(const void* z_in, const void* params, int64_t pstride, const 
     return check_launch("tnf_affine_bwd");
   }
   int nt = 256;
+  if (M == 1 && gstride == 0 && N >= 8192) {
+    // ONE shared parameter row and a large batch (regime A training): a single block would walk all N rows.  The rows
+    // are cut into pseudo parameter rows of kRows samples that all accumulate into the shared gradient row (atomics,
+    // as several m do); the remainder call adds the log-det gradient once.
+    constexpr int64_t kRows = 1024;
+    const int64_t Mf = N / kRows, tail = N - Mf * kRows;
+    const int grid_f = (int)(Mf < (int64_t)num_sms() * 8 ? Mf : (int64_t)num_sms() * 8);
+    TNF_DISPATCH(dtype, {
+      const T* gy = (const T*)g_z_out;
+      affine_bwd_kernel<T><<<grid_f, nt, 2 * nt * sizeof(double), st>>>(
+          (const T*)z_in, (const T*)params, 0, gy, (const T*)nullptr, (T*)g_z_in, (T*)g_params, 0, Mf, kRows, D,
+          direction == TNF_INVERSE);
+      const int64_t off = Mf * kRows * D;
+      affine_bwd_kernel<T><<<1, nt, 2 * nt * sizeof(double), st>>>(
+          (const T*)z_in + off, (const T*)params, 0, gy ? gy + off : gy, (const T*)g_log_det, (T*)g_z_in + off,
+          (T*)g_params, 0, 1, tail, D, direction == TNF_INVERSE);
+    });
+    count_launch();
+    return check_launch("tnf_affine_bwd");
+  }
   int grid = (int)(M < (int64_t)num_sms() * 8 ? M : (int64_t)num_sms() * 8);
   TNF_DISPATCH(dtype, {
     affine_bwd_kernel<T><<<grid, nt, 2 * nt * sizeof(double), st>>>(

@@ -251,6 +251,15 @@ class NormFlow(DensityEstimator):
                 and b.name == "RealNVP" and z.shape[0] * z.shape[1] >= config.tc_min_rows()
                 and ops.tc_supported(b.D, b.num_units, b.num_layers, mode))
 
+    def _tc_train(self, b, pd, z):
+        """The differentiable path of a coupling layer runs on tensor cores (forward ``tnf_coupling_tc``, backward
+        ``tnf_coupling_tc_bwd``) in the bf16-conditioner mode when the weights are shared and the shape is compiled;
+        in the fp32 modes training stays on the exact CUDA-core kernels."""
+        return (config.conditioner_precision() == "bf16" and pd.shape[0] == 1 and z.dtype == torch.float32
+                and z.shape[0] * z.shape[1] >= config.tc_min_rows()
+                and ops.tc_bwd_supported(b.D, b.num_units, b.num_layers)
+                and ops.tc_supported(b.D, b.num_units, b.num_layers, "bf16"))
+
     def _packed(self, b, idx, n, pd, src=None):
         """Packed tensor-core operand images of bijector ``b``'s weights (``pd[0, idx:idx+n]``).
 
@@ -677,7 +686,11 @@ class _ChainLogProbFn(torch.autograd.Function):
         cur = z.detach()
         for (b, idx, n) in reversed(nf._slices()):
             ins.append(cur)
-            if b.name == "RealNVP":
+            if b.name == "RealNVP" and nf._tc_train(b, pdd, cur):
+                # bf16-conditioner mode, shared weights: forward AND backward of the layer on tensor cores
+                cur, _ = ops.coupling_tc(cur, nf._packed(b, idx, n, pdd, src=pd), b.D, b.num_units, b.num_layers,
+                                         b.transform_upper, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD, precision="bf16")
+            elif b.name == "RealNVP":
                 cur, _ = ops.coupling(cur, pdd[:, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper, TNF_INVERSE,
                                       ld=ld_acc, accum=TNF_LD_ADD)
             elif b.name == "BatchNorm":
@@ -715,7 +728,11 @@ class _ChainLogProbFn(torch.autograd.Function):
         slices = nf._slices()                              # chain order = the reverse of the forward's execution order
         for k, (b, idx, n) in enumerate(slices):
             z_in = ins[len(slices) - 1 - k]
-            if b.name == "RealNVP":
+            if b.name == "RealNVP" and nf._tc_train(b, pdd, z_in):
+                packed_b = ops.tc_bwd_pack(pdd[0, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper)
+                g_z = ops.coupling_tc_bwd(z_in, packed_b, g_z, g_ld, g_params[0, idx:idx + n], b.D, b.num_units,
+                                          b.num_layers, b.transform_upper, TNF_INVERSE)
+            elif b.name == "RealNVP":
                 g_z = ops.coupling_bwd(z_in, pdd[:, idx:idx + n], g_z, g_ld, g_params[:, idx:idx + n], b.D, b.num_units,
                                        b.num_layers, b.transform_upper, TNF_INVERSE, overwrite=ow)
             elif b.name == "BatchNorm":                    # remembered statistics are constants: z alpha + mean

@@ -241,6 +241,83 @@ def coupling_tc(z, packed, D, U, L, upper, direction, ld=None, accum=TNF_LD_WRIT
     return z_out.view(z.shape), ld
 
 
+# ----------------------------------------------------------------- tensor-core coupling backward
+def tc_bwd_supported(D, U, L):
+    return bool(_lib.lib().tnf_tc_bwd_supported(D, U, L))
+
+
+def tc_bwd_pack(params_row, D, U, L, upper):
+    """fp32 parameter row -> forward + transposed bf16 operand images of the backward kernel."""
+    nbytes = _lib.lib().tnf_tc_bwd_packed_bytes(D, U, L)
+    if nbytes == 0:
+        raise ValueError("tensor-core backward: D=%d U=%d L=%d not supported" % (D, U, L))
+    p = params_row.reshape(-1)
+    need = coupling_num_params(D, U, L, upper)
+    if p.numel() < need:
+        raise ValueError("tc_bwd_pack: parameter row has %d values, the layer needs %d" % (p.numel(), need))
+    if p.dtype != torch.float32 or not p.is_contiguous():
+        p = p.float().contiguous()
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=p.device)
+    rc = _lib.lib().tnf_tc_bwd_pack(p.data_ptr(), packed.data_ptr(), D, U, L, int(upper), _stream())
+    _lib.check(rc, "tnf_tc_bwd_pack")
+    return packed
+
+
+TC_BWD_MAX_ROWS = 1 << 20      # rows per kernel call: bounds the bf16 workspace (4.2 KB per row at D=64, U=256)
+
+
+def _mm_f32(a_t, b):
+    """a_t^T @ b for bf16 (rows, m), (rows, n) -> (m, n) float32 (library GEMM over the batch dimension)."""
+    try:
+        return torch.mm(a_t.t(), b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return torch.mm(a_t.t(), b).float()
+
+
+def coupling_tc_bwd(z_in, packed_bwd, g_z_out, g_ld, g_params_row, D, U, L, upper, direction):
+    """Backward of the shared-weight coupling layer on tensor cores (tnf_coupling_tc_bwd).  Returns g_z_in and
+    ACCUMULATES the parameter gradient into ``g_params_row`` (flat, the layer's slice, layout of bijectors.py:224-235).
+    The data gradient and the recompute run in the CUDA kernel; the weight gradients are GEMMs over the batch
+    (K = rows) on the bf16 matrices the kernel leaves in its workspace."""
+    z2 = z_in.reshape(-1, D)
+    if z2.dtype != torch.float32 or not z2.is_contiguous():
+        raise TypeError("tensor-core coupling backward takes contiguous float32 z")
+    rows_all = z2.shape[0]
+    gz2 = None if g_z_out is None else g_z_out.reshape(-1, D).contiguous()
+    gl = None if g_ld is None else g_ld.reshape(-1).contiguous()
+    g_z = torch.empty_like(z2)
+    DH = D // 2
+    c_off = 0 if upper else DH
+    gp = g_params_row.reshape(-1)
+    # offsets of the layer's pieces in the flat row
+    o0, o1 = 0, 2 * DH * U + 2 * U
+    o2 = o1 + 2 * U * U + 2 * U
+    lay = [(o0, DH, U), (o1, U, U), (o2, U, DH)]
+    for lo in range(0, rows_all, TC_BWD_MAX_ROWS):
+        hi = min(rows_all, lo + TC_BWD_MAX_ROWS)
+        rows = hi - lo
+        nbytes = _lib.lib().tnf_tc_bwd_workspace_bytes(rows, D, U, L)
+        ws = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=z2.device)
+        rc = _lib.lib().tnf_coupling_tc_bwd(z2[lo:hi].data_ptr(), packed_bwd.data_ptr(),
+                                            0 if gz2 is None else gz2[lo:hi].data_ptr(),
+                                            0 if gl is None else gl[lo:hi].data_ptr(), g_z[lo:hi].data_ptr(),
+                                            ws.data_ptr(), rows, D, U, L, int(upper), direction, _stream())
+        _lib.check(rc, "tnf_coupling_tc_bwd")
+        mats = ws[:8 * rows * U].view(2, 4, rows, U)
+        d3 = ws[8 * rows * U:].view(2, rows, DH)
+        x = z2[lo:hi, c_off:c_off + DH].to(torch.bfloat16)
+        for net in range(2):
+            h1, h2, d1, d2 = mats[net, 0], mats[net, 1], mats[net, 2], mats[net, 3]
+            acts = (x, h1, h2)
+            deltas = (d1, d2, d3[net])
+            for l, (off, K, J) in enumerate(lay):
+                gp[off + net * K * J: off + (net + 1) * K * J] += _mm_f32(acts[l], deltas[l]).reshape(-1)
+                boff = off + 2 * K * J + net * J
+                gp[boff: boff + J] += deltas[l].sum(dim=0, dtype=torch.float32)
+        del ws
+    return g_z.view(z_in.shape)
+
+
 # ----------------------------------------------------------------- affine
 def affine(z, params, D, direction, want_ld=True):
     z = _check3(z)
