@@ -18,7 +18,8 @@ so every rank normalises with the global batch).  Prints ONE JSON line.
           measured in the same run and reported in the `fp32` object.
 `e2e`     the same step through the public API with HOST tensors (pinned):
           parameters and samples cross PCIe inside the timed region.
-`--workload train`  BASELINE config 4 (conditional-flow training step), `--config c5`  BASELINE config 5.
+`--workload train`  BASELINE config 4 (conditional-flow training step), `--workload train_c3`  the C3 flow's
+maximum-likelihood training step (tensor-core backward), `--config c5`  BASELINE config 5.
 `--impl reference`  times the reference's CPU algorithm (the oracle port, torch
           CPU ops on all host cores) on a bounded sample of the same workload.
 """
@@ -242,13 +243,16 @@ def main():
     ap.add_argument("--config", default="c3", choices=["c3", "c5"],
                     help="c3 (default): the configuration the metric is quoted on; c5: BASELINE.json config 5 "
                          "(D=256, 16 coupling layers, bf16 conditioner; quoted at batch 2^20 over 8 GPUs: --scaling strong)")
-    ap.add_argument("--workload", default="sample_logprob", choices=["sample_logprob", "train"],
+    ap.add_argument("--workload", default="sample_logprob", choices=["sample_logprob", "train", "train_c3"],
                     help="train: BASELINE.json config 4, the conditional-flow training step (forward + backward + gradient "
-                         "all-reduce + Adam) of profiles/scripts/bench_train.py; prints that script's JSON line")
+                         "all-reduce + Adam) of profiles/scripts/bench_train.py; train_c3: the maximum-likelihood training "
+                         "step of the C3 flow with the tensor-core backward (profiles/scripts/bench_train_c3.py); both print "
+                         "that script's JSON line")
     args = ap.parse_args()
-    if args.workload == "train":
+    if args.workload in ("train", "train_c3"):
         import runpy
-        sys.argv = [os.path.join(ROOT, "profiles", "scripts", "bench_train.py"), "--steps", str(args.steps), "--warmup", str(max(args.warmup, 3))]
+        script = "bench_train.py" if args.workload == "train" else "bench_train_c3.py"
+        sys.argv = [os.path.join(ROOT, "profiles", "scripts", script), "--steps", str(args.steps), "--warmup", str(max(args.warmup, 3))]
         runpy.run_path(sys.argv[0], run_name="__main__")
         return
     if args.config == "c5":

@@ -128,11 +128,37 @@ __host__ __device__ constexpr size_t smem_bytes_b() {
          sizeof(CtrlB);
 }
 
+// 256-bit global accesses (sm_100): a thread's 32-column piece of a bf16 row is two of them instead of four 128-bit
+// ones - every lane of such an instruction is in another 128-byte line (32 L1 wavefronts), so the instruction count is
+// what the LSU pipe pays for.  (Measured alternative: the pieces transposed through a per-warp shared-memory tile into
+// 8-rows-x-64-byte stores - fewer global wavefronts but as many shared-memory ones: 2.90 -> 2.62 ms, dropped for this.)
+__device__ __forceinline__ void ld256_cg(const void* p, uint32_t* r) {
+  asm volatile("ld.global.cg.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3])
                : "memory");
 }
+// D[tmem] (+)= A[tmem] . B[smem desc as two words]   (cta_group::1)
+__device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int V> struct IC { static constexpr int value = V; };
 __device__ __forceinline__ float bf_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
 
@@ -197,41 +223,47 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
     if (v_total > 0) { load_big(0); load_big(1); }
   }
 
-  // K-major SWIZZLE_NONE descriptors (tc_common.cuh): one K = 16 step reads two K groups
-  auto issue_small = [&](uint32_t d_tmem, bool a_smem, uint32_t a_tmem, bool a_strided, int K, int N) {
-    // control lane: wait for the slot, issue the job's MMAs, commit
+  // K-major SWIZZLE_NONE descriptors (tc_common.cuh): one K = 16 step reads two K groups.  The descriptors are kept as
+  // 32-bit words (only the start address in the low word moves) and the K loops are unrolled with compile-time shapes:
+  // one thread issues every MMA, its instruction count per MMA is the kernel's serial overhead.
+  const uint32_t a_dhi = (uint32_t)(make_desc(0u, kTileM) >> 32);
+  const uint32_t x_lo = (uint32_t)make_desc(smem_u32(sX), kTileM);
+  // AMODE 0: A = the conditioning-half image in shared memory; 1: tensor memory, in-place (strided) layout;
+  // 2: tensor memory, compact layout
+  auto issue_small = [&](uint32_t d_tmem, uint32_t a_tmem, auto amode_c, auto K_c, auto N_c) {
+    constexpr int AMODE = decltype(amode_c)::value, K = decltype(K_c)::value, N = decltype(N_c)::value;
     const int slot = (int)(u_use & 1);
     mbar_wait(&ct.full_s[slot], (ps >> slot) & 1u);
     ps ^= 1u << slot;
     tc_fence_after();
     const uint32_t idesc = make_idesc(N);
-    const uint32_t b_addr = smem_u32(sSmall + (size_t)slot * kSmall);
-    for (int k = 0; k < K; k += 16) {
-      const uint64_t bdesc = make_desc(b_addr + (uint32_t)(k >> 3) * (uint32_t)N * 16u, N);
-      if (a_smem) {
-        const uint64_t adesc = make_desc(smem_u32(sX) + (uint32_t)(k >> 3) * (kTileM * 16u), kTileM);
-        umma_ss(d_tmem, adesc, bdesc, idesc, k > 0 ? 1u : 0u);
+    const uint64_t bd = make_desc(smem_u32(sSmall + (size_t)slot * kSmall), N);
+    const uint32_t b_lo = (uint32_t)bd, b_hi = (uint32_t)(bd >> 32);
+#pragma unroll
+    for (int kk = 0; kk < K / 16; ++kk) {
+      if (AMODE == 0) {
+        umma_ss2(d_tmem, x_lo + (uint32_t)(kk * 2 * kTileM), a_dhi, b_lo + (uint32_t)(kk * 2 * N), b_hi, idesc, kk > 0 ? 1u : 0u);
       } else {
-        const int kk = k >> 4;
-        const uint32_t col = a_strided ? (uint32_t)(32 * (kk >> 1) + 8 * (kk & 1)) : (uint32_t)(8 * kk);
-        umma_ts(d_tmem, a_tmem + col, bdesc, idesc, k > 0 ? 1u : 0u);
+        const uint32_t col = AMODE == 1 ? (uint32_t)(32 * (kk >> 1) + 8 * (kk & 1)) : (uint32_t)(8 * kk);
+        umma_ts2(d_tmem, a_tmem + col, b_lo + (uint32_t)(kk * 2 * N), b_hi, idesc, kk > 0 ? 1u : 0u);
       }
     }
     tc_commit(&ct.mma_done);
   };
   auto issue_big = [&](uint32_t d_tmem, uint32_t a_tmem) {   // hidden -> hidden: NH column blocks of N = 128, K = U, A strided
     const uint32_t idesc = make_idesc(128);
+#pragma unroll
     for (int h = 0; h < NH; ++h) {
       const int slot = (int)((v_use + h) & 1);
       mbar_wait(&ct.full_b[slot], (pb >> slot) & 1u);
       pb ^= 1u << slot;
       tc_fence_after();
-      const uint32_t b_addr = smem_u32(sBig + (size_t)slot * kBig);
-      for (int k = 0; k < U; k += 16) {
-        const uint64_t bdesc = make_desc(b_addr + (uint32_t)(k >> 3) * 128u * 16u, 128);
-        const int kk = k >> 4;
-        umma_ts(d_tmem + (uint32_t)(128 * h), a_tmem + (uint32_t)(32 * (kk >> 1) + 8 * (kk & 1)), bdesc, idesc, k > 0 ? 1u : 0u);
-      }
+      const uint64_t bd = make_desc(smem_u32(sBig + (size_t)slot * kBig), 128);
+      const uint32_t b_lo = (uint32_t)bd, b_hi = (uint32_t)(bd >> 32);
+#pragma unroll
+      for (int kk = 0; kk < U / 16; ++kk)
+        umma_ts2(d_tmem + (uint32_t)(128 * h), a_tmem + (uint32_t)(32 * (kk >> 1) + 8 * (kk & 1)), b_lo + (uint32_t)(kk * 256),
+                 b_hi, idesc, kk > 0 ? 1u : 0u);
     }
     tc_commit(&ct.mma_done);
   };
@@ -258,6 +290,15 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
     tc_fence_after();
   };
 
+  // 32 columns (16 packed words) of this thread's row -> workspace matrix `mat` (rows x U, bf16), columns 32c..
+  auto store_chunk = [&](__nv_bfloat16* mat, int c, const uint32_t* o, bool valid_own, int64_t own_row) {
+    if (valid_own) {
+      __nv_bfloat16* dst = mat + own_row * U + 32 * c;
+      st256(dst, o);
+      st256(dst + 16, o + 8);
+    }
+  };
+
   for (int64_t it = 0; it < cnt; ++it) {
     const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
     const int64_t row = tile * kTileM + r_tile;
@@ -281,6 +322,32 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
 
     float tv[W], sv[W];      // t, then reused; s -> gradient of s
     float dxt[W];
+    constexpr int NI = NC / 4;
+    uint32_t hv[NI][16];     // tanh outputs of this thread's chunks, re-read for the tanh' phases of the backward part
+    // Requested one phase AHEAD of their use (before the MMAs of the previous, short job are even issued), so that the
+    // L2 latency hides behind that job and its epilogue
+    auto prefetch_h = [&](int net, int l) {
+      const __nv_bfloat16* hsrc = a.ws + sh.ws_mat(net, l, a.rows) + row * U;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        if (valid) {
+          ld256_cg(hsrc + 32 * (cq + 4 * i), hv[i]);
+          ld256_cg(hsrc + 32 * (cq + 4 * i) + 16, hv[i] + 8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hv[i][j] = 0u;
+        }
+      }
+    };
+    if (valid) {   // L2 prefetch of the rows' other operands (read once, a few phases from now): no registers held
+      const float* pf = cq == 0 ? a.z_in + row * sh.D + sh.t_off
+                                : (cq == 1 ? (a.g_z_out ? a.g_z_out + row * sh.D + sh.t_off : nullptr)
+                                           : (cq == 2 ? (a.g_z_out ? a.g_z_out + row * sh.D + sh.c_off : nullptr) : nullptr));
+      if (pf) {
+#pragma unroll
+        for (int j = 0; j < DH * 4; j += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + j / 4));
+      }
+    }
     // ======================= forward recompute, both nets =======================
 #pragma unroll
     for (int net = 0; net < 2; ++net) {
@@ -289,36 +356,49 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
       for (int l = 0; l < 2; ++l) {
         const uint32_t reg = l == 0 ? R0 : R1;
         if (ctl) {
-          if (l == 0) issue_small(R0, true, 0u, false, DH, U);
+          if (l == 0) issue_small(R0, 0u, IC<0>{}, IC<DH>{}, IC<U>{});
           else issue_big(R1, R0);
         }
         __syncwarp();
         wait_job(l == 1);
         if (!is_ctrl) {
-          __nv_bfloat16* hdst = a.ws + sh.ws_mat(net, l, a.rows) + row * U;
+          __nv_bfloat16* hmat = a.ws + sh.ws_mat(net, l, a.rows);
+          uint32_t x[NI][32];
 #pragma unroll
-          for (int i = 0; i < NC / 4; ++i) {
+          for (int i = 0; i < NI; ++i) tmem_ld32(reg + lane_addr + (uint32_t)(32 * (cq + 4 * i)), x[i]);   // all in flight
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
             const int c = cq + 4 * i;
-            uint32_t x[32], o[16];
-            tmem_ld32(reg + lane_addr + (uint32_t)(32 * c), x);
-            tc_wait_ld();
+            uint32_t o[16];
             const float* bl = bias + l * U + 32 * c;
 #pragma unroll
             for (int j = 0; j < 32; j += 2)
-              o[j >> 1] = pack_bf16(tanh_fast(__uint_as_float(x[j]) + bl[j]), tanh_fast(__uint_as_float(x[j + 1]) + bl[j + 1]));
+              o[j >> 1] = pack_bf16(tanh_fast(__uint_as_float(x[i][j]) + bl[j]), tanh_fast(__uint_as_float(x[i][j + 1]) + bl[j + 1]));
             tmem_st16(reg + lane_addr + (uint32_t)(32 * c), o);
-            if (valid) {
-              uint4* dst = reinterpret_cast<uint4*>(hdst + 32 * c);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-            }
+            store_chunk(hmat, c, o, valid, row);
           }
           tc_wait_st();
         }
         phase_end();
       }
       // final layer: t or s
-      if (ctl) issue_small(R0, false, R1, true, U, DH);
+      float z2[W], g2[W], gl = 0.f;
+      if (net == 1) {        // operands of the coupling phase and of the first tanh' phase: in flight during this job
+        gl = (valid && a.g_ld) ? a.g_ld[row] : 0.f;
+#pragma unroll
+        for (int j = 0; j < W; j += 4) {
+          float4 zz = make_float4(0.f, 0.f, 0.f, 0.f), gg = zz;
+          if (valid) {
+            zz = __ldg(reinterpret_cast<const float4*>(a.z_in + row * sh.D + sh.t_off + cq * W + j));
+            if (a.g_z_out) gg = __ldg(reinterpret_cast<const float4*>(a.g_z_out + row * sh.D + sh.t_off + cq * W + j));
+          }
+          z2[j] = zz.x; z2[j + 1] = zz.y; z2[j + 2] = zz.z; z2[j + 3] = zz.w;
+          g2[j] = gg.x; g2[j + 1] = gg.y; g2[j + 2] = gg.z; g2[j + 3] = gg.w;
+        }
+        prefetch_h(0, 1);
+      }
+      if (ctl) issue_small(R0, R1, IC<1>{}, IC<U>{}, IC<DH>{});
       __syncwarp();
       wait_job(false);
       if (!is_ctrl) {
@@ -334,18 +414,6 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
         }
         if (net == 1) {
           // ---- the coupling itself: gradients of t, s and of the transformed half (bijectors.py:172,198)
-          float z2[W], g2[W];
-          const float gl = (valid && a.g_ld) ? a.g_ld[row] : 0.f;
-#pragma unroll
-          for (int j = 0; j < W; j += 4) {
-            float4 zz = make_float4(0.f, 0.f, 0.f, 0.f), gg = zz;
-            if (valid) {
-              zz = __ldg(reinterpret_cast<const float4*>(a.z_in + row * sh.D + sh.t_off + cq * W + j));
-              if (a.g_z_out) gg = __ldg(reinterpret_cast<const float4*>(a.g_z_out + row * sh.D + sh.t_off + cq * W + j));
-            }
-            z2[j] = zz.x; z2[j + 1] = zz.y; z2[j + 2] = zz.z; z2[j + 3] = zz.w;
-            g2[j] = gg.x; g2[j + 1] = gg.y; g2[j + 2] = gg.z; g2[j + 3] = gg.w;
-          }
           float gz2[W];
           uint32_t pt[W / 2], psn[W / 2];
 #pragma unroll
@@ -396,43 +464,46 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
       for (int l = 1; l >= 0; --l) {
         const uint32_t reg = l == 1 ? R1 : R0;
         if (ctl) {
-          if (l == 1) issue_small(R1, false, R0 + (uint32_t)DH, false, DH, U);
+          if (l == 1) issue_small(R1, R0 + (uint32_t)DH, IC<2>{}, IC<DH>{}, IC<U>{});
           else issue_big(R0, R1);
         }
         __syncwarp();
+        // tanh outputs of this phase: the B3 phases' were requested a phase ago; the B2 phases' go out now and hide
+        // behind the long hidden-layer job
+        if (l == 0) prefetch_h(net, 0);
         wait_job(l == 0);
         if (!is_ctrl) {
-          const __nv_bfloat16* hsrc = a.ws + sh.ws_mat(net, l, a.rows) + row * U;
-          __nv_bfloat16* ddst = a.ws + sh.ws_mat(net, 2 + l, a.rows) + row * U;
+          __nv_bfloat16* dmat = a.ws + sh.ws_mat(net, 2 + l, a.rows);
 #pragma unroll
-          for (int i = 0; i < NC / 4; ++i) {
+          for (int i = 0; i < NI; ++i) {
             const int c = cq + 4 * i;
-            uint4 hv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              hv[j] = valid ? __ldcg(reinterpret_cast<const uint4*>(hsrc + 32 * c) + j) : make_uint4(0u, 0u, 0u, 0u);
             uint32_t x[32], o[16];
             tmem_ld32(reg + lane_addr + (uint32_t)(32 * c), x);
             tc_wait_ld();
-            const uint32_t* hp = reinterpret_cast<const uint32_t*>(hv);
+            const uint32_t* hp = hv[i];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float h0 = bf_lo(hp[j]), h1 = bf_hi(hp[j]);
               o[j] = pack_bf16(__uint_as_float(x[2 * j]) * fmaf(-h0, h0, 1.f), __uint_as_float(x[2 * j + 1]) * fmaf(-h1, h1, 1.f));
             }
             tmem_st16(reg + lane_addr + (uint32_t)(32 * c), o);
-            if (valid) {
-              uint4* dst = reinterpret_cast<uint4*>(ddst + 32 * c);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-            }
+            store_chunk(dmat, c, o, valid, row);
           }
           tc_wait_st();
         }
         phase_end();
       }
       // B1: dx = d1 . W1^T   (K = U, N = DH)
-      if (ctl) issue_small(R1, false, R0, true, U, DH);
+      float4 gx1[W / 4];
+      if (net == 0) {
+        prefetch_h(1, 1);
+      } else {
+#pragma unroll
+        for (int j = 0; j < W / 4; ++j)
+          gx1[j] = (valid && a.g_z_out) ? __ldg(reinterpret_cast<const float4*>(a.g_z_out + row * sh.D + sh.c_off + cq * W) + j)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (ctl) issue_small(R1, R0, IC<1>{}, IC<U>{}, IC<DH>{});
       __syncwarp();
       wait_job(false);
       if (!is_ctrl) {
@@ -453,8 +524,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
           float* gdst = a.g_z_in + row * sh.D + sh.c_off + cq * W;
 #pragma unroll
           for (int j = 0; j < W; j += 4) {
-            float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.g_z_out) gg = __ldg(reinterpret_cast<const float4*>(a.g_z_out + row * sh.D + sh.c_off + cq * W + j));
+            const float4 gg = gx1[j >> 2];
             *reinterpret_cast<float4*>(gdst + j) =
                 make_float4(gg.x + dxt[j] + __uint_as_float(o[j]), gg.y + dxt[j + 1] + __uint_as_float(o[j + 1]),
                             gg.z + dxt[j + 2] + __uint_as_float(o[j + 2]), gg.w + dxt[j + 3] + __uint_as_float(o[j + 3]));
