@@ -141,8 +141,10 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
  * 128-row tile from z_in on tcgen05, turns g_z_out (rows, D) and g_log_det (rows; gradient w.r.t. the plain sum s;
  * either may be NULL = zero) into g_z_in (rows, D), and stores the bf16 matrices the weight gradients are made of
  * into `workspace` (tnf_tc_bwd_workspace_bytes): per net n in {t, s}, in this order,
- *     h1, h2 (tanh outputs), d1, d2 (gradients of the hidden pre-activations): [n][4][rows][U]
+ *     h1, h2 (tanh outputs), d1, d2 (gradients of the hidden pre-activations): [n][4][rows][U + 16]
  *     d3 (gradient of the net's output):                                      [n][rows][D/2]  after the 8 matrices.
+ * (row pitch U + 16: the pad columns of h1 / h2 are written as [1, 0, ..., 0], so that (h | 1)^T d yields the weight
+ * gradient and, as its last row, the bias gradient in one GEMM; the pads of d1 / d2 are not written).
  * The weight gradients are then GEMMs over the batch (dW_l = a_{l-1}^T d_l, db_l = column sums of d_l, a_0 = the
  * conditioning half of z_in), left to the caller: a plain reduction with K = rows. */
 int tnf_tc_bwd_supported(int D, int U, int L);

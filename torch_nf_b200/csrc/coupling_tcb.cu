@@ -58,10 +58,12 @@ struct ShapeB {
     if (l >= 2) o += 2 * (int64_t)U * U + 2 * U;
     return o;
   }
-  // workspace (bf16 elements): [net][h1, h2, d1, d2][rows][U] then [net][rows][DH] (d3)
-  __host__ __device__ int64_t ws_mat(int net, int kind, int64_t rows) const { return ((int64_t)(net * 4 + kind) * rows) * U; }
-  __host__ __device__ int64_t ws_d3(int net, int64_t rows) const { return 8 * rows * U + (int64_t)net * rows * DH; }
-  __host__ __device__ int64_t ws_elems(int64_t rows) const { return 8 * rows * U + 2 * rows * DH; }
+  // workspace (bf16 elements): [net][h1, h2, d1, d2][rows][U + 16] then [net][rows][DH] (d3).  The 16 pad columns of
+  // h1 / h2 hold [1, 0, ..., 0]: (h | 1)^T d is the weight gradient AND (last row) the bias gradient in one GEMM
+  __host__ __device__ int64_t pitch() const { return U + 16; }
+  __host__ __device__ int64_t ws_mat(int net, int kind, int64_t rows) const { return ((int64_t)(net * 4 + kind) * rows) * pitch(); }
+  __host__ __device__ int64_t ws_d3(int net, int64_t rows) const { return 8 * rows * pitch() + (int64_t)net * rows * DH; }
+  __host__ __device__ int64_t ws_elems(int64_t rows) const { return 8 * rows * pitch() + 2 * rows * DH; }
 };
 
 // ---------------------------------------------------------------- weight packing
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
   // 32 columns (16 packed words) of this thread's row -> workspace matrix `mat` (rows x U, bf16), columns 32c..
   auto store_chunk = [&](__nv_bfloat16* mat, int c, const uint32_t* o, bool valid_own, int64_t own_row) {
     if (valid_own) {
-      __nv_bfloat16* dst = mat + own_row * U + 32 * c;
+      __nv_bfloat16* dst = mat + own_row * (U + 16) + 32 * c;
       st256(dst, o);
       st256(dst + 16, o + 8);
     }
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
     // Requested one phase AHEAD of their use (before the MMAs of the previous, short job are even issued), so that the
     // L2 latency hides behind that job and its epilogue
     auto prefetch_h = [&](int net, int l) {
-      const __nv_bfloat16* hsrc = a.ws + sh.ws_mat(net, l, a.rows) + row * U;
+      const __nv_bfloat16* hsrc = a.ws + sh.ws_mat(net, l, a.rows) + row * (U + 16);
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         if (valid) {
@@ -377,6 +379,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
               o[j >> 1] = pack_bf16(tanh_fast(__uint_as_float(x[i][j]) + bl[j]), tanh_fast(__uint_as_float(x[i][j + 1]) + bl[j + 1]));
             tmem_st16(reg + lane_addr + (uint32_t)(32 * c), o);
             store_chunk(hmat, c, o, valid, row);
+          }
+          if (cq == 0 && valid) {   // the pad columns: [1, 0, ..., 0] (bias-gradient row of the weight-gradient GEMM)
+            const uint32_t one[8] = {0x00003f80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            st256(hmat + row * (U + 16) + U, one);
           }
           tc_wait_st();
         }

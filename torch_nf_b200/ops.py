@@ -266,19 +266,20 @@ def tc_bwd_pack(params_row, D, U, L, upper):
 TC_BWD_MAX_ROWS = 1 << 20      # rows per kernel call: bounds the bf16 workspace (4.2 KB per row at D=64, U=256)
 
 
-def _mm_f32(a_t, b):
-    """a_t^T @ b for bf16 (rows, m), (rows, n) -> (m, n) float32 (library GEMM over the batch dimension)."""
+def _mm_t_f32(a, b):
+    """a^T @ b: a (rows, m), b (rows, n) bf16 -> (m, n) float32 (a library GEMM over the batch dimension K = rows)."""
     try:
-        return torch.mm(a_t.t(), b, out_dtype=torch.float32)
+        return torch.mm(a.t(), b, out_dtype=torch.float32)
     except (TypeError, RuntimeError):
-        return torch.mm(a_t.t(), b).float()
+        return torch.mm(a.t(), b).float()
 
 
 def coupling_tc_bwd(z_in, packed_bwd, g_z_out, g_ld, g_params_row, D, U, L, upper, direction):
     """Backward of the shared-weight coupling layer on tensor cores (tnf_coupling_tc_bwd).  Returns g_z_in and
     ACCUMULATES the parameter gradient into ``g_params_row`` (flat, the layer's slice, layout of bijectors.py:224-235).
     The data gradient and the recompute run in the CUDA kernel; the weight gradients are GEMMs over the batch
-    (K = rows) on the bf16 matrices the kernel leaves in its workspace."""
+    (K = rows) on the bf16 matrices the kernel leaves in its workspace: per net and layer ONE GEMM, the activation
+    operand carrying a ones column so that the bias gradient is a row of the product."""
     z2 = z_in.reshape(-1, D)
     if z2.dtype != torch.float32 or not z2.is_contiguous():
         raise TypeError("tensor-core coupling backward takes contiguous float32 z")
@@ -287,9 +288,10 @@ def coupling_tc_bwd(z_in, packed_bwd, g_z_out, g_ld, g_params_row, D, U, L, uppe
     gl = None if g_ld is None else g_ld.reshape(-1).contiguous()
     g_z = torch.empty_like(z2)
     DH = D // 2
+    UP = U + 16
     c_off = 0 if upper else DH
     gp = g_params_row.reshape(-1)
-    # offsets of the layer's pieces in the flat row
+    # offsets of the layer's pieces in the flat row: per layer [W_t | W_s | b_t | b_s]
     o0, o1 = 0, 2 * DH * U + 2 * U
     o2 = o1 + 2 * U * U + 2 * U
     lay = [(o0, DH, U), (o1, U, U), (o2, U, DH)]
@@ -303,17 +305,22 @@ def coupling_tc_bwd(z_in, packed_bwd, g_z_out, g_ld, g_params_row, D, U, L, uppe
                                             0 if gl is None else gl[lo:hi].data_ptr(), g_z[lo:hi].data_ptr(),
                                             ws.data_ptr(), rows, D, U, L, int(upper), direction, _stream())
         _lib.check(rc, "tnf_coupling_tc_bwd")
-        mats = ws[:8 * rows * U].view(2, 4, rows, U)
-        d3 = ws[8 * rows * U:].view(2, rows, DH)
-        x = z2[lo:hi, c_off:c_off + DH].to(torch.bfloat16)
+        mats = ws[:8 * rows * UP].view(2, 4, rows, UP)       # [net][h1, h2, d1, d2]
+        d3 = ws[8 * rows * UP:].view(2, rows, DH)
+        xa = torch.zeros((rows, DH + 8), dtype=torch.bfloat16, device=z2.device)      # (x | 1 | 0..)
+        xa[:, :DH] = z2[lo:hi, c_off:c_off + DH]
+        xa[:, DH] = 1.0
+        # per net and layer ONE GEMM: (activation | 1 | 0..)^T delta; rows 0..K-1 of the product are dW, row K is db.
+        # (measured, profiles/scripts/wgrad_gemm_probe.py: the full-pitch activation matrix with its ones column costs
+        # no more than the plain one and saves a column-sum pass over delta; a batched GEMM over both nets is 3x slower)
         for net in range(2):
-            h1, h2, d1, d2 = mats[net, 0], mats[net, 1], mats[net, 2], mats[net, 3]
-            acts = (x, h1, h2)
-            deltas = (d1, d2, d3[net])
+            acts = (xa, mats[net, 0], mats[net, 1])
+            deltas = (mats[net, 2][:, :U], mats[net, 3][:, :U], d3[net])
             for l, (off, K, J) in enumerate(lay):
-                gp[off + net * K * J: off + (net + 1) * K * J] += _mm_f32(acts[l], deltas[l]).reshape(-1)
+                g = _mm_t_f32(acts[l], deltas[l])
+                gp[off + net * K * J: off + (net + 1) * K * J] += g[:K].reshape(-1)
                 boff = off + 2 * K * J + net * J
-                gp[boff: boff + J] += deltas[l].sum(dim=0, dtype=torch.float32)
+                gp[boff: boff + J] += g[K]
         del ws
     return g_z.view(z_in.shape)
 
