@@ -109,3 +109,34 @@ def test_c3_training_gradients_bf16():
         assert rp < GRAD_TOL and rz < GRAD_TOL, (rp, rz)
     finally:
         config.set_conditioner_precision(old)
+
+
+def test_sample_direction_gradients_bf16():
+    """EFN-style loss through the SAMPLE direction (notebooks/two_network_arch.ipynb:77-83: mean(log_q - eta . T(z))) in
+    the bf16-conditioner mode: every coupling layer's forward and backward on tensor cores through the per-bijector
+    autograd functions, BatchNorm batch statistics differentiated, against oracle autograd."""
+    D, stages, U, N = 64, 1, 256, 4096
+    old = config.conditioner_precision()
+    config.set_conditioner_precision("bf16")
+    try:
+        nf = de.NormFlow(D, False, "coupling", stages, 2, U)
+        chain = O.build_chain(D, "coupling", stages, 2, U)
+        params0 = torch.tensor(synthetic_params(chain_spec(nf.bijectors), D, 1, seed=2))
+        omega = np.random.RandomState(3).standard_normal((1, N, D))
+        w = torch.tensor(np.random.RandomState(4).standard_normal(D).astype(np.float32))
+        p1 = params0.clone().requires_grad_(True)
+        z, lq = nf.forward(p1, N, omega=omega)
+        loss = (lq.float() - (z * w).sum(dim=2)).mean()
+        loss.backward()
+        p2 = params0.clone().requires_grad_(True)
+        zo, lqo, _ = O.normflow_forward(chain, D, p2, omega)
+        loss_o = (lqo.float() - (zo * w).sum(dim=2)).mean()
+        loss_o.backward()
+        rp = _rel(p1.grad, p2.grad)
+        print("sample direction, bf16: loss %.5f vs %.5f, max|dz| %.2e, rel-L2 g_params %.2e"
+              % (loss.item(), loss_o.item(), float((z.detach() - zo.detach()).abs().max()), rp))
+        assert float((z.detach() - zo.detach()).abs().max()) < config.BF16_TOL_Z
+        assert abs(loss.item() - loss_o.item()) < config.BF16_TOL_LOGP * max(1.0, abs(loss_o.item()))
+        assert rp < GRAD_TOL, rp
+    finally:
+        config.set_conditioner_precision(old)

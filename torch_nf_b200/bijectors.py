@@ -11,7 +11,7 @@ device.  There is no CPU compute path.
 import numpy as np
 import torch
 
-from . import ops
+from . import config, ops
 from .error_formatters import format_type_err_msg
 from .ops import TNF_FORWARD, TNF_INVERSE
 
@@ -67,11 +67,26 @@ class Bijector(object):
 
 
 # ------------------------------------------------------------------ RealNVP
+def _tc_differentiable(z, params, D, U, L):
+    """bf16-conditioner mode, shared weights, a compiled shape: the layer AND its backward run on tensor cores
+    (tnf_coupling_tc / tnf_coupling_tc_bwd); otherwise the exact CUDA-core kernels."""
+    return (config.conditioner_precision() == "bf16" and params.shape[0] == 1 and z.dtype == torch.float32
+            and params.dtype == torch.float32 and z.shape[0] * z.shape[1] >= config.tc_min_rows()
+            and ops.tc_bwd_supported(D, U, L) and ops.tc_supported(D, U, L, "bf16"))
+
+
 class _CouplingFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, params, D, U, L, upper, direction):
         ctx.set_materialize_grads(False)
-        z_out, ld = ops.coupling(z, params, D, U, L, upper, direction)
+        ctx.tc = (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and _tc_differentiable(z, params, D, U, L)
+        if ctx.tc:
+            zc = z.contiguous()
+            z_out, ld = ops.coupling_tc(zc, ops.tc_pack(params[0], D, U, L, upper, precision="bf16"), D, U, L, upper,
+                                        direction, precision="bf16")
+            ld = ld.view(z.shape[0], z.shape[1])
+        else:
+            z_out, ld = ops.coupling(z, params, D, U, L, upper, direction)
         ctx.save_for_backward(z, params)
         ctx.cfg = (D, U, L, upper, direction)
         return z_out, ld
@@ -81,7 +96,12 @@ class _CouplingFn(torch.autograd.Function):
         z, params = ctx.saved_tensors
         D, U, L, upper, direction = ctx.cfg
         g_params = torch.zeros(params.shape, dtype=params.dtype, device=params.device)
-        g_in = ops.coupling_bwd(z, params, g_z, g_ld, g_params, D, U, L, upper, direction)
+        if ctx.tc:
+            n = ops.coupling_num_params(D, U, L, upper)
+            g_in = ops.coupling_tc_bwd(z.contiguous(), ops.tc_bwd_pack(params[0], D, U, L, upper), g_z, g_ld,
+                                       g_params[0, :n], D, U, L, upper, direction)
+        else:
+            g_in = ops.coupling_bwd(z, params, g_z, g_ld, g_params, D, U, L, upper, direction)
         return g_in, g_params, None, None, None, None, None
 
 
