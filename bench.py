@@ -240,6 +240,7 @@ def main():
                     help="weak: --batch rows per GPU (default); strong: --batch rows in total, split over the ranks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-parity measurement of the same step")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement of the same flow")
     ap.add_argument("--config", default="c3", choices=["c3", "c5"],
                     help="c3 (default): the configuration the metric is quoted on; c5: BASELINE.json config 5 "
                          "(D=256, 16 coupling layers, bf16 conditioner; quoted at batch 2^20 over 8 GPUs: --scaling strong)")
@@ -416,6 +417,45 @@ def main():
         e2e = {"value": world * B * e_steps / (ms_h * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_h / e_steps}
 
+    # the same flow's maximum-likelihood TRAINING step (forward + tensor-core backward + Adam) on this GPU, as an extra
+    # object of the line (1 GPU, bf16 mode, C3 only); `--workload train_c3` is the multi-GPU form of this measurement
+    train_c3 = None
+    if world == 1 and args.config == "c3" and args.precision == "bf16" and not args.no_train:
+        del out
+        torch.cuda.empty_cache()
+        gen = torch.Generator(device=dev).manual_seed(7)
+        z_data = (torch.randn(1, B, D, device=dev, generator=gen) * 1.2 + 0.1).contiguous()
+        p_train = params.clone().requires_grad_(True)
+        opt = torch.optim.Adam([p_train], lr=1e-4)
+        t_losses = []
+
+        def train_step_fn():
+            opt.zero_grad(set_to_none=True)
+            loss = -nf.log_prob(z_data, p_train).mean()
+            loss.backward()
+            opt.step()
+            t_losses.append(loss.detach())
+        for _ in range(2):
+            train_step_fn()
+        torch.cuda.synchronize()
+        t_steps = 3
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(t_steps):
+            train_step_fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_t = e0.elapsed_time(e1) / t_steps
+        t_losses = [float(v) for v in t_losses]
+        train_c3 = {"metric": "maximum-likelihood training step (-mean log_prob: forward + backward of %d coupling layers on tensor cores, "
+                              "BatchNorm / Affine backward, Adam)" % N_LAYERS,
+                    "value": B / (ms_t * 1e-3), "unit": "samples/s", "ms_per_step": ms_t, "steps": t_steps, "rows": B,
+                    "gpu_launches_per_step": int(_lib.launch_count() - l0) // t_steps,
+                    "tflops_algorithmic": N_LAYERS * 4 * FLOP_PER_SAMPLE_LAYER * B / (ms_t * 1e-3) / 1e12,
+                    "loss_first": t_losses[0], "loss_last": t_losses[-1], "finite": bool(np.isfinite(t_losses).all())}
+        del z_data, p_train, opt
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -436,7 +476,7 @@ def main():
                        "bn_statistics_exchange": ("none (1 rank)" if world == 1 else
                                                   ("in-kernel over NVLink peer memory" if dist.peer_struct(0) is not None
                                                    else "NCCL all-reduce per BatchNorm (%s)" % (dist.peer_error or "peer exchange off")))},
-            "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
+            "roofline": roofline, "fp32": fp32, "train_c3": train_c3, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
             "clocks": clock_info,
             "checks": {"finite": finite, "max_abs_logq_minus_logprob": consistency},
         }

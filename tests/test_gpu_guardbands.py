@@ -94,3 +94,36 @@ def test_chain_and_fused_conditional_writes_stay_inside():
         torch.cuda.synchronize()
         assert _intact(lbuf, M) and torch.isfinite(lp).all()
         assert bool((pfull[:GUARD] == 0x7F).all()) and bool((pfull[GUARD + pbytes:] == 0x7F).all())
+
+
+@pytest.mark.parametrize("D,U", [(64, 256), (128, 128)])
+@pytest.mark.parametrize("N", [1, 129, 148 * 128 + 77])
+def test_coupling_tc_bwd_writes_stay_inside(D, U, N):
+    """Backward kernel: gradient output, bf16 workspace and packed images inside poisoned buffers; ragged row counts."""
+    lib = _lib.lib()
+    L = 2
+    params = torch.tensor(synthetic_params([("RealNVP", L, U, False)], D, 1, seed=4)).cuda()
+    pbytes = lib.tnf_tc_bwd_packed_bytes(D, U, L)
+    pfull = torch.full((pbytes + 2 * GUARD,), 0x7F, dtype=torch.uint8, device="cuda")
+    packed = pfull[GUARD:GUARD + pbytes]
+    _lib.check(lib.tnf_tc_bwd_pack(params.data_ptr(), packed.data_ptr(), D, U, L, 0, ops._stream()), "pack")
+    z = torch.randn(N, D, device="cuda")
+    gz = torch.randn(N, D, device="cuda")
+    gl = torch.randn(N, device="cuda")
+    gbuf, gout = _guarded(N * D)
+    wbytes = lib.tnf_tc_bwd_workspace_bytes(N, D, U, L)
+    wfull = torch.full((wbytes + 2 * GUARD,), 0x7F, dtype=torch.uint8, device="cuda")
+    ws = wfull[GUARD:GUARD + wbytes]
+    assert ws.data_ptr() % 32 == 0 and gout.data_ptr() % 16 == 0
+    _lib.check(lib.tnf_coupling_tc_bwd(z.data_ptr(), packed.data_ptr(), gz.data_ptr(), gl.data_ptr(), gout.data_ptr(),
+                                       ws.data_ptr(), N, D, U, L, 0, ops.TNF_INVERSE, ops._stream()), "tc_bwd")
+    torch.cuda.synchronize()
+    assert _intact(gbuf, N * D) and torch.isfinite(gout).all()
+    assert bool((wfull[:GUARD] == 0x7F).all()) and bool((wfull[GUARD + wbytes:] == 0x7F).all())
+    assert bool((pfull[:GUARD] == 0x7F).all()) and bool((pfull[GUARD + pbytes:] == 0x7F).all())
+    # everything the host GEMMs read has been written: h1, h2 with their ones column, d1, d2 (U columns), d3
+    UP = U + 16
+    mats = ws.view(torch.bfloat16)[:8 * N * UP].view(2, 4, N, UP)
+    assert torch.isfinite(mats[:, :2].float()).all() and torch.isfinite(mats[:, 2:, :, :U].float()).all()
+    assert bool((mats[:, :2, :, U] == 1).all()) and bool((mats[:, :2, :, U + 1:] == 0).all())
+    assert torch.isfinite(ws.view(torch.bfloat16)[8 * N * UP:].float()).all()
