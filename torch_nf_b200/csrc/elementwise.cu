@@ -135,6 +135,7 @@ __global__ void affine_bwd_kernel(const T* __restrict__ z_in, const T* __restric
       if (active) {
         T sc = exp_cr(p[d]);
         T sh = p[D + d];
+#pragma unroll 4
         for (int64_t n = sub; n < N; n += lanes_per_col) {
           int64_t e = (m * N + n) * D + d;
           T gy = g_y ? g_y[e] : T(0);

@@ -307,7 +307,9 @@ def coupling_tc_bwd(z_in, packed_bwd, g_z_out, g_ld, g_params_row, D, U, L, uppe
         _lib.check(rc, "tnf_coupling_tc_bwd")
         mats = ws[:8 * rows * UP].view(2, 4, rows, UP)       # [net][h1, h2, d1, d2]
         d3 = ws[8 * rows * UP:].view(2, rows, DH)
-        xa = torch.zeros((rows, DH + 8), dtype=torch.bfloat16, device=z2.device)      # (x | 1 | 0..)
+        # (x | 1 | 0..), padded to 64 / 128 columns: the library's 40-column product takes 0.49 ms, the 64-column one 0.28
+        # (profiles/r02_lines/r02z_wgrad_gemm_probe2.json)
+        xa = torch.zeros((rows, 64 if DH + 1 <= 64 else 128), dtype=torch.bfloat16, device=z2.device)
         xa[:, :DH] = z2[lo:hi, c_off:c_off + DH]
         xa[:, DH] = 1.0
         # per net and layer ONE GEMM: (activation | 1 | 0..)^T delta; rows 0..K-1 of the product are dW, row K is db.
