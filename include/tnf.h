@@ -142,11 +142,14 @@ int tnf_coupling_tc(const float* z_in, float* z_out, float* log_det, const void*
  * either may be NULL = zero) into g_z_in (rows, D), and stores the bf16 matrices the weight gradients are made of
  * into `workspace` (tnf_tc_bwd_workspace_bytes): per net n in {t, s}, in this order,
  *     h1, h2 (tanh outputs), d1, d2 (gradients of the hidden pre-activations): [n][4][rows][U + 16]
- *     d3 (gradient of the net's output):                                      [n][rows][D/2]  after the 8 matrices.
+ *     d3 (gradient of the net's output):                                      [n][rows][D/2]  after the 8 matrices,
+ *     xa = (conditioning half as the layer saw it | 1 | 0 ..):               [rows][64 (D = 64) or 128 (D = 128)]  last.
  * (row pitch U + 16: the pad columns of h1 / h2 are written as [1, 0, ..., 0], so that (h | 1)^T d yields the weight
  * gradient and, as its last row, the bias gradient in one GEMM; the pads of d1 / d2 are not written).
  * The weight gradients are then GEMMs over the batch (dW_l = a_{l-1}^T d_l, db_l = column sums of d_l, a_0 = the
- * conditioning half of z_in), left to the caller: a plain reduction with K = rows. */
+ * conditioning half of z_in), left to the caller: a plain reduction with K = rows.
+ * pre_scale / pre_shift (D floats each, or NULL): the layer was evaluated on z_in * pre_scale + pre_shift (a folded
+ * BatchNorm with remembered statistics, as in tnf_coupling_tc); g_z_in is the gradient w.r.t. z_in itself. */
 int tnf_tc_bwd_supported(int D, int U, int L);
 size_t tnf_tc_bwd_packed_bytes(int D, int U, int L);
 size_t tnf_tc_bwd_workspace_bytes(int64_t rows, int D, int U, int L);
@@ -154,7 +157,7 @@ int tnf_tc_bwd_pack(const float* params, void* packed, int D, int U, int L, int 
                     tnf_stream_t stream);
 int tnf_coupling_tc_bwd(const float* z_in, const void* packed, const float* g_z_out, const float* g_log_det,
                         float* g_z_in, void* workspace, int64_t rows, int D, int U, int L, int transform_upper,
-                        int direction, tnf_stream_t stream);
+                        int direction, const float* pre_scale, const float* pre_shift, tnf_stream_t stream);
 
 /* ---- Affine: replaces Affine.forward_and_log_det / inverse_and_log_det
  * (bijectors.py:277-315).  params row = [alpha(D), shift(D)].

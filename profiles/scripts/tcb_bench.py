@@ -52,7 +52,7 @@ def main():
 
     def kern():
         rc = lib.tnf_coupling_tc_bwd(z.data_ptr(), packed.data_ptr(), gz.data_ptr(), gl.data_ptr(), g_z.data_ptr(),
-                                     ws.data_ptr(), rows, D, U, L, 1, TNF_INVERSE, st)
+                                     ws.data_ptr(), rows, D, U, L, 1, TNF_INVERSE, 0, 0, st)
         assert rc == 0
     ms_k = timed(kern)
     flop = 3 * 327680 * rows        # recompute (1x) + data gradient (1x) on the kernel; weight gradient (1x) in the GEMMs

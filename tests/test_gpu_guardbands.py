@@ -116,7 +116,7 @@ def test_coupling_tc_bwd_writes_stay_inside(D, U, N):
     ws = wfull[GUARD:GUARD + wbytes]
     assert ws.data_ptr() % 32 == 0 and gout.data_ptr() % 16 == 0
     _lib.check(lib.tnf_coupling_tc_bwd(z.data_ptr(), packed.data_ptr(), gz.data_ptr(), gl.data_ptr(), gout.data_ptr(),
-                                       ws.data_ptr(), N, D, U, L, 0, ops.TNF_INVERSE, ops._stream()), "tc_bwd")
+                                       ws.data_ptr(), N, D, U, L, 0, ops.TNF_INVERSE, 0, 0, ops._stream()), "tc_bwd")
     torch.cuda.synchronize()
     assert _intact(gbuf, N * D) and torch.isfinite(gout).all()
     assert bool((wfull[:GUARD] == 0x7F).all()) and bool((wfull[GUARD + wbytes:] == 0x7F).all())

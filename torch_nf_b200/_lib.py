@@ -38,7 +38,7 @@ PROTOTYPES = {
     "tnf_tc_bwd_packed_bytes": (Z, [I, I, I]),
     "tnf_tc_bwd_workspace_bytes": (Z, [L, I, I, I]),
     "tnf_tc_bwd_pack": (I, [P, P, I, I, I, I, P]),
-    "tnf_coupling_tc_bwd": (I, [P, P, P, P, P, P, L, I, I, I, I, I, P]),
+    "tnf_coupling_tc_bwd": (I, [P, P, P, P, P, P, L, I, I, I, I, I, P, P, P]),
     "tnf_affine": (I, [P, P, P, P, L, L, L, I, I, I, P]),
     "tnf_affine_bwd": (I, [P, P, L, P, P, P, P, L, L, L, I, I, I, P]),
     "tnf_colstats_workspace_bytes": (Z, [I]),

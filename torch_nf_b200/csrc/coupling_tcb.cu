@@ -63,7 +63,11 @@ struct ShapeB {
   __host__ __device__ int64_t pitch() const { return U + 16; }
   __host__ __device__ int64_t ws_mat(int net, int kind, int64_t rows) const { return ((int64_t)(net * 4 + kind) * rows) * pitch(); }
   __host__ __device__ int64_t ws_d3(int net, int64_t rows) const { return 8 * rows * pitch() + (int64_t)net * rows * DH; }
-  __host__ __device__ int64_t ws_elems(int64_t rows) const { return 8 * rows * pitch() + 2 * rows * DH; }
+  // ... then xa [rows][xw()]: the conditioning half as the layer saw it (after the folded affine), bf16, followed by a
+  // ones column and zeros - the activation operand of the first layer's weight-gradient GEMM
+  __host__ __device__ int xw() const { return DH + 1 <= 64 ? 64 : 128; }
+  __host__ __device__ int64_t ws_xa(int64_t rows) const { return 8 * rows * pitch() + 2 * rows * DH; }
+  __host__ __device__ int64_t ws_elems(int64_t rows) const { return ws_xa(rows) + rows * xw(); }
 };
 
 // ---------------------------------------------------------------- weight packing
@@ -115,6 +119,7 @@ __global__ void pack_b_kernel(const float* __restrict__ params, unsigned char* _
 struct ArgsB {
   const float* z_in; const unsigned char* packed; const float* g_z_out; const float* g_ld; float* g_z_in;
   __nv_bfloat16* ws;
+  const float* pre_scale; const float* pre_shift;   // per-column affine applied to z_in on load (a folded BatchNorm), or NULL
   int64_t rows;
   int D, U, upper, inverse;
 };
@@ -127,7 +132,7 @@ struct __align__(16) CtrlB {
 template <int DH, int U>
 __host__ __device__ constexpr size_t smem_bytes_b() {
   return (size_t)2 * 128 * U * 2 + (size_t)2 * U * DH * 2 + (size_t)kTileM * DH * 2 + (size_t)2 * (2 * U + DH) * 4 +
-         sizeof(CtrlB);
+         sizeof(CtrlB) + (size_t)4 * DH * 4;
 }
 
 // 256-bit global accesses (sm_100): a thread's 32-column piece of a bf16 row is two of them instead of four 128-bit
@@ -177,6 +182,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
   unsigned char* sX = sSmall + 2 * (size_t)kSmall;     // conditioning half, bf16 A image (128 x DH)
   float* sBias = reinterpret_cast<float*>(sX + (size_t)kTileM * DH * 2);   // [net][b1 U | b2 U | b3 DH]
   CtrlB& ct = *reinterpret_cast<CtrlB*>(sBias + 2 * (2 * U + DH));
+  float* sPs = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&ct) + sizeof(CtrlB));   // pre_scale [D]
+  float* sPb = sPs + 2 * DH;                                                                       // pre_shift [D]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool is_ctrl = false;                      // no dedicated control warp: thread 0 also issues copies and MMAs
@@ -195,6 +202,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
   {
     const float* gb = reinterpret_cast<const float*>(a.packed + sh.bias_off());
     for (int i = threadIdx.x; i < 2 * (2 * U + DH); i += blockDim.x) sBias[i] = gb[i];
+    for (int i = threadIdx.x; i < 2 * DH; i += blockDim.x) {
+      sPs[i] = a.pre_scale ? a.pre_scale[i] : 1.0f;
+      sPb[i] = a.pre_shift ? a.pre_shift[i] : 0.0f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -305,18 +316,28 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
     const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
     const int64_t row = tile * kTileM + r_tile;
     const bool valid = !is_ctrl && row < a.rows;
-    // ---- conditioning half -> bf16 A image
+    // ---- conditioning half -> bf16 A image, and (with the ones column) -> workspace for the first layer's weight gradient
     if (!is_ctrl) {
-      for (int i = threadIdx.x; i < kTileM * DH / 8; i += kEpi * 32) {
-        const int r = i / (DH / 8), k8 = (i % (DH / 8)) * 8;
+      constexpr int XW = DH + 1 <= 64 ? 64 : 128;
+      __nv_bfloat16* xa = a.ws + sh.ws_xa(a.rows);
+      for (int i = threadIdx.x; i < kTileM * XW / 8; i += kEpi * 32) {
+        const int r = i / (XW / 8), k8 = (i % (XW / 8)) * 8;
         const int64_t grow = tile * kTileM + r;
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (grow < a.rows) {
-          const float4* src = reinterpret_cast<const float4*>(a.z_in + grow * sh.D + sh.c_off + k8);
-          v0 = __ldg(src); v1 = __ldg(src + 1);
+        uint4 pk = make_uint4(k8 == DH ? 0x00003f80u : 0u, 0u, 0u, 0u);      // [1, 0, ..] at column DH, zeros after it
+        if (k8 < DH) {
+          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+          if (grow < a.rows) {
+            const float4* src = reinterpret_cast<const float4*>(a.z_in + grow * sh.D + sh.c_off + k8);
+            v0 = __ldg(src); v1 = __ldg(src + 1);
+          }
+          const float4 s0 = *reinterpret_cast<const float4*>(sPs + sh.c_off + k8), s1 = *reinterpret_cast<const float4*>(sPs + sh.c_off + k8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(sPb + sh.c_off + k8), b1 = *reinterpret_cast<const float4*>(sPb + sh.c_off + k8 + 4);
+          v0.x = fmaf(v0.x, s0.x, b0.x); v0.y = fmaf(v0.y, s0.y, b0.y); v0.z = fmaf(v0.z, s0.z, b0.z); v0.w = fmaf(v0.w, s0.w, b0.w);
+          v1.x = fmaf(v1.x, s1.x, b1.x); v1.y = fmaf(v1.y, s1.y, b1.y); v1.z = fmaf(v1.z, s1.z, b1.z); v1.w = fmaf(v1.w, s1.w, b1.w);
+          pk = make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+          *reinterpret_cast<uint4*>(sX + img_off(r, k8, kTileM)) = pk;
         }
-        *reinterpret_cast<uint4*>(sX + img_off(r, k8, kTileM)) =
-            make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+        if (grow < a.rows) *reinterpret_cast<uint4*>(xa + grow * XW + k8) = pk;
       }
       fence_async_smem();
     }
@@ -399,7 +420,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
             zz = __ldg(reinterpret_cast<const float4*>(a.z_in + row * sh.D + sh.t_off + cq * W + j));
             if (a.g_z_out) gg = __ldg(reinterpret_cast<const float4*>(a.g_z_out + row * sh.D + sh.t_off + cq * W + j));
           }
-          z2[j] = zz.x; z2[j + 1] = zz.y; z2[j + 2] = zz.z; z2[j + 3] = zz.w;
+          const float* ps = sPs + sh.t_off + cq * W + j;
+          const float* pb = sPb + sh.t_off + cq * W + j;
+          z2[j] = fmaf(zz.x, ps[0], pb[0]); z2[j + 1] = fmaf(zz.y, ps[1], pb[1]);
+          z2[j + 2] = fmaf(zz.z, ps[2], pb[2]); z2[j + 3] = fmaf(zz.w, ps[3], pb[3]);
           g2[j] = gg.x; g2[j + 1] = gg.y; g2[j + 2] = gg.z; g2[j + 3] = gg.w;
         }
         prefetch_h(0, 1);
@@ -448,7 +472,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
           if (valid) {
             float* gdst = a.g_z_in + row * sh.D + sh.t_off + cq * W;
 #pragma unroll
-            for (int j = 0; j < W; j += 4) *reinterpret_cast<float4*>(gdst + j) = make_float4(gz2[j], gz2[j + 1], gz2[j + 2], gz2[j + 3]);
+            for (int j = 0; j < W; j += 4) {   // gradient w.r.t. the layer input BEFORE the folded affine
+              const float* ps = sPs + sh.t_off + cq * W + j;
+              *reinterpret_cast<float4*>(gdst + j) = make_float4(gz2[j] * ps[0], gz2[j + 1] * ps[1], gz2[j + 2] * ps[2], gz2[j + 3] * ps[3]);
+            }
             uint4* d3t = reinterpret_cast<uint4*>(a.ws + sh.ws_d3(0, a.rows) + row * DH + cq * W);
             uint4* d3s = reinterpret_cast<uint4*>(a.ws + sh.ws_d3(1, a.rows) + row * DH + cq * W);
 #pragma unroll
@@ -531,9 +558,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
 #pragma unroll
           for (int j = 0; j < W; j += 4) {
             const float4 gg = gx1[j >> 2];
+            const float* ps = sPs + sh.c_off + cq * W + j;
             *reinterpret_cast<float4*>(gdst + j) =
-                make_float4(gg.x + dxt[j] + __uint_as_float(o[j]), gg.y + dxt[j + 1] + __uint_as_float(o[j + 1]),
-                            gg.z + dxt[j + 2] + __uint_as_float(o[j + 2]), gg.w + dxt[j + 3] + __uint_as_float(o[j + 3]));
+                make_float4((gg.x + dxt[j] + __uint_as_float(o[j])) * ps[0], (gg.y + dxt[j + 1] + __uint_as_float(o[j + 1])) * ps[1],
+                            (gg.z + dxt[j + 2] + __uint_as_float(o[j + 2])) * ps[2], (gg.w + dxt[j + 3] + __uint_as_float(o[j + 3])) * ps[3]);
           }
         }
       }
@@ -590,7 +618,7 @@ int tnf_tc_bwd_pack(const float* params, void* packed, int D, int U, int L, int 
 
 int tnf_coupling_tc_bwd(const float* z_in, const void* packed, const float* g_z_out, const float* g_log_det,
                         float* g_z_in, void* workspace, int64_t rows, int D, int U, int L, int transform_upper,
-                        int direction, tnf_stream_t stream) {
+                        int direction, const float* pre_scale, const float* pre_shift, tnf_stream_t stream) {
   TNF_REQUIRE(z_in && packed && g_z_in && workspace, TNF_ERR_ARG, "tnf_coupling_tc_bwd: null pointer");
   TNF_REQUIRE(tcb::shape_supported_b(D, U, L), TNF_ERR_UNSUPPORTED, "tnf_coupling_tc_bwd: D=%d U=%d L=%d not supported", D, U, L);
   TNF_REQUIRE(rows >= 0, TNF_ERR_ARG, "tnf_coupling_tc_bwd: rows < 0");
@@ -603,6 +631,7 @@ int tnf_coupling_tc_bwd(const float* z_in, const void* packed, const float* g_z_
   a.z_in = z_in; a.packed = (const unsigned char*)packed; a.g_z_out = g_z_out; a.g_ld = g_log_det; a.g_z_in = g_z_in;
   a.ws = (__nv_bfloat16*)workspace; a.rows = rows; a.D = D; a.U = U; a.upper = transform_upper;
   a.inverse = direction == TNF_INVERSE;
+  a.pre_scale = pre_scale; a.pre_shift = pre_shift;
   const int64_t n_tiles = (rows + tc::kTileM - 1) / tc::kTileM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;

@@ -178,6 +178,56 @@ __global__ void affine_bwd_kernel(const T* __restrict__ z_in, const T* __restric
   }
 }
 
+// ONE shared parameter row and a large batch (regime A training), float32, D % 4 == 0: 128-bit accesses, a thread owns
+// four columns and walks rows_per_iter-strided rows of its block's chunk; per-block column sums through shared memory,
+// one atomicAdd per column and block into the shared gradient row.  HBM-bound (the generic kernel above: one 4-byte
+// access per thread and iteration, 0.48 ms per 2^20 x 64 pass; this one: see profiles/r02_lines).
+__global__ void __launch_bounds__(256) affine_bwd_shared_f32_kernel(const float* __restrict__ z_in, const float* __restrict__ params,
+                                                                    const float* __restrict__ g_y, const float* __restrict__ g_ld,
+                                                                    float* __restrict__ g_z, float* __restrict__ g_params,
+                                                                    int64_t N, int D, int inverse, int64_t rows_per_block) {
+  extern __shared__ unsigned char smem_raw[];
+  float* red = reinterpret_cast<float*>(smem_raw);            // [2][rpi][D]
+  const int lanes = D / 4, rpi = blockDim.x / lanes;          // threads per row, rows per iteration
+  const int t = threadIdx.x, c4 = (t % lanes) * 4, rsub = t / lanes;
+  const bool active = rsub < rpi;
+  const int64_t n0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t n1 = n0 + rows_per_block < N ? n0 + rows_per_block : N;
+  float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+  if (active) {
+    const float4 al = *reinterpret_cast<const float4*>(params + c4), sh = *reinterpret_cast<const float4*>(params + D + c4);
+    const float4 sc = make_float4(exp_cr(al.x), exp_cr(al.y), exp_cr(al.z), exp_cr(al.w));   // as the forward kernel
+#pragma unroll 4
+    for (int64_t n = n0 + rsub; n < n1; n += rpi) {
+      const int64_t e = n * D + c4;
+      const float4 gy = g_y ? *reinterpret_cast<const float4*>(g_y + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 z = *reinterpret_cast<const float4*>(z_in + e);
+      float4 gz;
+      if (!inverse) {
+        gz = make_float4(gy.x * sc.x, gy.y * sc.y, gy.z * sc.z, gy.w * sc.w);
+        ga.x = fmaf(gz.x, z.x, ga.x); ga.y = fmaf(gz.y, z.y, ga.y); ga.z = fmaf(gz.z, z.z, ga.z); ga.w = fmaf(gz.w, z.w, ga.w);
+        gb.x += gy.x; gb.y += gy.y; gb.z += gy.z; gb.w += gy.w;
+      } else {
+        gz = make_float4(gy.x / sc.x, gy.y / sc.y, gy.z / sc.z, gy.w / sc.w);
+        const float4 y = make_float4((z.x - sh.x) / sc.x, (z.y - sh.y) / sc.y, (z.z - sh.z) / sc.z, (z.w - sh.w) / sc.w);
+        ga.x = fmaf(-gy.x, y.x, ga.x); ga.y = fmaf(-gy.y, y.y, ga.y); ga.z = fmaf(-gy.z, y.z, ga.z); ga.w = fmaf(-gy.w, y.w, ga.w);
+        gb.x -= gz.x; gb.y -= gz.y; gb.z -= gz.z; gb.w -= gz.w;
+      }
+      *reinterpret_cast<float4*>(g_z + e) = gz;
+    }
+    *reinterpret_cast<float4*>(red + (size_t)rsub * D + c4) = ga;
+    *reinterpret_cast<float4*>(red + (size_t)(rpi + rsub) * D + c4) = gb;
+  }
+  __syncthreads();
+  for (int d = t; d < D; d += blockDim.x) {
+    float sa = 0.f, sb = 0.f;
+    for (int k = 0; k < rpi; ++k) { sa += red[(size_t)k * D + d]; sb += red[(size_t)(rpi + k) * D + d]; }
+    if (blockIdx.x == 0 && g_ld) sa += g_ld[0];               // the Affine log-det gradient enters once
+    atomicAdd(&g_params[d], sa);
+    atomicAdd(&g_params[D + d], sb);
+  }
+}
+
 // one sample (or a few) per parameter row - the conditional regime (N = 1): a block per m with two barriers per row is
 // ~1 ms at M = 2^18; here a thread owns (m, d) and walks its N samples, no shared memory, no barriers
 template <typename T>
@@ -933,6 +983,18 @@ int tnf_affine_bwd(const void* z_in, const void* params, int64_t pstride, const 
     return check_launch("tnf_affine_bwd");
   }
   int nt = 256;
+  if (M == 1 && gstride == 0 && N >= 8192 && dtype == TNF_F32 && D % 4 == 0 && D / 4 <= 256 && 256 % (D / 4) == 0 &&
+      ((((uintptr_t)z_in | (uintptr_t)params | (uintptr_t)g_z_out | (uintptr_t)g_z_in) & 15) == 0)) {
+    const int rpi = 256 / (D / 4);
+    int64_t blocks = (int64_t)num_sms() * 8;
+    int64_t rpb = (N + blocks - 1) / blocks;
+    rpb = (rpb + rpi - 1) / rpi * rpi;
+    blocks = (N + rpb - 1) / rpb;
+    affine_bwd_shared_f32_kernel<<<(int)blocks, 256, (size_t)2 * rpi * D * sizeof(float), st>>>(
+        (const float*)z_in, (const float*)params, (const float*)g_z_out, (const float*)g_log_det, (float*)g_z_in,
+        (float*)g_params, N, D, direction == TNF_INVERSE, rpb);
+    return check_launch("tnf_affine_bwd");
+  }
   if (M == 1 && gstride == 0 && N >= 8192) {
     // ONE shared parameter row and a large batch (regime A training): a single block would walk all N rows.  The rows
     // are cut into pseudo parameter rows of kRows samples that all accumulate into the shared gradient row (atomics,

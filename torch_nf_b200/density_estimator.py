@@ -684,18 +684,32 @@ class _ChainLogProbFn(torch.autograd.Function):
         scal = torch.zeros(pd.shape[0], dtype=z.dtype, device=z.device)
         pdd = pd.detach()
         cur = z.detach()
-        for (b, idx, n) in reversed(nf._slices()):
+        order = list(reversed(nf._slices()))             # execution order of the inverse chain
+        pre = None                                       # (alpha, mean) of a BatchNorm folded into the NEXT coupling layer
+        folded = {}                                      # position in `order` of a coupling layer -> its folded pre-affine
+        for k, (b, idx, n) in enumerate(order):
             ins.append(cur)
             if b.name == "RealNVP" and nf._tc_train(b, pdd, cur):
-                # bf16-conditioner mode, shared weights: forward AND backward of the layer on tensor cores
+                # bf16-conditioner mode, shared weights: forward AND backward of the layer on tensor cores; a BatchNorm
+                # right before it is applied on load (z alpha + mean with its remembered statistics: constants)
+                ps, pb = pre if pre is not None else (None, None)
+                if pre is not None:
+                    folded[k] = pre
+                    pre = None
                 cur, _ = ops.coupling_tc(cur, nf._packed(b, idx, n, pdd, src=pd), b.D, b.num_units, b.num_layers,
-                                         b.transform_upper, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD, precision="bf16")
+                                         b.transform_upper, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD, pre_scale=ps,
+                                         pre_shift=pb, precision="bf16")
             elif b.name == "RealNVP":
                 cur, _ = ops.coupling(cur, pdd[:, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper, TNF_INVERSE,
                                       ld=ld_acc, accum=TNF_LD_ADD)
             elif b.name == "BatchNorm":
                 mean, alpha = b._state_on(z.device, z.dtype)
-                cur = ops.bn_apply(cur, mean, alpha, D, TNF_INVERSE)
+                nxt = order[k + 1][0] if k + 1 < len(order) else None
+                if (nxt is not None and nxt.name == "RealNVP" and nf._tc_train(nxt, pdd, cur)
+                        and mean.numel() == D and alpha.numel() == D):       # (identity statistics before the first forward are scalars)
+                    pre = (alpha.reshape(-1).contiguous(), mean.reshape(-1).contiguous())
+                else:
+                    cur = ops.bn_apply(cur, mean, alpha, D, TNF_INVERSE)
                 ops.accum_bcast(scal, b._last_ld.to(device=z.device, dtype=z.dtype).reshape(1), pd.shape[0])
             elif b.name == "Affine":
                 cur, ld = ops.affine(cur, pdd[:, idx:idx + n], D, TNF_INVERSE)
@@ -703,7 +717,7 @@ class _ChainLogProbFn(torch.autograd.Function):
             else:   # ToInterval
                 cur, _ = ops.tointerval(cur, b._consts(z.device), D, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD)
         lp = ops.base_logprob(cur, ld_acc, scal, N if pd.shape[0] == M and M > 1 else M * N)
-        ctx.nf, ctx.ins, ctx.z0 = nf, ins, cur
+        ctx.nf, ctx.ins, ctx.z0, ctx.folded = nf, ins, cur, folded
         ctx.save_for_backward(pd)
         ctx.need = (z.requires_grad, pd.requires_grad)
         return lp
@@ -726,16 +740,21 @@ class _ChainLogProbFn(torch.autograd.Function):
         g_ld = -g_lp                                       # log_prob = log N(z0) - sum of log-dets
         g_ld_rows = g_ld.sum(dim=1) if Mp == M and M > 1 else g_ld.sum().reshape(1)     # Affine: log-det per parameter row
         slices = nf._slices()                              # chain order = the reverse of the forward's execution order
+        folded = ctx.folded
         for k, (b, idx, n) in enumerate(slices):
-            z_in = ins[len(slices) - 1 - k]
+            pos = len(slices) - 1 - k                    # this bijector's position in the forward's execution order
+            z_in = ins[pos]
             if b.name == "RealNVP" and nf._tc_train(b, pdd, z_in):
                 packed_b = ops.tc_bwd_pack(pdd[0, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper)
+                ps, pb = folded.get(pos, (None, None))
                 g_z = ops.coupling_tc_bwd(z_in, packed_b, g_z, g_ld, g_params[0, idx:idx + n], b.D, b.num_units,
-                                          b.num_layers, b.transform_upper, TNF_INVERSE)
+                                          b.num_layers, b.transform_upper, TNF_INVERSE, pre_scale=ps, pre_shift=pb)
             elif b.name == "RealNVP":
                 g_z = ops.coupling_bwd(z_in, pdd[:, idx:idx + n], g_z, g_ld, g_params[:, idx:idx + n], b.D, b.num_units,
                                        b.num_layers, b.transform_upper, TNF_INVERSE, overwrite=ow)
             elif b.name == "BatchNorm":                    # remembered statistics are constants: z alpha + mean
+                if (pos + 1) in folded:                    # folded into the coupling layer after it: that kernel scaled g_z
+                    continue
                 _, alpha = b._state_on(z0.device, z0.dtype)
                 g_z = ops.bn_apply(g_z, torch.zeros_like(alpha), alpha, D, TNF_INVERSE)
             elif b.name == "Affine":

@@ -274,12 +274,14 @@ def _mm_t_f32(a, b):
         return torch.mm(a.t(), b).float()
 
 
-def coupling_tc_bwd(z_in, packed_bwd, g_z_out, g_ld, g_params_row, D, U, L, upper, direction):
+def coupling_tc_bwd(z_in, packed_bwd, g_z_out, g_ld, g_params_row, D, U, L, upper, direction, pre_scale=None, pre_shift=None):
     """Backward of the shared-weight coupling layer on tensor cores (tnf_coupling_tc_bwd).  Returns g_z_in and
     ACCUMULATES the parameter gradient into ``g_params_row`` (flat, the layer's slice, layout of bijectors.py:224-235).
     The data gradient and the recompute run in the CUDA kernel; the weight gradients are GEMMs over the batch
     (K = rows) on the bf16 matrices the kernel leaves in its workspace: per net and layer ONE GEMM, the activation
-    operand carrying a ones column so that the bias gradient is a row of the product."""
+    operand carrying a ones column so that the bias gradient is a row of the product.
+    ``pre_scale`` / ``pre_shift`` (D floats): the layer acted on ``z_in * pre_scale + pre_shift`` (a folded BatchNorm);
+    the returned gradient is w.r.t. ``z_in``."""
     z2 = z_in.reshape(-1, D)
     if z2.dtype != torch.float32 or not z2.is_contiguous():
         raise TypeError("tensor-core coupling backward takes contiguous float32 z")
@@ -303,15 +305,15 @@ def coupling_tc_bwd(z_in, packed_bwd, g_z_out, g_ld, g_params_row, D, U, L, uppe
         rc = _lib.lib().tnf_coupling_tc_bwd(z2[lo:hi].data_ptr(), packed_bwd.data_ptr(),
                                             0 if gz2 is None else gz2[lo:hi].data_ptr(),
                                             0 if gl is None else gl[lo:hi].data_ptr(), g_z[lo:hi].data_ptr(),
-                                            ws.data_ptr(), rows, D, U, L, int(upper), direction, _stream())
+                                            ws.data_ptr(), rows, D, U, L, int(upper), direction, _ptr(pre_scale),
+                                            _ptr(pre_shift), _stream())
         _lib.check(rc, "tnf_coupling_tc_bwd")
         mats = ws[:8 * rows * UP].view(2, 4, rows, UP)       # [net][h1, h2, d1, d2]
-        d3 = ws[8 * rows * UP:].view(2, rows, DH)
-        # (x | 1 | 0..), padded to 64 / 128 columns: the library's 40-column product takes 0.49 ms, the 64-column one 0.28
-        # (profiles/r02_lines/r02z_wgrad_gemm_probe2.json)
-        xa = torch.zeros((rows, 64 if DH + 1 <= 64 else 128), dtype=torch.bfloat16, device=z2.device)
-        xa[:, :DH] = z2[lo:hi, c_off:c_off + DH]
-        xa[:, DH] = 1.0
+        d3 = ws[8 * rows * UP: 8 * rows * UP + 2 * rows * DH].view(2, rows, DH)
+        # xa = (x | 1 | 0..) as the layer saw it, written by the kernel; padded to 64 / 128 columns: the library's
+        # 40-column product takes 0.49 ms, the 64-column one 0.28 (profiles/r02_lines/r02z_wgrad_gemm_probe2.json)
+        XW = 64 if DH + 1 <= 64 else 128
+        xa = ws[8 * rows * UP + 2 * rows * DH:].view(rows, XW)
         # per net and layer ONE GEMM: (activation | 1 | 0..)^T delta; rows 0..K-1 of the product are dW, row K is db.
         # (measured, profiles/scripts/wgrad_gemm_probe.py: the full-pitch activation matrix with its ones column costs
         # no more than the plain one and saves a column-sum pass over delta; a batched GEMM over both nets is 3x slower)
