@@ -1616,8 +1616,8 @@ int coupling_tc_impl(const float* z_in, float* z_out, float* log_det, const void
     TNF_REQUIRE(rows >= 0, TNF_ERR_ARG, "tnf_coupling_tc: rows < 0");
     if (rows == 0) return 0;
     TNF_REQUIRE(z_in && (z_out || out_lp) && log_det && packed, TNF_ERR_ARG, "tnf_coupling_tc: null pointer");
-    TNF_REQUIRE((((uintptr_t)z_in | (uintptr_t)z_out | (uintptr_t)packed) & 15) == 0, TNF_ERR_ALIGN,
-                "tnf_coupling_tc: z and packed weights must be 16-byte aligned");
+    TNF_REQUIRE((((uintptr_t)z_in | (uintptr_t)z_out) & 31) == 0 && ((uintptr_t)packed & 15) == 0, TNF_ERR_ALIGN,
+                "tnf_coupling_tc: z must be 32-byte aligned (256-bit accesses), the packed weights 16-byte aligned");
     TNF_REQUIRE(col_stats == nullptr || (stats_workspace != nullptr && direction == TNF_FORWARD), TNF_ERR_ARG,
                 "tnf_coupling_tc: this kernel takes fused column statistics in the sample direction, with a workspace");
     const int64_t n_super6 = ((rows + tc::kTileM - 1) / tc::kTileM + 1) / 2;
@@ -1715,6 +1715,9 @@ int coupling_tc_impl(const float* z_in, float* z_out, float* log_det, const void
   int stat_blocks = grid * tc::kEpiWarps;
   if (pairs) {
     stat_blocks = grid;
+    // coupling_tc5 moves the transformed half with 256-bit accesses (rows are 256 / 512 bytes: only the base matters)
+    TNF_REQUIRE(!pairs5 || (((uintptr_t)z_in | (uintptr_t)z_out) & 31) == 0, TNF_ERR_ALIGN,
+                "tnf_coupling_tc: z must be 32-byte aligned for this kernel");
     e = (cudaError_t)(pairs5 ? tc::launch_tc5(a, grid, smem, st) : tc::launch_tc4(a, grid, smem, st));
   } else if (pingpong2) {
     stat_blocks = grid;

@@ -495,9 +495,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
         float ld_old = 0.f;
         if (net == 1) {
 #pragma unroll
-          for (int j = 0; j < W; j += 4) {
-            const float4 t4 = valid ? __ldg(reinterpret_cast<const float4*>(zrow + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            zin[j] = t4.x; zin[j + 1] = t4.y; zin[j + 2] = t4.z; zin[j + 3] = t4.w;
+          for (int j = 0; j < W; j += 8) {   // 256-bit accesses: half the instructions, each 32 L1 wavefronts (one row per lane)
+            if (valid) {
+              ldg256_nc(zrow + j, zin + j);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) zin[j + e] = 0.f;
+            }
           }
           if (cq == 0 && valid && a.accum != TNF_LD_WRITE) ld_old = a.log_det[row];
         }
@@ -550,8 +554,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads6, 1) coupli
           if (valid) {
             float* orow = a.z_out + row * sh.D + sh.t_off + cq * W;
 #pragma unroll
-            for (int j = 0; j < W; j += 4)
-              *reinterpret_cast<float4*>(orow + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            for (int j = 0; j < W; j += 8) stg256(orow + j, y + j);
           }
           if (want_stats) {   // release the stored tile half to the I/O warps
             __syncwarp();

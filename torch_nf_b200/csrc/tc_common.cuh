@@ -341,6 +341,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+// 256-bit global accesses (sm_100): a thread that owns 8+ consecutive floats of a row moves them in half the
+// instructions; with one row per lane every lane of such an instruction is in another 128-byte line, so the LSU pipe
+// pays per instruction (32 wavefronts each)
+__device__ __forceinline__ void ldg256_nc(const float* p, float* r) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* r) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]),
+               "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
+               : "memory");
+}
+
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
