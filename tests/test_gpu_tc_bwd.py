@@ -140,3 +140,26 @@ def test_sample_direction_gradients_bf16():
         assert rp < GRAD_TOL, rp
     finally:
         config.set_conditioner_precision(old)
+
+
+def test_tc_backward_full_size_against_cuda_cores():
+    """At more than BASELINE's full batch (2^20 + 2^17 + 5 rows: two workspace chunks, 55 tiles per CTA, a ragged last
+    tile) the tensor-core backward against the EXACT CUDA-core backward kernel on the same inputs: the same stated bound."""
+    D, U, L, rows = 64, 256, 2, (1 << 20) + (1 << 17) + 5
+    params = torch.tensor(synthetic_params([("RealNVP", L, U, True)], D, 1, seed=11)).cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    z = torch.randn(1, rows, D, device="cuda", generator=g)
+    gz = torch.randn(1, rows, D, device="cuda", generator=g)
+    gl = torch.randn(1, rows, device="cuda", generator=g)
+    gp_tc = torch.zeros_like(params)
+    gz_tc = ops.coupling_tc_bwd(z, ops.tc_bwd_pack(params[0], D, U, L, True), gz, gl, gp_tc[0], D, U, L, True, TNF_INVERSE)
+    gp_cc = torch.zeros_like(params)
+    gz_cc = ops.coupling_bwd(z, params, gz, gl, gp_cc, D, U, L, True, TNF_INVERSE)
+    torch.cuda.synchronize()
+    rz, rp = _rel(gz_tc, gz_cc), _rel(gp_tc, gp_cc)
+    print("full size (%d rows): tensor-core vs CUDA-core backward rel-L2 g_z %.2e g_params %.2e" % (rows, rz, rp))
+    assert rz < GRAD_TOL and rp < GRAD_TOL, (rz, rp)
+    # linearity in the output gradients (a size-independent property): bwd(2 g) = 2 bwd(g)
+    gp2 = torch.zeros_like(params)
+    gz2 = ops.coupling_tc_bwd(z, ops.tc_bwd_pack(params[0], D, U, L, True), 2 * gz, 2 * gl, gp2[0], D, U, L, True, TNF_INVERSE)
+    assert _rel(gz2, 2 * gz_tc) < 1e-6 and _rel(gp2, 2 * gp_tc) < 2e-3
