@@ -1,17 +1,11 @@
 """The reference's test files run unmodified against the `torch_nf` shim (= torch_nf_b200): every item needs the
-GPU; MoG (out of scope, no bijector chain) is skipped / expected to raise."""
+GPU.  Nothing is skipped or expected to fail: the mixture-of-Gaussians estimator (`test_MoG`, the last block of
+`test_ConditionalDensityEstimator`) is built too."""
 import pytest
 
 
 def pytest_collection_modifyitems(config, items):
-    from torch_nf_b200.density_estimator import MoGOutOfScope
     for item in items:
         if "reference_suite" not in str(item.fspath):
             continue
         item.add_marker(pytest.mark.gpu)
-        if item.name == "test_MoG":
-            item.add_marker(pytest.mark.skip(reason="MoG is outside the hot path (SURVEY.md section 2)"))
-        if item.name == "test_ConditionalDensityEstimator":
-            # everything up to the final MoG block must pass; the block itself raises MoGOutOfScope
-            item.add_marker(pytest.mark.xfail(raises=MoGOutOfScope, strict=True,
-                                              reason="last block constructs de.MoG (out of scope)"))

@@ -42,7 +42,7 @@ class ConditionalDensityEstimator(torch.nn.Module):
     @density_estimator.setter
     def density_estimator(self, val):
         # exact type, as in the reference (:48): subclasses are rejected
-        if type(val) is not de.NormFlow:
+        if type(val) not in (de.NormFlow, de.MoG):
             raise TypeError(format_type_err_msg(self, "density_estimator", val, de.DensityEstimator))
         self._density_estimator = val
 
@@ -87,7 +87,9 @@ class ConditionalDensityEstimator(torch.nn.Module):
 
     def __call__(self, x, N=100, freeze_bn=False):
         params = self.param_net(x)
-        return self.density_estimator(N=N, params=params, freeze_bn=freeze_bn)
+        if type(self.density_estimator) is de.NormFlow:       # only the flow has BatchNorm state to freeze (:95-98)
+            return self.density_estimator(N=N, params=params, freeze_bn=freeze_bn)
+        return self.density_estimator(N=N, params=params)
 
     def log_prob(self, z, x):
         lp = self._log_prob_fused(z, x)
@@ -105,7 +107,7 @@ class ConditionalDensityEstimator(torch.nn.Module):
         from . import _lib, config, ops
         nf = self.density_estimator
         last = self.param_net[-1]
-        if (not config.cde_fusion() or self.dropout or not isinstance(last, torch.nn.Linear) or len(self.param_net) < 2
+        if (type(nf) is not de.NormFlow or not config.cde_fusion() or self.dropout or not isinstance(last, torch.nn.Linear) or len(self.param_net) < 2
                 or z.dim() != 3 or z.shape[1] != 1 or x.dim() != 2 or x.shape[0] != z.shape[0]
                 or z.dtype != torch.float32 or x.dtype != torch.float32 or not torch.cuda.is_available()):
             return None

@@ -66,18 +66,141 @@ class DensityEstimator(object):
         raise NotImplementedError()
 
 
-class MoGOutOfScope(NotImplementedError):
-    pass
+MOG_EPS = 1e-12
 
 
 class MoG(DensityEstimator):
-    """Mixture of Gaussians (reference density_estimator.py:58-237) is NOT part of the bijector-chain hot path
-    (no chain, sampling is a host-side scipy loop); the name exists so that the reference's
-    ``de.MoG`` lookups fail with a clear message instead of an AttributeError."""
+    """Mixture of K Gaussians (reference density_estimator.py:57-237): the other density estimator a
+    ``ConditionalDensityEstimator`` accepts.  No bijector chain - it is adjacent to the hot path and is
+    evaluated with torch ops: the parameter map (``_get_MoG_params``, a few values per context) on the device of
+    ``params``; sampling and the densities, which scale with ``M N K D^2``, on the CUDA device.  Parameter row:
+    ``[alpha logits (K) | mu (K D) | upper-triangular factor U (K D(D+1)/2)]`` with ``Sigma^-1 = U^T U`` and
+    ``diag(U) = exp(.)`` (:98-133); with bounds ``mu = m tanh(mu) + c`` and ``diag(U) /= sqrt(m)``.
 
-    def __init__(self, *args, **kwargs):
-        raise MoGOutOfScope("MoG is outside the B200 hot path of torch_nf_b200 (SURVEY.md section 2); "
-                            "use the reference implementation for it")
+    Difference from the reference: ``forward`` draws its samples on the device (component index by inverse-CDF,
+    ``mu_k + chol(Sigma_k + 1e-3 I) eps``) instead of one scipy call per sample (:146-155) - the same distribution,
+    another random stream; ``log_q_z`` is the reference's float64 mixture density of the drawn points (:160, :217-235)."""
+
+    def __init__(self, D, conditioner=False, K=1, lb=None, ub=None):
+        super().__init__(D, conditioner)
+        self.K = K
+        self.alpha_softmax = torch.nn.Softmax(dim=1)
+        self.count_num_params()
+        if not self.conditioner:
+            self._param_init()
+        self.lb = lb
+        self.ub = ub
+
+    @property
+    def K(self):
+        return self._K
+
+    @K.setter
+    def K(self, val):
+        if type(val) is not int:
+            raise TypeError(format_type_err_msg(self, "K", val, int))
+        if val < 1:
+            raise ValueError("MoG K %d must be greater than 0." % val)
+        self._K = val
+
+    def count_num_params(self):
+        self.D_params = self.K * (1 + self.D + self.D * (self.D + 1) // 2)
+
+    def _param_init(self):
+        self.params = torch.nn.init.xavier_normal_(torch.zeros(1, self.D_params, requires_grad=True))
+
+    def _bounds(self, like):
+        if self.lb is None or self.ub is None:
+            return None, None
+        lb, ub = np.asarray(self.lb, dtype=np.float64), np.asarray(self.ub, dtype=np.float64)
+        m = torch.tensor((ub - lb) / 2.0).float().to(like.device)
+        c = torch.tensor((ub + lb) / 2.0).float().to(like.device)
+        return m, c
+
+    def _get_MoG_params(self, params, numpy=False):
+        """alpha (M, K), mu (M, K, D), Sigma_inv (M, K, D, D), Sigma_det (M, K) (:89-140)."""
+        M, K, D = params.shape[0], self.K, self.D
+        T = D * (D + 1) // 2
+        m, c = self._bounds(params)
+        alpha = self.alpha_softmax(params[:, :K])
+        mu = params[:, K:K + K * D].reshape(M, K, D)
+        if m is not None:
+            mu = m * torch.tanh(mu) + c
+        tri = params[:, K + K * D:K + K * D + K * T].reshape(M, K, T)
+        iu = torch.triu_indices(D, D, device=params.device)
+        is_diag = iu[0] == iu[1]
+        log_diag = tri[:, :, is_diag]                                  # (M, K, D): row-major triu order visits (d, d) in order
+        diag = torch.exp(log_diag)
+        if m is not None:
+            diag = diag / torch.sqrt(m)
+        vals = tri.clone()
+        vals[:, :, is_diag] = diag
+        U = torch.zeros((M, K, D, D), dtype=params.dtype, device=params.device)
+        U[:, :, iu[0], iu[1]] = vals
+        Sigma_inv = torch.matmul(U.transpose(3, 2), U)
+        Sigma_det = torch.prod(torch.exp(-2.0 * log_diag) * (m if m is not None else 1.0), dim=2)
+        if numpy:
+            alpha = alpha.detach().cpu().numpy()
+            alpha = alpha / np.sum(alpha, axis=1)[:, None]
+            mu = mu.detach().cpu().numpy()
+            Sigma_inv = Sigma_inv.detach().cpu().numpy()
+        return alpha, mu, Sigma_inv, Sigma_det
+
+    def _mixture_log_density64(self, z, alpha, mu, Sigma_inv):
+        """log(sum_k alpha_k N(z; mu_k, Sigma_k) + EPS) in float64 (the reference's ``log_prob_np``, :217-235)."""
+        z, alpha, mu, P = z.double(), alpha.double(), mu.double(), Sigma_inv.double()
+        alpha = alpha / alpha.sum(dim=1, keepdim=True)
+        d = z[:, :, None, :] - mu[:, None, :, :]                                        # (M, N, K, D)
+        quad = torch.einsum("mnki,mkij,mnkj->mnk", d, P, d)
+        log_norm = 0.5 * torch.logdet(P) - 0.5 * self.D * float(np.log(2.0 * np.pi))     # (M, K)
+        pdf = torch.exp(log_norm[:, None, :] - 0.5 * quad)
+        return torch.log((alpha[:, None, :] * pdf).sum(dim=2) + MOG_EPS)
+
+    def forward(self, params, N=100):
+        """Samples ``z (M, N, D)`` and ``log_q_z (M, N)``, float32, on the device of ``params`` (:142-165)."""
+        home = params.device
+        pd = ops.to_device(params.detach(), torch.float32)
+        M, K, D = pd.shape[0], self.K, self.D
+        alpha, mu, Sigma_inv, _ = self._get_MoG_params(pd)
+        alpha = alpha / alpha.sum(dim=1, keepdim=True)
+        Sigma = torch.inverse(Sigma_inv.double()) + 0.001 * torch.eye(D, dtype=torch.float64, device=pd.device)
+        L = torch.linalg.cholesky(Sigma)                                                # (M, K, D, D)
+        g = torch.Generator(device=pd.device)
+        g.manual_seed(int(np.random.randint(0, 2 ** 31 - 1)))      # numpy's global stream seeds the device stream
+        u = torch.rand((M, N), generator=g, device=pd.device, dtype=torch.float64)
+        comp = torch.searchsorted(torch.cumsum(alpha.double(), dim=1).contiguous(), u).clamp_(max=K - 1)   # (M, N)
+        eps = torch.randn((M, N, D), generator=g, device=pd.device, dtype=torch.float64)
+        rows = torch.arange(M, device=pd.device)[:, None].expand(M, N)
+        z = mu.double()[rows, comp] + torch.einsum("mnij,mnj->mni", L[rows, comp], eps)
+        log_q_z = self._mixture_log_density64(z, alpha, mu, Sigma_inv)
+        return _to(z.float(), home), _to(log_q_z.float(), home)
+
+    def log_prob(self, z, params=None):
+        """log q(z) with the reference's two formulas (K = 1: exact Gaussian log-density; K > 1: log of the summed
+        component densities + EPS, :167-215), float32, on the device of ``z``."""
+        if params is None:
+            params = self.params
+        home = z.device
+        zd = ops.to_device(z, torch.float32)
+        pd = ops.to_device(params, torch.float32)
+        alpha, mu, Sigma_inv, Sigma_det = self._get_MoG_params(pd)
+        d = zd[:, :, None, :] - mu[:, None, :, :]                                       # (M, N, K, D)
+        quad = torch.einsum("mnki,mkij,mnkj->mnk", d, Sigma_inv, d)
+        if self.K == 1:
+            lp = quad[:, :, 0] + torch.log(Sigma_det + MOG_EPS) + self.D * float(np.log(2.0 * np.pi))
+            lp = -0.5 * lp
+        else:
+            denom = torch.sqrt(((2.0 * np.pi) ** self.D) * Sigma_det + MOG_EPS)[:, None, :]
+            prob = torch.sum(alpha[:, None, :] * (torch.exp(-0.5 * quad) / denom), dim=2)
+            lp = torch.log(prob + MOG_EPS)
+        return _to(lp, home)
+
+    def log_prob_np(self, z, params):
+        """numpy in / out variant (:217-235)."""
+        pd = ops.to_device(params.detach(), torch.float32)
+        alpha, mu, Sigma_inv, _ = self._get_MoG_params(pd)
+        zt = ops.to_device(torch.as_tensor(np.asarray(z)), torch.float64)
+        return self._mixture_log_density64(zt, alpha, mu, Sigma_inv).cpu().numpy()
 
 
 class NormFlow(DensityEstimator):
