@@ -186,8 +186,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
   float* sPb = sPs + 2 * DH;                                                                       // pre_shift [D]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr bool is_ctrl = false;                      // no dedicated control warp: thread 0 also issues copies and MMAs
-  const bool ctl = threadIdx.x == 0;
+  const bool ctl = threadIdx.x == 0;                   // no dedicated control warp: thread 0 also issues copies and MMAs
   const int q = warp & 3, cq = (warp >> 2) & 3;        // TMEM lane quadrant, chunk owner
   const int64_t n_tiles = (a.rows + kTileM - 1) / kTileM;
   const int64_t cnt = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -215,7 +214,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   const int r_tile = q * 32 + lane;
 
-  // ---- weight slots (control lane): use u of the small sequence / v of the big sequence
+  // ---- weight slots (thread 0): use u of the small sequence / v of the big sequence
   const int64_t u_total = 8 * cnt, v_total = 4 * NH * cnt;
   auto load_small = [&](int64_t u) {
     const int u8 = (int)(u & 7), net = (u8 >> 1) & 1, slot = (int)(u & 1);
@@ -280,7 +279,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
     }
     tc_commit(&ct.mma_done);
   };
-  // every thread: the job's MMAs are complete; the control lane then refills the slot(s) the job used
+  // every thread: the job's MMAs are complete; thread 0 then refills the slot(s) the job used
   auto wait_job = [&](bool big) {
     mbar_wait(&ct.mma_done, dpar);
     dpar ^= 1u;
@@ -315,9 +314,9 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
   for (int64_t it = 0; it < cnt; ++it) {
     const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
     const int64_t row = tile * kTileM + r_tile;
-    const bool valid = !is_ctrl && row < a.rows;
+    const bool valid = row < a.rows;
     // ---- conditioning half -> bf16 A image, and (with the ones column) -> workspace for the first layer's weight gradient
-    if (!is_ctrl) {
+    {
       constexpr int XW = DH + 1 <= 64 ? 64 : 128;
       __nv_bfloat16* xa = a.ws + sh.ws_xa(a.rows);
       for (int i = threadIdx.x; i < kTileM * XW / 8; i += kEpi * 32) {
@@ -384,7 +383,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
         }
         __syncwarp();
         wait_job(l == 1);
-        if (!is_ctrl) {
+        {
           __nv_bfloat16* hmat = a.ws + sh.ws_mat(net, l, a.rows);
           uint32_t x[NI][32];
 #pragma unroll
@@ -431,7 +430,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
       if (ctl) issue_small(R0, R1, IC<1>{}, IC<U>{}, IC<DH>{});
       __syncwarp();
       wait_job(false);
-      if (!is_ctrl) {
+      {
         uint32_t o[W];
         if (W == 8) tmem_ld8(R0 + lane_addr + (uint32_t)(cq * W), reinterpret_cast<uint32_t(&)[8]>(o));
         else tmem_ld16(R0 + lane_addr + (uint32_t)(cq * W), reinterpret_cast<uint32_t(&)[16]>(o));
@@ -505,7 +504,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
         // behind the long hidden-layer job
         if (l == 0) prefetch_h(net, 0);
         wait_job(l == 0);
-        if (!is_ctrl) {
+        {
           __nv_bfloat16* dmat = a.ws + sh.ws_mat(net, 2 + l, a.rows);
 #pragma unroll
           for (int i = 0; i < NI; ++i) {
@@ -539,7 +538,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) coupling_tcb_kernel(ArgsB a) {
       if (ctl) issue_small(R1, R0, IC<1>{}, IC<U>{}, IC<DH>{});
       __syncwarp();
       wait_job(false);
-      if (!is_ctrl) {
+      {
         uint32_t o[W];
         if (W == 8) tmem_ld8(R1 + lane_addr + (uint32_t)(cq * W), reinterpret_cast<uint32_t(&)[8]>(o));
         else tmem_ld16(R1 + lane_addr + (uint32_t)(cq * W), reinterpret_cast<uint32_t(&)[16]>(o));

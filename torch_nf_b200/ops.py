@@ -291,7 +291,6 @@ def coupling_tc_bwd(z_in, packed_bwd, g_z_out, g_ld, g_params_row, D, U, L, uppe
     g_z = torch.empty_like(z2)
     DH = D // 2
     UP = U + 16
-    c_off = 0 if upper else DH
     gp = g_params_row.reshape(-1)
     # offsets of the layer's pieces in the flat row: per layer [W_t | W_s | b_t | b_s]
     o0, o1 = 0, 2 * DH * U + 2 * U
