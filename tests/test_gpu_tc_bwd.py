@@ -163,3 +163,35 @@ def test_tc_backward_full_size_against_cuda_cores():
     gp2 = torch.zeros_like(params)
     gz2 = ops.coupling_tc_bwd(z, ops.tc_bwd_pack(params[0], D, U, L, True), 2 * gz, 2 * gl, gp2[0], D, U, L, True, TNF_INVERSE)
     assert _rel(gz2, 2 * gz_tc) < 1e-6 and _rel(gp2, 2 * gp_tc) < 2e-3
+
+
+def test_mixed_precision_training_fp32_forward_bf16_backward():
+    """config.set_training_backward("bf16") in the default fp32 mode: the forward keeps fp32 parity (tensor cores, split
+    operands), the gradients come from the bf16 tensor-core backward: loss at the fp32 tolerance, gradients at the bf16 one."""
+    D, stages, U, N = 64, 2, 256, 148 * 128 + 19
+    assert config.conditioner_precision() == "fp32" and not config.tc_backward_enabled()
+    config.set_training_backward("bf16")
+    try:
+        assert config.tc_backward_enabled()
+        nf = de.NormFlow(D, False, "coupling", stages, 2, U)
+        chain = O.build_chain(D, "coupling", stages, 2, U)
+        params0 = torch.tensor(synthetic_params(chain_spec(nf.bijectors), D, 1, seed=6))
+        with torch.no_grad():
+            z, _ = nf.forward(params0, N, omega=np.random.RandomState(2).standard_normal((1, N, D)))
+        st = [(b.get_last_mean().float().cpu(), b.get_last_alpha().float().cpu()) if b.name == "BatchNorm" else None
+              for b in nf.bijectors]
+        z = (z.detach() * 1.25 + 0.1).contiguous()
+        p1 = params0.clone().requires_grad_(True)
+        nf.params = p1
+        loss = -nf.log_prob(z).mean()
+        loss.backward()
+        p2 = params0.clone().requires_grad_(True)
+        loss_o = -O.normflow_log_prob(chain, D, z, p2, st).mean()
+        loss_o.backward()
+        rp = _rel(p1.grad, p2.grad)
+        print("mixed precision: loss %.6f vs %.6f, rel-L2 g_params %.2e" % (loss.item(), loss_o.item(), rp))
+        assert abs(loss.item() - loss_o.item()) < config.FP32_TOL_LOGP * max(1.0, abs(loss_o.item()))
+        assert rp < GRAD_TOL, rp
+    finally:
+        config.set_training_backward("auto")
+    assert not config.tc_backward_enabled()

@@ -12,7 +12,7 @@ All arithmetic runs in hand-written sm_100a CUDA kernels reached through the
 C ABI in ``include/tnf.h`` (``torch_nf_b200/_C.so``).  There is no CPU path.
 """
 from . import config  # noqa: F401
-from .config import set_conditioner_precision, conditioner_precision  # noqa: F401
+from .config import set_conditioner_precision, conditioner_precision, set_training_backward  # noqa: F401
 
 __all__ = ["bijectors", "density_estimator", "conditional_density_estimator", "error_formatters", "config",
-           "dist", "set_conditioner_precision", "conditioner_precision"]
+           "dist", "set_conditioner_precision", "conditioner_precision", "set_training_backward"]

@@ -68,11 +68,12 @@ class Bijector(object):
 
 # ------------------------------------------------------------------ RealNVP
 def _tc_differentiable(z, params, D, U, L):
-    """bf16-conditioner mode, shared weights, a compiled shape: the layer AND its backward run on tensor cores
-    (tnf_coupling_tc / tnf_coupling_tc_bwd); otherwise the exact CUDA-core kernels."""
-    return (config.conditioner_precision() == "bf16" and params.shape[0] == 1 and z.dtype == torch.float32
+    """Shared weights, a compiled shape and the tensor-core backward enabled (config.tc_backward_enabled: the bf16 mode, or
+    set_training_backward("bf16")): the layer AND its backward run on tensor cores (tnf_coupling_tc /
+    tnf_coupling_tc_bwd); otherwise the exact CUDA-core kernels."""
+    return (config.tc_backward_enabled() and params.shape[0] == 1 and z.dtype == torch.float32
             and params.dtype == torch.float32 and z.shape[0] * z.shape[1] >= config.tc_min_rows()
-            and ops.tc_bwd_supported(D, U, L) and ops.tc_supported(D, U, L, "bf16"))
+            and ops.tc_bwd_supported(D, U, L) and ops.tc_supported(D, U, L, config.tc_precision()))
 
 
 class _CouplingFn(torch.autograd.Function):
@@ -82,8 +83,9 @@ class _CouplingFn(torch.autograd.Function):
         ctx.tc = (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and _tc_differentiable(z, params, D, U, L)
         if ctx.tc:
             zc = z.contiguous()
-            z_out, ld = ops.coupling_tc(zc, ops.tc_pack(params[0], D, U, L, upper, precision="bf16"), D, U, L, upper,
-                                        direction, precision="bf16")
+            mode = config.tc_precision()
+            z_out, ld = ops.coupling_tc(zc, ops.tc_pack(params[0], D, U, L, upper, precision=mode), D, U, L, upper,
+                                        direction, precision=mode)
             ld = ld.view(z.shape[0], z.shape[1])
         else:
             z_out, ld = ops.coupling(z, params, D, U, L, upper, direction)

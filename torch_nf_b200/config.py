@@ -63,6 +63,35 @@ def tc_min_rows():
     return _tc_min_rows
 
 
+_training_backward = os.environ.get("TNF_TRAINING_BACKWARD", "auto")
+
+
+def set_training_backward(mode):
+    """Backward of shared-weight coupling layers on the differentiable path.
+    ``"auto"`` (default): the tensor-core backward (tnf_coupling_tc_bwd, bf16 conditioner, gradients within rel-L2 1e-2)
+    in the ``"bf16"`` conditioner mode, the exact CUDA-core backward (~100x slower at C3) in the fp32 modes.
+    ``"bf16"``: the tensor-core backward in EVERY tensor-core mode - with ``"fp32"`` the forward values keep fp32 parity
+    (fp16 hi / lo split on tcgen05) while the gradients carry the bf16 tolerance: mixed-precision training.
+    ``"exact"``: the CUDA-core backward everywhere."""
+    global _training_backward
+    if mode not in ("auto", "bf16", "exact"):
+        raise ValueError('training backward must be "auto", "bf16" or "exact"')
+    _training_backward = mode
+
+
+def training_backward():
+    return _training_backward
+
+
+def tc_backward_enabled():
+    """The tensor-core backward is in use for the current settings."""
+    if _training_backward == "exact":
+        return False
+    if _training_backward == "bf16":
+        return tc_precision() is not None
+    return _precision == "bf16"
+
+
 _host_pipeline_min_rows = int(os.environ.get("TNF_HOST_PIPELINE_MIN_ROWS", str(1 << 17)))
 _host_pipeline_chunks = int(os.environ.get("TNF_HOST_PIPELINE_CHUNKS", "4"))   # measured at 2^20 x 64: 2: 16.5, 3: 16.0, 4: 15.8, 8: 16.2, 16: 18.7 ms per e2e step
 

@@ -376,12 +376,13 @@ class NormFlow(DensityEstimator):
 
     def _tc_train(self, b, pd, z):
         """The differentiable path of a coupling layer runs on tensor cores (forward ``tnf_coupling_tc``, backward
-        ``tnf_coupling_tc_bwd``) in the bf16-conditioner mode when the weights are shared and the shape is compiled;
-        in the fp32 modes training stays on the exact CUDA-core kernels."""
-        return (config.conditioner_precision() == "bf16" and pd.shape[0] == 1 and z.dtype == torch.float32
+        ``tnf_coupling_tc_bwd``) when the weights are shared and the shape is compiled: in the bf16-conditioner mode, or
+        in any tensor-core mode after ``config.set_training_backward("bf16")`` (fp32-parity forward, bf16 gradients);
+        otherwise training stays on the exact CUDA-core kernels."""
+        return (config.tc_backward_enabled() and pd.shape[0] == 1 and z.dtype == torch.float32
                 and z.shape[0] * z.shape[1] >= config.tc_min_rows()
                 and ops.tc_bwd_supported(b.D, b.num_units, b.num_layers)
-                and ops.tc_supported(b.D, b.num_units, b.num_layers, "bf16"))
+                and ops.tc_supported(b.D, b.num_units, b.num_layers, config.tc_precision()))
 
     def _packed(self, b, idx, n, pd, src=None):
         """Packed tensor-core operand images of bijector ``b``'s weights (``pd[0, idx:idx+n]``).
@@ -810,18 +811,20 @@ class _ChainLogProbFn(torch.autograd.Function):
         order = list(reversed(nf._slices()))             # execution order of the inverse chain
         pre = None                                       # (alpha, mean) of a BatchNorm folded into the NEXT coupling layer
         folded = {}                                      # position in `order` of a coupling layer -> its folded pre-affine
+        tc_pos = set()                                   # positions whose coupling layer ran (and will be differentiated) on tensor cores
         for k, (b, idx, n) in enumerate(order):
             ins.append(cur)
             if b.name == "RealNVP" and nf._tc_train(b, pdd, cur):
                 # bf16-conditioner mode, shared weights: forward AND backward of the layer on tensor cores; a BatchNorm
                 # right before it is applied on load (z alpha + mean with its remembered statistics: constants)
                 ps, pb = pre if pre is not None else (None, None)
+                tc_pos.add(k)
                 if pre is not None:
                     folded[k] = pre
                     pre = None
                 cur, _ = ops.coupling_tc(cur, nf._packed(b, idx, n, pdd, src=pd), b.D, b.num_units, b.num_layers,
                                          b.transform_upper, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD, pre_scale=ps,
-                                         pre_shift=pb, precision="bf16")
+                                         pre_shift=pb, precision=config.tc_precision())
             elif b.name == "RealNVP":
                 cur, _ = ops.coupling(cur, pdd[:, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper, TNF_INVERSE,
                                       ld=ld_acc, accum=TNF_LD_ADD)
@@ -840,7 +843,7 @@ class _ChainLogProbFn(torch.autograd.Function):
             else:   # ToInterval
                 cur, _ = ops.tointerval(cur, b._consts(z.device), D, TNF_INVERSE, ld=ld_acc, accum=TNF_LD_ADD)
         lp = ops.base_logprob(cur, ld_acc, scal, N if pd.shape[0] == M and M > 1 else M * N)
-        ctx.nf, ctx.ins, ctx.z0, ctx.folded = nf, ins, cur, folded
+        ctx.nf, ctx.ins, ctx.z0, ctx.folded, ctx.tc_pos = nf, ins, cur, folded, tc_pos
         ctx.save_for_backward(pd)
         ctx.need = (z.requires_grad, pd.requires_grad)
         return lp
@@ -867,7 +870,7 @@ class _ChainLogProbFn(torch.autograd.Function):
         for k, (b, idx, n) in enumerate(slices):
             pos = len(slices) - 1 - k                    # this bijector's position in the forward's execution order
             z_in = ins[pos]
-            if b.name == "RealNVP" and nf._tc_train(b, pdd, z_in):
+            if b.name == "RealNVP" and pos in ctx.tc_pos:      # as decided in the forward
                 packed_b = ops.tc_bwd_pack(pdd[0, idx:idx + n], b.D, b.num_units, b.num_layers, b.transform_upper)
                 ps, pb = folded.get(pos, (None, None))
                 g_z = ops.coupling_tc_bwd(z_in, packed_b, g_z, g_ld, g_params[0, idx:idx + n], b.D, b.num_units,
