@@ -247,3 +247,22 @@ def test_no_cpu_fallback():
                     (BatchNorm(4), (torch.zeros(1, 2, 4),)), (ToSimplex(4), (torch.zeros(1, 2, 3),))):
         with raises(RuntimeError, match="no CPU fallback"):
             b(*args)
+
+
+def test_training_backward_switch():
+    """config.set_training_backward: validation and the mode table (no GPU needed)."""
+    from torch_nf_b200 import config
+    old_p, old_b = config.conditioner_precision(), config.training_backward()
+    try:
+        with pytest.raises(ValueError):
+            config.set_training_backward("fp16")
+        table = {("fp32", "auto"): False, ("bf16", "auto"): True, ("fp32_cc", "auto"): False,
+                 ("fp32", "bf16"): True, ("bf16", "bf16"): True, ("fp32_cc", "bf16"): False,
+                 ("fp32", "exact"): False, ("bf16", "exact"): False}
+        for (prec, bwd), want in table.items():
+            config.set_conditioner_precision(prec)
+            config.set_training_backward(bwd)
+            assert config.tc_backward_enabled() is want, (prec, bwd)
+    finally:
+        config.set_conditioner_precision(old_p)
+        config.set_training_backward(old_b)
