@@ -15,6 +15,42 @@ from . import density_estimator as de
 from .error_formatters import format_type_err_msg
 
 
+class _WideLinearFn(torch.autograd.Function):
+    """``h @ W^T + b`` of the hyper-network's LAST Linear (H -> D_params, the (M, D_params) parameter matrix of regime B)
+    as ONE GEMM in the forward: the bias rides as a column of ``W`` against a ones column of ``h``.  torch's
+    ``F.linear`` adds the bias in a separate epilogue pass over the M x D_params output and reduces the bias gradient in
+    another one (at C4: 2.0 + 0.4 ms of a 10.3 ms training step, profiles/r02_lines/r02n_train_breakdown_final.txt).  The
+    augmented width is padded to a multiple of 8."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias):
+        M, H = h.shape
+        Hp = (H + 1 + 7) // 8 * 8
+        h_aug = h.new_zeros((M, Hp))
+        h_aug[:, :H] = h
+        h_aug[:, H] = 1.0
+        w_aug = weight.new_zeros((weight.shape[0], Hp))
+        w_aug[:, :H] = weight
+        w_aug[:, H] = bias
+        ctx.save_for_backward(h_aug, weight)
+        ctx.H = H
+        return torch.mm(h_aug, w_aug.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        h_aug, weight = ctx.saved_tensors
+        H = ctx.H
+        g = g.contiguous()
+        g_h = torch.mm(g, weight) if ctx.needs_input_grad[0] else None
+        # measured at C4 (profiles/r02_lines/r02zk_*): the 72-column product g^T (h | 1) picks a kernel 1.9x slower than
+        # the 64-column one, so the bias gradient is a column sum here; the forward keeps the augmented GEMM (no epilogue pass)
+        g_w = torch.mm(g.t(), h_aug[:, :H])
+        return g_h, g_w, g.sum(dim=0)
+
+
+WIDE_LINEAR_MIN_ROWS = 4096
+
+
 class ConditionalDensityEstimator(torch.nn.Module):
     def __init__(self, density_estimator, D_x, hidden_layers, dropout=False):
         super().__init__()
@@ -85,8 +121,17 @@ class ConditionalDensityEstimator(torch.nn.Module):
                 raise ValueError("Hidden unit counts must be positive.")
         self._hidden_layers = val
 
+    def _params(self, x):
+        """``param_net(x)`` (reference :94,:102).  With many contexts on the GPU the last Linear runs as one GEMM per
+        direction (``_WideLinearFn``); the modules and their ``state_dict`` are untouched."""
+        last = self.param_net[-1]
+        if (x.is_cuda and x.dim() == 2 and x.shape[0] >= WIDE_LINEAR_MIN_ROWS and x.dtype == torch.float32
+                and isinstance(last, torch.nn.Linear) and last.bias is not None and len(self.param_net) >= 2):
+            return _WideLinearFn.apply(self.param_net[:-1](x), last.weight, last.bias)
+        return self.param_net(x)
+
     def __call__(self, x, N=100, freeze_bn=False):
-        params = self.param_net(x)
+        params = self._params(x)
         if type(self.density_estimator) is de.NormFlow:       # only the flow has BatchNorm state to freeze (:95-98)
             return self.density_estimator(N=N, params=params, freeze_bn=freeze_bn)
         return self.density_estimator(N=N, params=params)
@@ -95,7 +140,7 @@ class ConditionalDensityEstimator(torch.nn.Module):
         lp = self._log_prob_fused(z, x)
         if lp is not None:
             return lp
-        params = self.param_net(x)
+        params = self._params(x)
         return self.density_estimator.log_prob(z, params)
 
     # ---- hyper-network fusion: the last Linear is evaluated inside the flow kernel ------------------
