@@ -440,6 +440,8 @@ def main():
                 train_step_fn()
             torch.cuda.synchronize()
             t_steps = 3
+            bt = []
+            ops.bwd_kernel_timer = bt
             l0 = _lib.launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -447,13 +449,24 @@ def main():
                 train_step_fn()
             e1.record()
             torch.cuda.synchronize()
+            ops.bwd_kernel_timer = None
             ms_t = e0.elapsed_time(e1) / t_steps
+            k_ms = [a.elapsed_time(b) for (a, b, _r) in bt]
+            k_rows = sum(r for (_a, _b, r) in bt)
+            pk = peaks()
+            k_tflops = 2 * FLOP_PER_SAMPLE_LAYER * k_rows / (sum(k_ms) * 1e-3) / 1e12 if k_ms else None
             t_losses = [float(v) for v in t_losses]
             train_c3 = {"metric": "maximum-likelihood training step (-mean log_prob: forward + backward of %d coupling layers on tensor cores, "
                                   "BatchNorm / Affine backward, Adam)" % N_LAYERS,
                         "value": B / (ms_t * 1e-3), "unit": "samples/s", "ms_per_step": ms_t, "steps": t_steps, "rows": B,
                         "gpu_launches_per_step": int(_lib.launch_count() - l0) // t_steps,
                         "tflops_algorithmic": N_LAYERS * 4 * FLOP_PER_SAMPLE_LAYER * B / (ms_t * 1e-3) / 1e12,
+                        "roofline": {"bound": "tensor", "kernel": "coupling_tcb_kernel", "launches_timed": len(k_ms),
+                                     "avg_launch_ms": (sum(k_ms) / len(k_ms)) if k_ms else None,
+                                     "achieved": k_tflops, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                                     "frac": (k_tflops / pk["tflops_burst"]) if k_tflops else None,
+                                     "algorithmic_flop_per_launch": "2 x %d x rows (conditioner recompute + data gradient; the weight gradient runs in library GEMMs)" % FLOP_PER_SAMPLE_LAYER,
+                                     "kernel_share_of_step": (sum(k_ms) / t_steps / ms_t) if k_ms else None},
                         "loss_first": t_losses[0], "loss_last": t_losses[-1], "finite": bool(np.isfinite(t_losses).all())}
             del z_data, p_train, opt
         except Exception as exc:       # the extra object must never cost the headline line

@@ -55,6 +55,7 @@ def to_like(t, device):
 # bench.py hook: when set to a list, (start, end) CUDA events are recorded around
 # every tensor-core coupling launch on the launching stream.
 kernel_timer = None
+bwd_kernel_timer = None     # the same for the launches of the tensor-core backward kernel (tnf_coupling_tc_bwd)
 
 
 def _stream():
@@ -301,11 +302,18 @@ def coupling_tc_bwd(z_in, packed_bwd, g_z_out, g_ld, g_params_row, D, U, L, uppe
         rows = hi - lo
         nbytes = _lib.lib().tnf_tc_bwd_workspace_bytes(rows, D, U, L)
         ws = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=z2.device)
+        btimer = bwd_kernel_timer
+        if btimer is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = _lib.lib().tnf_coupling_tc_bwd(z2[lo:hi].data_ptr(), packed_bwd.data_ptr(),
                                             0 if gz2 is None else gz2[lo:hi].data_ptr(),
                                             0 if gl is None else gl[lo:hi].data_ptr(), g_z[lo:hi].data_ptr(),
                                             ws.data_ptr(), rows, D, U, L, int(upper), direction, _ptr(pre_scale),
                                             _ptr(pre_shift), _stream())
+        if btimer is not None:
+            e1.record()
+            btimer.append((e0, e1, rows))
         _lib.check(rc, "tnf_coupling_tc_bwd")
         mats = ws[:8 * rows * UP].view(2, 4, rows, UP)       # [net][h1, h2, d1, d2]
         d3 = ws[8 * rows * UP: 8 * rows * UP + 2 * rows * DH].view(2, rows, DH)
